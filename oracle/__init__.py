@@ -1,0 +1,34 @@
+"""CPU oracle for the MFCC -> diag-GMM-UBM hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``speech_signal_processing_b200/``
+imports this package.  The only allowed importers are ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs, and there only as the checker / CPU baseline.
+
+What is restated, and how each piece is pinned
+----------------------------------------------
+* ``oracle.frontend.processing_mfcc``  restates /root/reference/utils/processing.py:19-144
+  (enframe, mfccInitFilterBanks, stMFCC, MFCC).  PINNED: the reference file is
+  imported unchanged (with import shims) by ``tests/golden/make_golden.py`` and
+  its outputs are committed under ``tests/golden/``; ``tests/test_oracle.py``
+  checks the restatement against them.
+* ``oracle.frontend.delta`` restates /root/reference/GMM_UBM.py:53-69.  PINNED the
+  same way (reference ``delta`` imported and run).
+* ``oracle.frontend.scale`` restates sklearn.preprocessing.scale as called at
+  /root/reference/GMM_UBM.py:93.  PINNED against sklearn 1.9.0 outputs.
+* ``oracle.gmm`` restates sklearn.mixture.GaussianMixture (diag) E-step, M-step,
+  score and the EM loop as called at /root/reference/GMM_UBM.py:158-170,185,194.
+  PINNED against sklearn 1.9.0 (golden fixtures + live comparison in the tests).
+* ``oracle.frontend.sidekit_mfcc`` restates SIDEKIT 1.3.x ``frontend/features.py``
+  ``mfcc`` (the function /root/reference/GMM_UBM.py:20,89 binds).  SIDEKIT is an
+  un-vendored, un-pinned dependency (requirements.txt:5) that is absent from
+  this container: **parity unpinned** except for the reference's own witnesses
+  (98x13 cepstra for 1 s @ 16 kHz, report/final.pdf p.5; ``[0]`` is the cepstra,
+  UI/GMM_UBM_GUI.py:91).
+* ``oracle.frontend.psf_mfcc`` restates python_speech_features 0.6 ``mfcc``
+  (imported, never called, at /root/reference/GMM_UBM.py:13; BASELINE config 1
+  quotes its 26-filter default).  Absent here: **parity unpinned**.
+* ``oracle.gmm.map_adapt`` is Reynolds/Quatieri/Dunn (2000) mean-only (and full)
+  relevance MAP.  The reference has NO MAP code: **parity unpinned**,
+  defined by formula.
+"""

@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference and sklearn 1.9.0):
+
+    python tests/golden/make_golden.py
+
+Writes small ``.npz`` files next to this script.  The reference modules are imported
+through ``oracle.ref_shims`` (stub modules for the absent GUI/audio packages).
+
+Fixtures
+--------
+processing_mfcc.npz   utils/processing.py::MFCC / enframe / mfccInitFilterBanks outputs
+delta.npz             GMM_UBM.py::delta outputs
+sklearn_gmm.npz       sklearn GaussianMixture(diag) score_samples / predict_proba / fit
+                      trajectory from fixed initial parameters, preprocessing.scale
+pipeline.npz          GMM_UBM.py::extract_feature + GMM() end to end on synthetic audio with
+                      the sidekit restatement plugged in as ``mfcc`` and a seeded
+                      GaussianMixture (random_state only; everything else stock)
+"""
+from __future__ import annotations
+
+import contextlib
+import functools
+import io
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import frontend as ofe  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+from speech_signal_processing_b200 import synth  # noqa: E402
+
+
+def gen_processing():
+    proc = ref_shims.load("utils.processing")
+    out = {}
+    cases = [("a", 8000, 512, 256, 4000), ("b", 16000, 512, 160, 4800), ("c", 16000, 400, 160, 4000),
+             ("d", 8000, 256, 128, 1500)]
+    for tag, fs, fsz, step, n in cases:
+        sig = synth.synth_utterance(3, ord(tag), n, fs)
+        out[f"{tag}_sig"] = sig
+        out[f"{tag}_cfg"] = np.array([fs, fsz, step])
+        out[f"{tag}_mfcc"] = proc.MFCC(sig, fs, fsz, step)
+    fb, fr = proc.mfccInitFilterBanks(16000, 512)
+    out["fbank_16k_512"] = fb
+    out["freqs_16k_512"] = fr
+    fb, fr = proc.mfccInitFilterBanks(8000, 512)
+    out["fbank_8k_512"] = fb
+    out["enframe_a"] = proc.enframe(out["a_sig"].astype(np.float64), 400, 160)
+    np.savez_compressed(os.path.join(HERE, "processing_mfcc.npz"), **out)
+
+
+def gen_delta(gu):
+    rs = np.random.RandomState(7)
+    out = {}
+    for i, (t, f, n) in enumerate([(1, 13, 2), (2, 13, 2), (3, 5, 2), (4, 13, 2), (5, 13, 2), (37, 13, 2), (50, 13, 1), (50, 13, 3),
+                                   (298, 13, 2)]):
+        x = rs.standard_normal((t, f))
+        out[f"x{i}"] = x
+        out[f"n{i}"] = np.array(n)
+        out[f"d{i}"] = gu.delta(x, n)
+    ramp = np.arange(20, dtype=np.float64)[:, None] * np.array([[1.0, -2.0]])
+    out["ramp"] = ramp
+    out["ramp_d"] = gu.delta(ramp, 2)
+    np.savez_compressed(os.path.join(HERE, "delta.npz"), **out)
+
+
+def gen_sklearn():
+    from sklearn import preprocessing
+    from sklearn.mixture import GaussianMixture
+
+    out = {}
+    for tag, k, d, n in [("s", 8, 5, 400), ("m", 64, 26, 1000), ("l", 128, 39, 600)]:
+        w, mu, var = synth.synth_ubm(k, d, seed=11 + k)
+        x = synth.sample_gmm(w, mu * 0.9, var * 1.3, n, seed=k).astype(np.float64)
+        import warnings
+
+        gm = GaussianMixture(n_components=k, covariance_type="diag")
+        # load fixed parameters the way an unpickled model carries them (GMM_UBM.py:141-146)
+        gm.weights_, gm.means_, gm.covariances_ = w, mu, var
+        gm.precisions_cholesky_ = 1.0 / np.sqrt(var)
+        out[f"{tag}_w"], out[f"{tag}_mu"], out[f"{tag}_var"], out[f"{tag}_x"] = w, mu, var, x
+        out[f"{tag}_score_samples"] = gm.score_samples(x)
+        out[f"{tag}_score"] = np.array(gm.score(x))
+        if k <= 64:
+            out[f"{tag}_proba"] = gm.predict_proba(x)
+        # EM trajectory from fixed init, stock tolerances
+        for iters in (1, 3, 100):
+            g2 = GaussianMixture(n_components=k, covariance_type="diag", weights_init=w, means_init=mu,
+                                 precisions_init=1.0 / var, max_iter=iters)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                g2.fit(x)
+            out[f"{tag}_fit{iters}_w"] = g2.weights_
+            out[f"{tag}_fit{iters}_mu"] = g2.means_
+            out[f"{tag}_fit{iters}_var"] = g2.covariances_
+            out[f"{tag}_fit{iters}_niter"] = np.array(g2.n_iter_)
+            out[f"{tag}_fit{iters}_lb"] = np.array(g2.lower_bound_)
+            out[f"{tag}_fit{iters}_conv"] = np.array(g2.converged_)
+    rs = np.random.RandomState(3)
+    xs = rs.standard_normal((57, 26)) * rs.uniform(0.1, 30, size=(1, 26)) + rs.uniform(-50, 50, size=(1, 26))
+    xs[:, 3] = 4.25  # constant column -> std 0 -> divisor 1
+    out["scale_x"] = xs
+    out["scale_y"] = preprocessing.scale(xs)
+    out["scale_y32"] = preprocessing.scale(xs.astype(np.float32))
+    np.savez_compressed(os.path.join(HERE, "sklearn_gmm.npz"), **out)
+
+
+def gen_pipeline():
+    """Reference extract_feature + GMM() on 4 synthetic speakers x 6 utterances of 1 s."""
+    from sklearn.mixture import GaussianMixture
+
+    def mfcc_cepstra(sig, **kw):  # GMM_UBM.py:89 omits the [0]; contract = cepstra ndarray
+        return ofe.sidekit_mfcc(sig, **kw)[0]
+
+    gu = ref_shims.load("GMM_UBM", sidekit_mfcc=mfcc_cepstra)
+    gu.mfcc = mfcc_cepstra
+    gen_delta(gu)
+
+    n_spk, n_utt, n_samp, k = 4, 8, 16000, 4
+    x, y = synth.synth_corpus(n_spk, n_utt, n_samp)
+    from sklearn.model_selection import train_test_split
+
+    x_tr, x_te, y_tr, y_te = train_test_split(x, y, test_size=0.3, random_state=0)  # GMM_UBM.py:125
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+        train, f_tr, y_tr2 = gu.extract_feature(x=x_tr, y=y_tr, is_train=True)
+        f_te, y_te2 = gu.extract_feature(x=x_te, y=y_te)
+    gu.label_encoder.clear()
+    gu.label_encoder.update({f"spk{i}": i for i in range(n_spk)})
+    gu.GaussianMixture = functools.partial(GaussianMixture, random_state=0)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+                gu.GMM(train, f_tr, y_tr2, f_te, y_te2, n_components=k, model=False)
+            with open("Model/GMM_MFCC_model.pkl", "rb") as f:
+                gmms = pickle.load(f)
+            with open("Model/UBM_MFCC_model.pkl", "rb") as f:
+                ubm = pickle.load(f)
+        finally:
+            os.chdir(cwd)
+    line = [ln for ln in buf.getvalue().splitlines() if "train acc" in ln][-1]
+    pred = np.zeros((len(f_te), len(gmms)))
+    for i in range(len(gmms)):
+        for j in range(len(f_te)):
+            pred[j, i] = gmms[i].score(f_te[j]) - ubm.score(f_te[j])  # GMM_UBM.py:194
+    out = {
+        "x_test": np.stack(x_te), "y_test": np.array(y_te2), "x_train": np.stack(x_tr), "y_train": np.array(y_tr2),
+        "feat_test": np.stack(f_te).astype(np.float64), "feat_train0": np.asarray(f_tr[0], dtype=np.float64),
+        "gmm_w": np.stack([g.weights_ for g in gmms]), "gmm_mu": np.stack([g.means_ for g in gmms]),
+        "gmm_var": np.stack([g.covariances_ for g in gmms]),
+        "ubm_w": ubm.weights_, "ubm_mu": ubm.means_, "ubm_var": ubm.covariances_,
+        "pred": pred, "printed": np.array(line),
+    }
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
+    print("reference GMM() printed:", line)
+
+
+if __name__ == "__main__":
+    if not ref_shims.available():
+        sys.exit("reference tree not found; fixtures can only be generated in the build container")
+    gen_processing()
+    gen_sklearn()
+    gen_pipeline()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -1,0 +1,144 @@
+"""The oracle restatements against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py) and against sklearn 1.9.0 live.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import frontend as ofe
+from oracle import gmm as ogmm
+
+
+def test_processing_mfcc_matches_reference(golden):
+    g = golden("processing_mfcc.npz")
+    for tag in "abcd":
+        fs, fsz, step = (int(v) for v in g[f"{tag}_cfg"])
+        got = ofe.processing_mfcc(g[f"{tag}_sig"], fs, fsz, step)
+        ref = g[f"{tag}_mfcc"]
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+
+
+def test_processing_fbank_and_enframe(golden):
+    g = golden("processing_mfcc.npz")
+    fb, fr = ofe.processing_fbank(16000, 512)
+    np.testing.assert_allclose(fb, g["fbank_16k_512"], atol=1e-14)
+    np.testing.assert_allclose(fr, g["freqs_16k_512"], atol=1e-9)
+    np.testing.assert_allclose(ofe.processing_fbank(8000, 512)[0], g["fbank_8k_512"], atol=1e-14)
+    np.testing.assert_allclose(ofe.processing_enframe(g["a_sig"], 400, 160), g["enframe_a"], atol=1e-9)
+
+
+def test_delta_matches_reference(golden):
+    g = golden("delta.npz")
+    i = 0
+    while f"x{i}" in g.files:
+        got = ofe.delta(g[f"x{i}"], int(g[f"n{i}"]))
+        np.testing.assert_allclose(got, g[f"d{i}"], atol=1e-13)
+        i += 1
+    assert i >= 8
+    # known answer: interior of a ramp has delta == slope
+    d = ofe.delta(g["ramp"], 2)
+    np.testing.assert_allclose(d, g["ramp_d"], atol=1e-13)
+    np.testing.assert_allclose(d[2:-2], np.tile([[1.0, -2.0]], (16, 1)), atol=1e-13)
+    with pytest.raises(ValueError):
+        ofe.delta(g["ramp"], 0)
+
+
+def test_scale_matches_sklearn(golden):
+    g = golden("sklearn_gmm.npz")
+    np.testing.assert_allclose(ofe.scale(g["scale_x"]), g["scale_y"], atol=1e-10)
+    y = ofe.scale(g["scale_x"])
+    np.testing.assert_allclose(y.mean(axis=0), 0, atol=1e-10)
+    keep = np.arange(26) != 3
+    np.testing.assert_allclose(y.std(axis=0)[keep], 1, atol=1e-10)
+    np.testing.assert_allclose(y[:, 3], 0, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["s", "m", "l"])
+def test_gmm_score_matches_sklearn(golden, tag):
+    g = golden("sklearn_gmm.npz")
+    w, mu, var, x = g[f"{tag}_w"], g[f"{tag}_mu"], g[f"{tag}_var"], g[f"{tag}_x"]
+    np.testing.assert_allclose(ogmm.score_samples(x, w, mu, var), g[f"{tag}_score_samples"], rtol=1e-12, atol=1e-10)
+    assert abs(ogmm.score(x, w, mu, var) - float(g[f"{tag}_score"])) < 1e-10
+    if f"{tag}_proba" in g.files:
+        np.testing.assert_allclose(ogmm.responsibilities(x, w, mu, var)[1], g[f"{tag}_proba"], atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["s", "m"])
+@pytest.mark.parametrize("iters", [1, 3, 100])
+def test_em_trajectory_matches_sklearn(golden, tag, iters):
+    g = golden("sklearn_gmm.npz")
+    w, mu, var, x = g[f"{tag}_w"], g[f"{tag}_mu"], g[f"{tag}_var"], g[f"{tag}_x"]
+    w2, mu2, var2, n_iter, conv, bounds = ogmm.em_fit(x, w, mu, var, max_iter=iters)
+    assert n_iter == int(g[f"{tag}_fit{iters}_niter"])
+    assert conv == bool(g[f"{tag}_fit{iters}_conv"])
+    np.testing.assert_allclose(w2, g[f"{tag}_fit{iters}_w"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(mu2, g[f"{tag}_fit{iters}_mu"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var2, g[f"{tag}_fit{iters}_var"], rtol=1e-7, atol=1e-9)
+    assert abs(bounds[-1] - float(g[f"{tag}_fit{iters}_lb"])) < 1e-9
+
+
+def test_identify_matches_reference_pipeline(golden):
+    """GMM_UBM.py:191-197 pred matrix recomputed by the oracle from the reference-trained models."""
+    g = golden("pipeline.npz")
+    models = [(g["gmm_w"][i], g["gmm_mu"][i], g["gmm_var"][i]) for i in range(g["gmm_w"].shape[0])]
+    ubm = (g["ubm_w"], g["ubm_mu"], g["ubm_var"])
+    pred, arg = ogmm.identify(list(g["feat_test"]), models, ubm)
+    np.testing.assert_allclose(pred, g["pred"], rtol=1e-10, atol=1e-9)
+    acc = (arg == g["y_test"]).mean()
+    assert f"test acc {acc:.2%}" in str(g["printed"])
+
+
+def test_features_recipe_matches_reference_extract_feature(golden):
+    """oracle.features == GMM_UBM.extract_feature (with the sidekit restatement as mfcc)."""
+    g = golden("pipeline.npz")
+    for j in range(3):
+        got = ofe.features(g["x_test"][j], preset="sidekit", delta_order=1, cmvn=True)
+        np.testing.assert_allclose(got, g["feat_test"][j], atol=1e-9)
+
+
+def test_sidekit_shape_witness():
+    """report/final.pdf p.5, d_vector.py:81-91: 1 s @ 16 kHz -> 98 x 13 cepstra."""
+    from speech_signal_processing_b200 import synth
+
+    out = ofe.sidekit_mfcc(synth.synth_utterance(1, 1, 16000))
+    assert out[0].shape == (98, 13) and out[1].shape == (98,) and out[2] is None and out[3] is None
+    assert ofe.sidekit_mfcc(synth.synth_utterance(1, 1, 48000))[0].shape == (298, 13)
+
+
+def test_psf_known_answers():
+    from speech_signal_processing_b200 import synth
+
+    sig = synth.synth_utterance(2, 0, 48000)
+    c = ofe.psf_mfcc(sig)
+    assert c.shape == (299, 13)  # 1 + ceil((48000-400)/160)
+    fb = ofe.psf_filterbanks()
+    assert fb.shape == (26, 257) and np.isclose(fb.max(), 1.0)
+
+
+def test_dct_orthonormal():
+    m = ofe.dct2_ortho_matrix(24, 24)
+    np.testing.assert_allclose(m @ m.T, np.eye(24), atol=1e-12)
+    from scipy.fft import dct
+
+    x = np.random.RandomState(0).standard_normal(24)
+    np.testing.assert_allclose(m @ x, dct(x, type=2, norm="ortho"), atol=1e-12)
+
+
+def test_single_gaussian_closed_form():
+    x = np.array([[0.5, -1.0], [2.0, 0.0]])
+    mu, var = np.array([[0.0, 1.0]]), np.array([[2.0, 0.5]])
+    want = -0.5 * (2 * np.log(2 * np.pi) + np.log(var).sum() + ((x - mu) ** 2 / var).sum(axis=1))
+    np.testing.assert_allclose(ogmm.score_samples(x, np.array([1.0]), mu, var), want, atol=1e-12)
+
+
+def test_map_adapt_limits():
+    from speech_signal_processing_b200 import synth
+
+    w, mu, var = synth.synth_ubm(8, 5, seed=2)
+    x = synth.sample_gmm(w, mu + 0.5, var, 500, seed=3).astype(np.float64)
+    n, f, s, _ = ogmm.suff_stats(x, w, mu, var)
+    _, m_inf, _ = ogmm.map_adapt(n, f, s, w, mu, var, 500, relevance=1e12)
+    np.testing.assert_allclose(m_inf, mu, atol=1e-6)  # r -> inf keeps the UBM
+    _, m_0, _ = ogmm.map_adapt(n, f, s, w, mu, var, 500, relevance=1e-12)
+    np.testing.assert_allclose(m_0, f / n[:, None], atol=1e-6)  # r -> 0 is the ML mean
+    w2, m2, v2 = ogmm.map_adapt(n, f, s, w, mu, var, 500, adapt=("means", "weights", "variances"))
+    assert np.isclose(w2.sum(), 1.0) and (v2 > 0).all()
