@@ -1,0 +1,179 @@
+/*
+ * ssp_b200.h -- C ABI of the B200-native MFCC -> diag-GMM-UBM hot path.
+ *
+ * The reference (kleinzcy/speech_signal_processing) is pure Python; its "plugin API" for
+ * this path is a set of module-level Python names.  Each entry point below
+ * names the reference call it replaces; speech_signal_processing_b200/*.py binds them with
+ * ctypes and re-exposes the reference's own signatures (mfcc, MFCC, delta, scale,
+ * GaussianMixture.fit/score, GMM()).  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer into caller-owned memory
+ *     (torch CUDA tensors in the Python host); nothing is allocated behind the caller's back;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous;
+ *   - return value: 0 on success, negative SSP_E* on error, message via ssp_last_error();
+ *   - there is NO CPU fallback: every entry point launches sm_100a kernels or fails.
+ */
+#ifndef SSP_B200_H_
+#define SSP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSP_OK 0
+#define SSP_EINVAL (-1)   /* bad argument / unsupported shape */
+#define SSP_ECUDA (-2)    /* CUDA runtime error (see ssp_last_error) */
+#define SSP_EUNSUP (-3)   /* valid request this build does not implement */
+
+#define SSP_ABI_VERSION 1
+
+int ssp_abi_version(void);
+const char* ssp_last_error(void);
+/* Names of the kernels this library has launched since load (comma separated) and how many
+ * launches in total; evidence for bench.py's "gpu_launches". */
+int64_t ssp_launch_count(void);
+void ssp_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Front-end: PCM -> cepstra (+delta, +delta-delta, +per-utterance CMVN) in ONE kernel.
+ * Replaces, per utterance: sidekit.frontend.features.mfcc (bound at GMM_UBM.py:20, called
+ * GMM_UBM.py:89), GMM_UBM.delta (GMM_UBM.py:53-69), np.hstack (:91), preprocessing.scale
+ * (:93); and utils.processing.MFCC (utils/processing.py:110-144) with the "processing" tables.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ssp_frontend_cfg {
+  int32_t frame_len;     /* samples per frame (400)                                          */
+  int32_t frame_shift;   /* hop (160)                                                        */
+  int32_t nfft;          /* power of two in [64, 4096], >= frame_len                          */
+  int32_t n_filt;        /* mel filters (24 sidekit, 26 psf, 40 processing.py)               */
+  int32_t n_ceps;        /* cepstra kept (13)                                                */
+  int32_t framing;       /* 0: floor((N-len)/shift)+1, no padding (sidekit)
+                            1: 1+ceil((N-len)/shift), zero-padded tail (psf)
+                            2: ceil(N/shift), zero-padded tail (utils/processing.py:27)       */
+  int32_t preemph_mode;  /* 0 none; 1 per frame, y[0]=x[0]-p*x[0] (sidekit);
+                            2 whole signal, y[0]=x[0] (psf)                                    */
+  float preemph;         /* 0.97                                                             */
+  int32_t spec_type;     /* 0 power re^2+im^2; 1 magnitude                                    */
+  float spec_scale;      /* spectrum multiplied by this (1/nfft for psf and processing.py)   */
+  int32_t log_type;      /* 0 natural log; 1 log10                                            */
+  float log_add;         /* added before the log (1e-8 at utils/processing.py:105)           */
+  float log_zero_floor;  /* if > 0: exact zeros are replaced by this before the log (psf eps) */
+  int32_t energy_mode;   /* 0 none; 1 sidekit ln(sum y^2) of the pre-emphasised, un-windowed
+                            frame -> out_log_energy; 2 psf: c0 := ln(sum of scaled spectrum)  */
+  int32_t delta_order;   /* 0, 1 (reference, 26-d) or 2 (39-d)                                 */
+  int32_t delta_n;       /* regression half-width N (2)                                       */
+  int32_t cmvn;          /* 1: per-utterance mean/variance normalisation (ddof=0, std<10eps->1) */
+  int32_t pcm_dtype;     /* 0 int16, 1 float32                                                 */
+} ssp_frontend_cfg;
+
+/* Number of frames the framing rule yields for n_samples (0 if the utterance is too short). */
+int64_t ssp_frontend_num_frames(const ssp_frontend_cfg* cfg, int64_t n_samples);
+/* Longest utterance (in frames) the fused single-pass kernel accepts (shared-memory bound). */
+int64_t ssp_frontend_max_frames(const ssp_frontend_cfg* cfg);
+
+/*
+ * pcm            device, int16 or float32 samples of all utterances back to back
+ * sample_offsets device int64[n_utts+1], start of each utterance in `pcm` (16-byte aligned
+ *                starts are not required)
+ * window         device float[frame_len]
+ * fb_start/len   device int32[n_filt]: first FFT bin and number of bins of each triangle
+ * fb_offset      device int32[n_filt]: offset of the triangle's weights in fb_weights
+ * fb_weights     device float[sum(fb_len)]
+ * dct            device float[n_ceps * n_filt] (row-major; lifter folded in)
+ * frame_offsets  device int64[n_utts+1], prefix sum of ssp_frontend_num_frames per utterance
+ * out_feats      device float[total_frames * n_ceps*(1+delta_order)]
+ * out_log_energy device float[total_frames] or NULL
+ */
+int ssp_frontend_batch(const void* pcm, const int64_t* sample_offsets, int64_t n_utts,
+                       const ssp_frontend_cfg* cfg, const float* window, const int32_t* fb_start,
+                       const int32_t* fb_len, const int32_t* fb_offset, const float* fb_weights,
+                       const float* dct, const int64_t* frame_offsets, int64_t max_frames_per_utt,
+                       float* out_feats, float* out_log_energy, void* stream);
+
+/* GMM_UBM.delta (GMM_UBM.py:53-69) on a (T, F) float32 device matrix. */
+int ssp_delta(const float* feat, int64_t n_frames, int32_t n_feat, int32_t delta_n, float* out,
+              void* stream);
+/* sklearn.preprocessing.scale (GMM_UBM.py:93) per utterance over concatenated (T, F) features. */
+int ssp_cmvn(const float* feat, const int64_t* frame_offsets, int64_t n_utts, int32_t n_feat,
+             float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GMM: packed models, scoring, EM/MAP sufficient statistics.
+ * Replaces sklearn.mixture.GaussianMixture(covariance_type='diag').score / .fit internals as
+ * called at GMM_UBM.py:158-160,169-170,185,194 (sklearn/mixture/_gaussian_mixture.py:536-553,
+ * _base.py:373,393,552-582).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ssp_gmm_dims {
+  int32_t n_models;
+  int32_t n_comp;   /* K                                         */
+  int32_t n_feat;   /* D (<= 80)                                 */
+} ssp_gmm_dims;
+
+/* Bytes of the packed-model buffer for these dims (0 if unsupported). */
+int64_t ssp_gmm_pack_bytes(const ssp_gmm_dims* dims);
+/*
+ * weights   device double[n_models*K], means/variances device double[n_models*K*D].
+ * out_pack  device, ssp_gmm_pack_bytes() bytes, 128-byte aligned.  Holds, per model,
+ *           (a) exact fp32 rows [mu/var, -1/(2 var)] + log-constant for the CUDA-core kernels and
+ *           (b) TF32-rounded, log2(e)-scaled [mu/var, -1/(2 var), c_hi, c_lo] tiles laid out as
+ *               tcgen05 shared-memory images (one bulk copy per 128-component tile).
+ */
+int ssp_gmm_pack_models(const double* weights, const double* means, const double* variances,
+                        const ssp_gmm_dims* dims, void* out_pack, void* stream);
+
+#define SSP_PREC_FP32 0 /* CUDA-core FP32 FMA, ~1e-7 relative                              */
+#define SSP_PREC_TF32 1 /* tcgen05 kind::tf32 MMA, FP32 accumulate in TMEM, ~3e-5 relative */
+
+/*
+ * scores[u, m] = mean over the frames of utterance u of log sum_c w_c N(x_t; mu_mc, var_mc)
+ * -- GaussianMixture.score for every (utterance, model) pair in one launch (GMM_UBM.py:182-197
+ * makes S*N*2 separate calls).
+ * feats          device float[total_frames * D]
+ * frame_offsets  device int64[n_utts+1]; total_frames == frame_offsets[n_utts] (host copy, so that
+ *                the launch needs no device read-back)
+ * out_scores     device double[n_utts * n_models], overwritten
+ * out_frame_lse  device float[n_models * total_frames] or NULL: per-frame log-likelihood
+ *                (GaussianMixture.score_samples)
+ */
+int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, int64_t n_utts,
+                  int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, int32_t precision,
+                  double* out_scores, float* out_frame_lse, void* stream);
+
+/*
+ * Posterior-weighted sufficient statistics of ONE model (dims->n_models must be 1) over
+ * segments of frames (one segment = all frames for UBM EM; one segment per speaker for MAP
+ * enrolment):  N[s,c] = sum_t g_tc, F[s,c,:] = sum_t g_tc x_t, S[s,c,:] = sum_t g_tc x_t^2,
+ * loglik[s] = sum_t log p(x_t); g = posterior (sklearn _base.py:552-582; M-step inputs of
+ * _gaussian_mixture.py:312-313,250-252).  Outputs are ACCUMULATED into (caller zeroes them).
+ * frame_lse      device float[total_frames] scratch (written by this call)
+ */
+int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs,
+                  int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n,
+                  double* out_f, double* out_s, double* out_loglik, void* stream);
+
+/*
+ * M-step on device (sklearn _gaussian_mixture.py:312-313,250-252,898): from (all-reduced)
+ * statistics to weights/means/variances, double precision.
+ * nk = N + 10*eps_of(stat_dtype); mu = F/nk; var = S/nk - mu^2 + reg_covar; w = nk/sum(nk).
+ */
+int ssp_gmm_mstep(const double* n, const double* f, const double* s, int32_t n_comp, int32_t n_feat,
+                  double reg_covar, double nk_eps, double* out_weights, double* out_means,
+                  double* out_variances, void* stream);
+
+/*
+ * Relevance-MAP adaptation (Reynolds et al. 2000; absent from the reference code)
+ * for a batch of speakers from their UBM statistics: alpha = n/(n+r);
+ * mu^ = alpha F/n + (1-alpha) mu_ubm.  flags bit0: adapt means, bit1: weights, bit2: variances.
+ */
+int ssp_gmm_map_adapt(const double* n, const double* f, const double* s, const int64_t* seg_offsets,
+                      int64_t n_spk, const double* ubm_weights, const double* ubm_means,
+                      const double* ubm_variances, int32_t n_comp, int32_t n_feat, double relevance,
+                      int32_t flags, double* out_weights, double* out_means, double* out_variances,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSP_B200_H_ */

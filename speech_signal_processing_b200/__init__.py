@@ -1,0 +1,16 @@
+"""speech_signal_processing_b200 -- the MFCC -> diag-GMM-UBM hot path of
+kleinzcy/speech_signal_processing on B200 (sm_100a) behind the reference's own entry points.
+
+Nothing here imports ``oracle`` and nothing falls back to the CPU: the CUDA library
+(``libssp_b200.so``, built by ``python -m speech_signal_processing_b200.build``) is loaded on the
+first call that needs it and a missing library or device raises.
+"""
+from . import synth  # noqa: F401  (host-side synthetic inputs)
+from .frontend import (FrontEnd, MFCC, Recipe, delta, extract_feature, mfcc, preprocessing, processing_recipe,  # noqa: F401
+                       psf_recipe, scale, sidekit_recipe)
+from .mixture import GaussianMixture, ModelSet, score_matrix  # noqa: F401
+from .ubm import GMM, identify, install, map_adapt  # noqa: F401
+
+__all__ = ["FrontEnd", "Recipe", "sidekit_recipe", "psf_recipe", "processing_recipe", "mfcc", "MFCC", "delta", "scale",
+           "preprocessing", "extract_feature", "GaussianMixture", "ModelSet", "score_matrix", "GMM", "identify",
+           "map_adapt", "install", "synth"]

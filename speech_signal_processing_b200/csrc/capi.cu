@@ -1,0 +1,76 @@
+// extern "C" entry points that are not tied to one kernel file: error string, launch counter,
+// packing and the score / stats dispatch.
+#include <cstdarg>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace ssp {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+}  // namespace ssp
+
+extern "C" int ssp_abi_version(void) { return SSP_ABI_VERSION; }
+extern "C" const char* ssp_last_error(void) { return ssp::g_err; }
+extern "C" int64_t ssp_launch_count(void) { return ssp::g_launches.load(); }
+extern "C" void ssp_reset_launch_count(void) { ssp::g_launches.store(0); }
+
+extern "C" int64_t ssp_gmm_pack_bytes(const ssp_gmm_dims* dims) {
+  ssp::PackLayout L;
+  if (!ssp::make_layout(dims, &L)) return 0;
+  return (int64_t)L.bytes;
+}
+
+extern "C" int ssp_gmm_pack_models(const double* weights, const double* means, const double* variances,
+                                   const ssp_gmm_dims* dims, void* out_pack, void* stream) {
+  ssp::PackLayout L;
+  SSP_REQUIRE(ssp::make_layout(dims, &L), "ssp_gmm_pack_models: unsupported dims (need 1 <= D <= %d)", ssp::kMaxFeat);
+  SSP_REQUIRE(weights && means && variances && out_pack, "ssp_gmm_pack_models: null pointer");
+  SSP_REQUIRE(((uintptr_t)out_pack & 127) == 0, "ssp_gmm_pack_models: out_pack must be 128-byte aligned");
+  return ssp::launch_pack(weights, means, variances, L, out_pack, (cudaStream_t)stream);
+}
+
+extern "C" int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, int64_t n_utts, int64_t total_frames,
+                             const void* pack, const ssp_gmm_dims* dims, int32_t precision, double* out_scores,
+                             float* out_frame_lse, void* stream) {
+  ssp::PackLayout L;
+  SSP_REQUIRE(ssp::make_layout(dims, &L), "ssp_gmm_score: unsupported dims");
+  SSP_REQUIRE(frame_offsets && pack && out_scores && (feats || total_frames == 0), "ssp_gmm_score: null pointer");
+  SSP_REQUIRE(n_utts >= 0 && total_frames >= 0, "ssp_gmm_score: negative size");
+  if (n_utts == 0) return SSP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == SSP_PREC_FP32)
+    return ssp::launch_score_simt(feats, frame_offsets, n_utts, total_frames, pack, L, true, out_scores, out_frame_lse, st);
+  if (precision == SSP_PREC_TF32)
+    return ssp::launch_score_tc(feats, frame_offsets, n_utts, total_frames, pack, L, true, out_scores, out_frame_lse, st);
+  SSP_REQUIRE(false, "ssp_gmm_score: unknown precision %d", precision);
+}
+
+extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
+                             const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n, double* out_f,
+                             double* out_s, double* out_loglik, void* stream) {
+  ssp::PackLayout L;
+  SSP_REQUIRE(ssp::make_layout(dims, &L), "ssp_gmm_stats: unsupported dims");
+  SSP_REQUIRE(dims->n_models == 1, "ssp_gmm_stats: statistics are taken under ONE model (got %d)", dims->n_models);
+  SSP_REQUIRE(seg_offsets && pack && frame_lse && out_n && out_f && out_s && out_loglik, "ssp_gmm_stats: null pointer");
+  SSP_REQUIRE(n_segs >= 0 && total_frames >= 0, "ssp_gmm_stats: negative size");
+  if (n_segs == 0) return SSP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // pass 1: per-frame log-likelihood (FP32 exact; posteriors are exp(L - lse) so TF32 logits are not enough) and
+  // the per-segment sum of frame log-likelihoods (the EM lower bound numerator, sklearn _base.py:558)
+  int rc = ssp::launch_score_simt(feats, seg_offsets, n_segs, total_frames, pack, L, false, out_loglik, frame_lse, st);
+  if (rc != SSP_OK) return rc;
+  // pass 2: posteriors and N/F/S
+  return ssp::launch_stats_simt(feats, seg_offsets, n_segs, total_frames, pack, L, frame_lse, out_n, out_f, out_s, st);
+}

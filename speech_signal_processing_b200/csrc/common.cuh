@@ -1,0 +1,140 @@
+// Shared host/device helpers for the ssp_b200 library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ssp_b200.h"
+
+namespace ssp {
+
+// ---------------------------------------------------------------- error / launch bookkeeping
+void set_error(const char* fmt, ...);
+void count_launch(const char* kernel_name);
+
+#define SSP_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::ssp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SSP_ECUDA;                                                                \
+    }                                                                                  \
+  } while (0)
+
+#define SSP_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::ssp::set_error(__VA_ARGS__);    \
+      return SSP_EINVAL;                \
+    }                                   \
+  } while (0)
+
+#define SSP_LAUNCH_CHECK(name)          \
+  do {                                  \
+    ::ssp::count_launch(name);          \
+    SSP_CUDA_OK(cudaGetLastError());    \
+  } while (0)
+
+// ---------------------------------------------------------------- packed-model layout
+// One buffer holds both operand forms of every model (see ssp_gmm_pack_models):
+//   E (exact, CUDA-core kernels): ab[m][c][d] = (mu/var, -1/(2 var)) float2, d < DP (zero padded),
+//                                 cst[m][c]   = log w - 0.5(D log 2pi + sum mu^2/var) + 0.5 sum log(1/var)
+//   T (tensor, tcgen05 kernel):   tile[m][c/128] = shared-memory image [KD/4][128] float4 of the
+//                                 TF32-rounded, log2(e)-scaled rows [mu/var, -1/(2var), c_hi, c_lo, 0..]
+constexpr int kTileN = 128;  // components per tensor tile / padding granule of K
+constexpr int kMaxFeat = 80;
+
+struct PackLayout {
+  int n_models, K, D;
+  int Kp;  // K rounded up to kTileN (padded components have cst = -1e30, zero rows)
+  int DP;  // D padded for the CUDA-core kernels: 16, 32, 40, 64 or 80
+  int KD;  // contraction length of the tensor kernel: roundup(2D + 2, 8)
+  size_t off_ab, off_cst, off_tile, bytes;
+  size_t tile_floats() const { return (size_t)kTileN * KD; }
+};
+
+inline int pad_feat(int d) {
+  if (d <= 16) return 16;
+  if (d <= 32) return 32;
+  if (d <= 40) return 40;
+  if (d <= 64) return 64;
+  return 80;
+}
+
+inline bool make_layout(const ssp_gmm_dims* dims, PackLayout* L) {
+  if (!dims || dims->n_models < 1 || dims->n_comp < 1 || dims->n_feat < 1 || dims->n_feat > kMaxFeat) return false;
+  L->n_models = dims->n_models;
+  L->K = dims->n_comp;
+  L->D = dims->n_feat;
+  L->Kp = (L->K + kTileN - 1) / kTileN * kTileN;
+  L->DP = pad_feat(L->D);
+  L->KD = (2 * L->D + 2 + 7) / 8 * 8;
+  auto up = [](size_t x) { return (x + 127) / 128 * 128; };
+  size_t o = 0;
+  L->off_ab = o;
+  o = up(o + (size_t)L->n_models * L->Kp * L->DP * sizeof(float2));
+  L->off_cst = o;
+  o = up(o + (size_t)L->n_models * L->Kp * sizeof(float));
+  L->off_tile = o;
+  o = up(o + (size_t)L->n_models * L->Kp * L->KD * sizeof(float));
+  L->bytes = o;
+  return true;
+}
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// index u with offsets[u] <= x < offsets[u+1]; offsets has n+1 non-decreasing entries
+// (empty segments allowed).  Returns -1 if x is outside [offsets[0], offsets[n]).
+__device__ __forceinline__ int find_segment(const int64_t* __restrict__ offsets, int64_t n, int64_t x) {
+  if (x < offsets[0] || x >= offsets[n]) return -1;
+  int64_t lo = 0, hi = n;  // invariant: offsets[lo] <= x < offsets[hi]
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= x) lo = mid; else hi = mid;
+  }
+  return (int)lo;
+}
+
+// Sum `val` over runs of equal `seg` among the 32 lanes (runs are contiguous) and let the first
+// lane of each run add it to out[seg * stride + col] (double atomics).  seg < 0: lane inactive.
+__device__ __forceinline__ void warp_segmented_atomic_add(double* out, int seg, int64_t stride, int64_t col, float val,
+                                                          int lane) {
+  const unsigned full = 0xffffffffu;
+  float v = seg >= 0 ? val : 0.f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float ov = __shfl_down_sync(full, v, d);
+    int os = __shfl_down_sync(full, seg, d);
+    if (lane + d < 32 && os == seg) v += ov;
+  }
+  int prev = __shfl_up_sync(full, seg, 1);
+  bool head = (lane == 0) || (prev != seg);
+  if (head && seg >= 0) atomicAdd(out + (int64_t)seg * stride + col, (double)v);
+}
+#endif
+
+// kernels / launchers implemented in the .cu files ------------------------------------------
+int launch_pack(const double* w, const double* mu, const double* var, const PackLayout& L, void* pack, cudaStream_t st);
+int launch_score_simt(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
+                      const PackLayout& L, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
+int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
+                    const PackLayout& L, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
+int launch_stats_simt(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
+                      const void* pack, const PackLayout& L, const float* frame_lse, double* out_n, double* out_f,
+                      double* out_s, cudaStream_t st);
+
+}  // namespace ssp

@@ -1,0 +1,175 @@
+// Model packing, M-step and MAP adaptation: small double-precision kernels that keep the whole
+// EM / enrolment loop resident in HBM (no host round trip of parameters between iterations).
+#include "common.cuh"
+
+namespace ssp {
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// One thread per (model, padded component).  Follows sklearn/mixture/_gaussian_mixture.py:536-553:
+//   L[t,c] = log w_c - 0.5 (D log 2pi + sum_d (mu^2 p - 2 x mu p + x^2 p)) + 0.5 sum_d log p,  p = 1/var
+// which is the contraction [x, x^2, 1] . [mu p, -p/2, cst_c].
+__global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __restrict__ mu,
+                                const double* __restrict__ var, int n_models, int K, int Kp, int D, int DP, int KD,
+                                float2* __restrict__ ab, float* __restrict__ cst, float* __restrict__ tiles) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_models * Kp) return;
+  int m = (int)(idx / Kp), c = (int)(idx % Kp);
+  float2* ab_row = ab + idx * DP;
+  // tile image: [KD/4][128] float4, element (kc, n) holds row n, columns 4kc..4kc+3
+  float* tile = tiles + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KD;
+  const int n = c % kTileN;
+  auto tile_at = [&](int j) -> float& { return tile[((j >> 2) * kTileN + n) * 4 + (j & 3)]; };
+  const double LOG2E = 1.4426950408889634074;
+  if (c >= K) {
+    for (int d = 0; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
+    cst[idx] = -1e30f;
+    for (int j = 0; j < KD; ++j) tile_at(j) = 0.f;
+    tile_at(2 * D) = to_tf32(-1e30f);
+    return;
+  }
+  const double* mu_r = mu + ((int64_t)m * K + c) * D;
+  const double* var_r = var + ((int64_t)m * K + c) * D;
+  double quad = 0.0, logdet = 0.0;
+  for (int d = 0; d < D; ++d) {
+    double p = 1.0 / var_r[d];
+    double a1 = mu_r[d] * p, a2 = -0.5 * p;
+    quad += mu_r[d] * mu_r[d] * p;
+    logdet += log(p);
+    ab_row[d] = make_float2((float)a1, (float)a2);
+    tile_at(d) = to_tf32((float)(a1 * LOG2E));
+    tile_at(D + d) = to_tf32((float)(a2 * LOG2E));
+  }
+  for (int d = D; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
+  double cc = log(w[(int64_t)m * K + c]) - 0.5 * (D * 1.8378770664093454836 + quad) + 0.5 * logdet;
+  if (!(cc > -1e30)) cc = -1e30;  // w == 0 -> log w = -inf; keep finite so exp() underflows cleanly
+  cst[idx] = (float)cc;
+  // the constant goes through the TF32 MMA as two exactly-representable pieces times A columns of 1.0
+  double c2 = cc * LOG2E;
+  float hi = to_tf32((float)c2);
+  float lo = to_tf32((float)(c2 - (double)hi));
+  tile_at(2 * D) = hi;
+  tile_at(2 * D + 1) = lo;
+  for (int j = 2 * D + 2; j < KD; ++j) tile_at(j) = 0.f;
+}
+
+int launch_pack(const double* w, const double* mu, const double* var, const PackLayout& L, void* pack, cudaStream_t st) {
+  char* base = (char*)pack;
+  int64_t n = (int64_t)L.n_models * L.Kp;
+  int threads = 128;
+  int64_t blocks = (n + threads - 1) / threads;
+  gmm_pack_kernel<<<(unsigned)blocks, threads, 0, st>>>(w, mu, var, L.n_models, L.K, L.Kp, L.D, L.DP, L.KD,
+                                                       (float2*)(base + L.off_ab), (float*)(base + L.off_cst),
+                                                       (float*)(base + L.off_tile));
+  SSP_LAUNCH_CHECK("gmm_pack_kernel");
+  return SSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ M-step
+// sklearn _gaussian_mixture.py:312-313 (nk = resp.sum + 10 eps), :250-252 (diag covariance),
+// :898 (weights /= weights.sum()).  One block; K*D is small.
+__global__ void gmm_mstep_kernel(const double* __restrict__ n, const double* __restrict__ f, const double* __restrict__ s,
+                                 int K, int D, double reg_covar, double nk_eps, double* __restrict__ ow,
+                                 double* __restrict__ omu, double* __restrict__ ovar) {
+  __shared__ double red[32];
+  __shared__ double total_s;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) part += n[c] + nk_eps;
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+    total_s = t;
+  }
+  __syncthreads();
+  const double total = total_s;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) ow[c] = (n[c] + nk_eps) / total;
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+    double nk = n[i / D] + nk_eps;
+    double m = f[i] / nk;
+    omu[i] = m;
+    ovar[i] = s[i] / nk - m * m + reg_covar;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ MAP
+// Reynolds, Quatieri, Dunn (2000) eq. 11-14.  One block per speaker.
+__global__ void gmm_map_kernel(const double* __restrict__ n, const double* __restrict__ f, const double* __restrict__ s,
+                               const int64_t* __restrict__ seg, const double* __restrict__ uw,
+                               const double* __restrict__ umu, const double* __restrict__ uvar, int K, int D,
+                               double relevance, int flags, double* __restrict__ ow, double* __restrict__ omu,
+                               double* __restrict__ ovar) {
+  const int spk = blockIdx.x;
+  const double* n_s = n + (int64_t)spk * K;
+  const double* f_s = f + (int64_t)spk * K * D;
+  const double* s_s = s + (int64_t)spk * K * D;
+  __shared__ double red[32];
+  __shared__ double total_s;
+  if (ow) {
+    const double T = (double)(seg[spk + 1] - seg[spk]);
+    double part = 0.0;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+      double a = n_s[c] / (n_s[c] + relevance);
+      double v = (flags & 2) ? a * n_s[c] / T + (1.0 - a) * uw[c] : uw[c];
+      ow[(int64_t)spk * K + c] = v;
+      part += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+      total_s = t;
+    }
+    __syncthreads();
+    if (flags & 2)
+      for (int c = threadIdx.x; c < K; c += blockDim.x) ow[(int64_t)spk * K + c] /= total_s;
+  }
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+    int c = i / D;
+    double nc = n_s[c];
+    double a = nc / (nc + relevance);
+    double safe = nc > 1e-300 ? nc : 1e-300;
+    double m_new = (flags & 1) ? a * (f_s[i] / safe) + (1.0 - a) * umu[i] : umu[i];
+    if (omu) omu[(int64_t)spk * K * D + i] = m_new;
+    if (ovar) {
+      double v = uvar[i];
+      if (flags & 4) v = a * (s_s[i] / safe) + (1.0 - a) * (uvar[i] + umu[i] * umu[i]) - m_new * m_new;
+      ovar[(int64_t)spk * K * D + i] = v;
+    }
+  }
+}
+
+}  // namespace ssp
+
+extern "C" int ssp_gmm_mstep(const double* n, const double* f, const double* s, int32_t n_comp, int32_t n_feat,
+                             double reg_covar, double nk_eps, double* out_weights, double* out_means,
+                             double* out_variances, void* stream) {
+  SSP_REQUIRE(n && f && s && out_weights && out_means && out_variances, "ssp_gmm_mstep: null pointer");
+  SSP_REQUIRE(n_comp > 0 && n_feat > 0, "ssp_gmm_mstep: bad dims");
+  ssp::gmm_mstep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, f, s, n_comp, n_feat, reg_covar, nk_eps, out_weights,
+                                                             out_means, out_variances);
+  SSP_LAUNCH_CHECK("gmm_mstep_kernel");
+  return SSP_OK;
+}
+
+extern "C" int ssp_gmm_map_adapt(const double* n, const double* f, const double* s, const int64_t* seg_offsets,
+                                 int64_t n_spk, const double* ubm_weights, const double* ubm_means,
+                                 const double* ubm_variances, int32_t n_comp, int32_t n_feat, double relevance,
+                                 int32_t flags, double* out_weights, double* out_means, double* out_variances,
+                                 void* stream) {
+  SSP_REQUIRE(n && f && s && seg_offsets && ubm_weights && ubm_means && ubm_variances, "ssp_gmm_map_adapt: null pointer");
+  SSP_REQUIRE(n_spk > 0 && n_comp > 0 && n_feat > 0 && relevance >= 0.0, "ssp_gmm_map_adapt: bad dims");
+  ssp::gmm_map_kernel<<<(unsigned)n_spk, 256, 0, (cudaStream_t)stream>>>(n, f, s, seg_offsets, ubm_weights, ubm_means,
+                                                                       ubm_variances, n_comp, n_feat, relevance, flags,
+                                                                       out_weights, out_means, out_variances);
+  SSP_LAUNCH_CHECK("gmm_map_kernel");
+  return SSP_OK;
+}

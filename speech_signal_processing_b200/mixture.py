@@ -1,0 +1,376 @@
+"""Diagonal-covariance GMM on the GPU behind sklearn's ``GaussianMixture`` surface.
+
+The reference binds ``sklearn.mixture.GaussianMixture`` at GMM_UBM.py:16 and uses exactly
+``GaussianMixture(n_components=K, covariance_type='diag').fit(X)`` (:158-160, :169-170) and
+``.score(X)`` (:185, :194), plus pickling of the fitted objects (:173-179).  :class:`GaussianMixture`
+mirrors that surface (same constructor names, attributes and error behaviour); the arithmetic runs
+in the CUDA library: ``ssp_gmm_pack_models`` / ``ssp_gmm_score`` / ``ssp_gmm_stats`` /
+``ssp_gmm_mstep``.  :class:`ModelSet` + :func:`score_matrix` are the batched form the reference
+lacks (all utterances x all models in one launch instead of S*N*2 Python calls).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32}
+
+
+def _as_feats(x, device):
+    """numpy (T, D) or torch tensor -> contiguous float32 CUDA tensor."""
+    torch = _lib.require_cuda()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    x = np.asarray(x)
+    if x.ndim != 2:
+        raise ValueError(f"Expected 2D array, got {x.ndim}D array instead")
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32), device=device)
+
+
+def concat_utterances(utts, device):
+    """list of (T_i, D) arrays -> (feats (sum T, D) cuda, frame_offsets np.int64)."""
+    torch = _lib.require_cuda()
+    if isinstance(utts, tuple) and len(utts) == 2 and isinstance(utts[0], torch.Tensor):
+        return utts[0].contiguous(), np.asarray(utts[1], dtype=np.int64)
+    lens = np.array([len(u) for u in utts], dtype=np.int64)
+    offs = np.zeros(len(utts) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    d = np.asarray(utts[0]).shape[1]
+    host = torch.empty((int(offs[-1]), d), dtype=torch.float32, pin_memory=True)
+    hv = host.numpy()
+    for u, o in zip(utts, offs[:-1]):
+        hv[o : o + len(u)] = u
+    return host.to(device, non_blocking=True), offs
+
+
+class ModelSet:
+    """``n_models`` diagonal GMMs with the same (K, D), packed once in HBM for the scoring kernels."""
+
+    def __init__(self, weights, means, variances, device=None):
+        torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+        def dev(a):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=self.device, dtype=torch.float64).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+
+        w, mu, var = dev(weights), dev(means), dev(variances)
+        if mu.dim() == 2:
+            w, mu, var = w[None], mu[None], var[None]
+        if mu.dim() != 3 or var.shape != mu.shape or w.shape != mu.shape[:2]:
+            raise ValueError("expected weights (S,K), means (S,K,D), variances (S,K,D)")
+        self.n_models, self.n_comp, self.n_feat = (int(v) for v in mu.shape)
+        self.dims = _lib.GmmDims(self.n_models, self.n_comp, self.n_feat)
+        nbytes = int(self.lib.ssp_gmm_pack_bytes(C.byref(self.dims)))
+        if nbytes <= 0:
+            raise ValueError(f"unsupported GMM dims K={self.n_comp} D={self.n_feat} (need 1 <= D <= 80)")
+        self.pack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.repack(w, mu, var)
+
+    def repack(self, w, mu, var):
+        """Re-derive the packed operands from (device, float64) parameters -- one tiny kernel."""
+        self._params = (w, mu, var)
+        _lib.check(self.lib.ssp_gmm_pack_models(_lib.ptr(w), _lib.ptr(mu), _lib.ptr(var), C.byref(self.dims),
+                                                _lib.ptr(self.pack), _lib.stream_ptr()), "ssp_gmm_pack_models")
+
+    # ---------------------------------------------------------------------------------------
+    def score(self, feats, frame_offsets, precision="tf32", want_frame_lse=False):
+        """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None)."""
+        torch = _lib.require_cuda()
+        frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
+        n_utts, total = len(frame_offsets) - 1, int(frame_offsets[-1])
+        if precision == "auto":  # tensor cores whenever the contraction fits the tcgen05 kernel's tile
+            precision = "tf32" if 2 * self.n_feat + 2 <= 80 else "fp32"
+        if feats.shape[1] != self.n_feat:
+            raise ValueError(f"X has {feats.shape[1]} features, but the models expect {self.n_feat}")
+        d_off = torch.as_tensor(frame_offsets, device=self.device)
+        scores = torch.empty((n_utts, self.n_models), dtype=torch.float64, device=self.device)
+        lse = torch.empty((self.n_models, total), dtype=torch.float32, device=self.device) if want_frame_lse else None
+        rc = self.lib.ssp_gmm_score(_lib.ptr(feats), _lib.ptr(d_off), n_utts, total, _lib.ptr(self.pack),
+                                    C.byref(self.dims), PRECISIONS[precision], _lib.ptr(scores), _lib.ptr(lse),
+                                    _lib.stream_ptr())
+        _lib.check(rc, "ssp_gmm_score")
+        self._keep = d_off
+        return scores, lse
+
+    def stats(self, feats, seg_offsets):
+        """N (S,K), F (S,K,D), S2 (S,K,D), loglik (S,) float64 cuda, under this (single) model."""
+        torch = _lib.require_cuda()
+        if self.n_models != 1:
+            raise ValueError("statistics are taken under one model (the UBM)")
+        seg_offsets = np.asarray(seg_offsets, dtype=np.int64)
+        n_segs, total = len(seg_offsets) - 1, int(seg_offsets[-1])
+        k, d = self.n_comp, self.n_feat
+        n = torch.zeros((n_segs, k), dtype=torch.float64, device=self.device)
+        f = torch.zeros((n_segs, k, d), dtype=torch.float64, device=self.device)
+        s = torch.zeros((n_segs, k, d), dtype=torch.float64, device=self.device)
+        ll = torch.zeros(n_segs, dtype=torch.float64, device=self.device)
+        lse = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
+        d_off = torch.as_tensor(seg_offsets, device=self.device)
+        rc = self.lib.ssp_gmm_stats(_lib.ptr(feats), _lib.ptr(d_off), n_segs, total, _lib.ptr(self.pack),
+                                    C.byref(self.dims), _lib.ptr(lse), _lib.ptr(n), _lib.ptr(f), _lib.ptr(s), _lib.ptr(ll),
+                                    _lib.stream_ptr())
+        _lib.check(rc, "ssp_gmm_stats")
+        self._keep = (d_off, lse)
+        return n, f, s, ll
+
+
+def score_matrix(utts, models, precision="tf32", device=None):
+    """``pred[j, i] = models[i].score(utts[j])`` for all pairs in one launch (GMM_UBM.py:182-185,
+    191-194 without the Python double loop).  ``models``: list of fitted :class:`GaussianMixture`
+    (or anything with ``weights_/means_/covariances_``) or a :class:`ModelSet`.  Returns float64 numpy."""
+    torch = _lib.require_cuda()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    ms = models if isinstance(models, ModelSet) else ModelSet(
+        np.stack([np.asarray(m.weights_) for m in models]), np.stack([np.asarray(m.means_) for m in models]),
+        np.stack([np.asarray(m.covariances_) for m in models]), device=dev)
+    feats, offs = concat_utterances(utts, dev)
+    scores, _ = ms.score(feats, offs, precision=precision)
+    return scores.cpu().numpy()
+
+
+class GaussianMixture:
+    """GPU drop-in for ``sklearn.mixture.GaussianMixture(covariance_type='diag')``.
+
+    Same constructor arguments and fitted attributes as sklearn 1.9 (``weights_``, ``means_``,
+    ``covariances_``, ``precisions_``, ``precisions_cholesky_``, ``converged_``, ``n_iter_``,
+    ``lower_bound_``, ``lower_bounds_``).  ``init_params='kmeans'`` runs a GPU Lloyd iteration from
+    random frames (sklearn's KMeans++ stream is not reproduced: the reference leaves
+    ``random_state=None``, so its own runs are not reproducible either -- SURVEY F7); parity with
+    sklearn is defined for given ``weights_init/means_init/precisions_init``.
+
+    ``comm``: optional :class:`speech_signal_processing_b200.dist.Comm`; when given, ``fit`` treats X as
+    this rank's shard of the frames and all-reduces the statistics tensor each EM iteration (NCCL).
+    """
+
+    def __init__(self, n_components=1, *, covariance_type="diag", tol=1e-3, reg_covar=1e-6, max_iter=100, n_init=1,
+                 init_params="kmeans", weights_init=None, means_init=None, precisions_init=None, random_state=None,
+                 warm_start=False, verbose=0, verbose_interval=10, precision="auto", comm=None):
+        self.n_components = n_components
+        self.covariance_type = covariance_type
+        self.tol = tol
+        self.reg_covar = reg_covar
+        self.max_iter = max_iter
+        self.n_init = n_init
+        self.init_params = init_params
+        self.weights_init = weights_init
+        self.means_init = means_init
+        self.precisions_init = precisions_init
+        self.random_state = random_state
+        self.warm_start = warm_start
+        self.verbose = verbose
+        self.verbose_interval = verbose_interval
+        self.precision = precision
+        self.comm = comm
+        self._ms = None
+
+    # ------------------------------------------------------------------ pickling (GMM_UBM.py:173-179)
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_ms"] = None
+        st["comm"] = None
+        return st
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self):
+        if self.covariance_type != "diag":
+            raise NotImplementedError("only covariance_type='diag' (the reference's setting, GMM_UBM.py:158) is implemented")
+        if self.n_components < 1:
+            raise ValueError(f"Invalid value for 'n_components': {self.n_components}")
+
+    def _model_set(self):
+        if self._ms is None:
+            if not hasattr(self, "means_"):
+                raise AttributeError("This GaussianMixture instance is not fitted yet. Call 'fit' first.")
+            self._ms = ModelSet(self.weights_, self.means_, self.covariances_)
+        return self._ms
+
+    def _set_params_from_device(self, w, mu, var):
+        self.weights_ = w.cpu().numpy()
+        self.means_ = mu.cpu().numpy()
+        self.covariances_ = var.cpu().numpy()
+        self.precisions_cholesky_ = 1.0 / np.sqrt(self.covariances_)
+        self.precisions_ = self.precisions_cholesky_ ** 2
+
+    # ------------------------------------------------------------------ EM
+    def _em_iteration(self, ms, feats, seg, n_total, nk_eps, w, mu, var):
+        """One E+M step on device.  Returns the lower bound (mean frame log-likelihood under the
+        parameters the E-step used)."""
+        torch = _lib.require_cuda()
+        n, f, s, ll = ms.stats(feats, seg)
+        if self.comm is not None and self.comm.world_size > 1:
+            k, d = ms.n_comp, ms.n_feat
+            cnt = torch.tensor([float(feats.shape[0])], dtype=torch.float64, device=feats.device)
+            flat = torch.cat([n.reshape(-1), f.reshape(-1), s.reshape(-1), ll.reshape(-1), cnt])
+            flat = self.comm.allreduce_sum(flat)
+            n, f, s = flat[:k].reshape(1, k), flat[k : k + k * d].reshape(1, k, d), flat[k + k * d : k + 2 * k * d].reshape(1, k, d)
+            ll, n_total = flat[k + 2 * k * d : k + 2 * k * d + 1], float(flat[-1].item())
+        rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), ms.n_comp, ms.n_feat, float(self.reg_covar),
+                                  float(nk_eps), _lib.ptr(w), _lib.ptr(mu), _lib.ptr(var), _lib.stream_ptr())
+        _lib.check(rc, "ssp_gmm_mstep")
+        return float(ll.item()) / n_total, n
+
+    def _kmeans_init(self, feats, seg, rs, w, mu, var, nk_eps, iters=10):
+        """Lloyd iterations as hard EM: equal weights, one small shared variance, so posteriors are
+        (numerically) one-hot; empty clusters are re-seeded from random frames.  Ends with sklearn's
+        ``_initialize(X, resp)`` M-step from those assignments."""
+        torch = _lib.require_cuda()
+        n_frames, d = feats.shape
+        k = self.n_components
+        comm = self.comm if (self.comm is not None and self.comm.world_size > 1) else None
+
+        def seed_rows(count):
+            """`count` random frames, identical on every rank (rank 0 draws from its shard)."""
+            rows = torch.zeros((count, d), dtype=torch.float64, device=feats.device)
+            if comm is None or comm.rank == 0:
+                pick = rs.choice(n_frames, size=count, replace=False)
+                rows = feats[torch.as_tensor(pick, device=feats.device)].to(torch.float64)
+            return comm.broadcast(rows.contiguous()) if comm is not None else rows
+
+        def reduced(t):
+            return comm.allreduce_sum(t) if comm is not None else t
+
+        mu.copy_(seed_rows(k)[None])
+        cnt = reduced(torch.tensor([float(n_frames)], dtype=torch.float64, device=feats.device))
+        m1 = reduced(feats.to(torch.float64).sum(dim=0)) / cnt
+        m2 = reduced((feats.to(torch.float64) ** 2).sum(dim=0)) / cnt
+        gvar = (m2 - m1 * m1).clamp_min(1e-12)
+        sharp = (0.02 * gvar)[None, None].expand(1, k, d).contiguous()
+        w.fill_(1.0 / k)
+        ms = ModelSet(w, mu, sharp, device=feats.device)
+        for it in range(iters + 1):
+            ms.repack(w, mu, sharp)
+            n, f, s, _ = ms.stats(feats, seg)
+            if comm is not None:
+                flat = reduced(torch.cat([n.reshape(-1), f.reshape(-1), s.reshape(-1)]))
+                n, f, s = flat[:k].reshape(1, k), flat[k : k + k * d].reshape(1, k, d), flat[k + k * d :].reshape(1, k, d)
+            rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), k, d, float(self.reg_covar), float(nk_eps),
+                                      _lib.ptr(w), _lib.ptr(mu), _lib.ptr(var), _lib.stream_ptr())
+            _lib.check(rc, "ssp_gmm_mstep")
+            if it == iters:
+                break
+            w.fill_(1.0 / k)
+            empty = (n[0] < 0.5).nonzero().flatten()
+            if empty.numel():
+                mu[0, empty] = seed_rows(int(empty.numel()))
+
+    def fit(self, X, y=None):
+        """Estimate parameters with EM (sklearn/mixture/_base.py:203-312)."""
+        torch = _lib.require_cuda()
+        self._check()
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        x_dtype = X.dtype if isinstance(X, np.ndarray) and X.dtype in (np.float32, np.float64) else np.float64
+        if isinstance(X, torch.Tensor):
+            x_dtype = np.float32 if X.dtype == torch.float32 else np.float64
+        feats = _as_feats(X, dev)
+        n_frames, d = feats.shape
+        k = self.n_components
+        if n_frames < 2:
+            raise ValueError(f"Found array with {n_frames} sample(s) while a minimum of 2 is required.")
+        if n_frames < k:
+            raise ValueError("Expected n_samples >= n_components "
+                             f"but got n_components = {k}, n_samples = {n_frames}")
+        nk_eps = 10.0 * float(np.finfo(x_dtype).eps)
+        seg = np.array([0, n_frames], dtype=np.int64)
+        rs = self.random_state if isinstance(self.random_state, np.random.RandomState) else np.random.RandomState(self.random_state)
+
+        do_init = not (self.warm_start and hasattr(self, "converged_"))
+        best = None
+        for _init in range(self.n_init if do_init else 1):
+            w = torch.empty((1, k), dtype=torch.float64, device=dev)
+            mu = torch.empty((1, k, d), dtype=torch.float64, device=dev)
+            var = torch.empty((1, k, d), dtype=torch.float64, device=dev)
+            if not do_init:
+                w.copy_(torch.as_tensor(self.weights_)[None]); mu.copy_(torch.as_tensor(self.means_)[None])
+                var.copy_(torch.as_tensor(self.covariances_)[None])
+            else:
+                have_all = self.weights_init is not None and self.means_init is not None and self.precisions_init is not None
+                if not have_all:
+                    if self.init_params not in ("kmeans", "k-means++", "random_from_data", "random"):
+                        raise ValueError(f"Invalid value for 'init_params': {self.init_params}")
+                    self._kmeans_init(feats, seg, rs, w, mu, var, nk_eps,
+                                      iters=10 if self.init_params in ("kmeans", "k-means++") else 0)
+                if self.weights_init is not None:
+                    w.copy_(torch.as_tensor(np.asarray(self.weights_init, dtype=np.float64))[None])
+                if self.means_init is not None:
+                    mu.copy_(torch.as_tensor(np.asarray(self.means_init, dtype=np.float64))[None])
+                if self.precisions_init is not None:
+                    var.copy_(1.0 / torch.as_tensor(np.asarray(self.precisions_init, dtype=np.float64))[None])
+            ms = ModelSet(w, mu, var, device=dev)
+            lower, bounds, converged, n_iter = -np.inf, [], False, 0
+            for n_iter in range(1, self.max_iter + 1):
+                prev = lower
+                ms.repack(w, mu, var)
+                lower, _ = self._em_iteration(ms, feats, seg, float(n_frames), nk_eps, w, mu, var)
+                bounds.append(lower)
+                if abs(lower - prev) < self.tol:
+                    converged = True
+                    break
+            if best is None or lower > best[0] or best[0] == -np.inf:
+                best = (lower, w.clone(), mu.clone(), var.clone(), n_iter, converged, bounds)
+        lower, w, mu, var, n_iter, converged, bounds = best
+        if not converged and self.max_iter > 0:
+            warnings.warn("Best performing initialization did not converge. Try different init parameters, or "
+                          "increase max_iter, tol, or check for degenerate data.", UserWarning)
+        self._set_params_from_device(w[0], mu[0], var[0])
+        if not np.all(np.isfinite(self.covariances_)) or np.any(self.covariances_ <= 0):
+            raise ValueError("Fitting the mixture model failed because some components have ill-defined empirical "
+                             "covariance (for instance caused by singleton or collapsed samples). Try to decrease the "
+                             "number of components, increase reg_covar, or scale the input data.")
+        self.converged_, self.n_iter_, self.lower_bound_, self.lower_bounds_ = converged, n_iter, lower, bounds
+        self._ms = None
+        return self
+
+    # ------------------------------------------------------------------ scoring
+    def score_samples(self, X):
+        """Per-frame log-likelihood (sklearn/mixture/_base.py:373)."""
+        ms = self._model_set()
+        feats = _as_feats(X, ms.device)
+        _, lse = ms.score(feats, np.array([0, feats.shape[0]]), precision=self.precision, want_frame_lse=True)
+        return lse[0].cpu().numpy().astype(np.float64)
+
+    def score(self, X, y=None):
+        """Mean per-frame log-likelihood (sklearn/mixture/_base.py:393) -- what GMM_UBM.py:185 calls."""
+        ms = self._model_set()
+        feats = _as_feats(X, ms.device)
+        scores, _ = ms.score(feats, np.array([0, feats.shape[0]]), precision=self.precision)
+        return float(scores[0, 0].item())
+
+    # ------------------------------------------------------------------ interchange
+    @classmethod
+    def from_params(cls, weights, means, covariances, **kw):
+        gm = cls(n_components=len(weights), **kw)
+        gm.weights_ = np.asarray(weights, dtype=np.float64)
+        gm.means_ = np.asarray(means, dtype=np.float64)
+        gm.covariances_ = np.asarray(covariances, dtype=np.float64)
+        gm.precisions_cholesky_ = 1.0 / np.sqrt(gm.covariances_)
+        gm.precisions_ = gm.precisions_cholesky_ ** 2
+        gm.converged_, gm.n_iter_, gm.lower_bound_ = True, 0, -np.inf
+        return gm
+
+    @classmethod
+    def from_sklearn(cls, sk, **kw):
+        """Adopt a fitted (e.g. unpickled ``Model/GMM_MFCC_model.pkl``) sklearn GaussianMixture."""
+        if sk.covariance_type != "diag":
+            raise NotImplementedError("only diag covariances")
+        return cls.from_params(sk.weights_, sk.means_, sk.covariances_, **kw)
+
+    def to_sklearn(self):
+        """A stock sklearn estimator carrying these parameters, so the reference's GUIs / pickles
+        (UI/GMM_UBM_GUI.py:77-80) consume GPU-trained models unchanged."""
+        from sklearn.mixture import GaussianMixture as SkGM
+
+        sk = SkGM(n_components=self.n_components, covariance_type="diag", tol=self.tol, reg_covar=self.reg_covar,
+                  max_iter=self.max_iter)
+        sk.weights_, sk.means_, sk.covariances_ = self.weights_, self.means_, self.covariances_
+        sk.precisions_cholesky_ = self.precisions_cholesky_
+        sk.precisions_ = self.precisions_
+        sk.converged_, sk.n_iter_, sk.lower_bound_ = self.converged_, self.n_iter_, self.lower_bound_
+        sk.n_features_in_ = self.means_.shape[1]
+        return sk

@@ -1,0 +1,139 @@
+"""GMM-UBM speaker identification: UBM training, MAP enrolment, batched scoring, and the
+reference's ``GMM()`` entry point.
+
+* :func:`GMM` has the signature and printed output of ``GMM_UBM.GMM`` (GMM_UBM.py:134-199): one
+  GMM per speaker + a UBM on the pooled frames, ``pred[j, i] = GMM[i].score(x_j) - UBM.score(x_j)``,
+  argmax accuracy, models pickled under ``Model/`` as stock sklearn estimators.
+* :func:`map_adapt` is the enrolment the reference's report describes but its code never does
+  (SURVEY F4): relevance MAP of the UBM from per-speaker statistics, all speakers in one launch.
+* :func:`identify` scores every test utterance against every speaker model (+ the UBM) in one
+  kernel launch and returns the LLR matrix and the argmax decisions (GMM_UBM.py:191-197).
+* :func:`install` rebinds the module-level names of an imported ``GMM_UBM`` module
+  (GMM_UBM.py:16-20) to this package, which is the whole integration.
+"""
+from __future__ import annotations
+
+import os
+import pickle as pkl
+import time
+
+import numpy as np
+
+from . import _lib
+from . import frontend as fe
+from .mixture import GaussianMixture, ModelSet, concat_utterances
+
+
+def map_adapt(ubm: GaussianMixture, speaker_frames, relevance: float = 16.0, adapt=("means",), device=None):
+    """Enrol speakers by relevance MAP (Reynolds, Quatieri & Dunn 2000, eq. 11-14).
+
+    ``speaker_frames``: list (one entry per speaker) of (T_s, D) arrays, or ``(feats, seg_offsets)``
+    already on the GPU.  Returns ``(weights (S,K), means (S,K,D), variances (S,K,D))`` as float64
+    CUDA tensors, ready for :class:`ModelSet`.
+    """
+    torch = _lib.require_cuda()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    feats, seg = concat_utterances(speaker_frames, dev)
+    ms = ubm._model_set()
+    n, f, s, _ = ms.stats(feats, seg)
+    n_spk, k, d = len(seg) - 1, ms.n_comp, ms.n_feat
+    flags = (1 if "means" in adapt else 0) | (2 if "weights" in adapt else 0) | (4 if "variances" in adapt else 0)
+    ow = torch.empty((n_spk, k), dtype=torch.float64, device=dev)
+    omu = torch.empty((n_spk, k, d), dtype=torch.float64, device=dev)
+    ovar = torch.empty((n_spk, k, d), dtype=torch.float64, device=dev)
+    uw, umu, uvar = ms._params
+    d_seg = torch.as_tensor(seg, device=dev)
+    rc = ms.lib.ssp_gmm_map_adapt(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), _lib.ptr(d_seg), n_spk, _lib.ptr(uw), _lib.ptr(umu),
+                                  _lib.ptr(uvar), k, d, float(relevance), flags, _lib.ptr(ow), _lib.ptr(omu), _lib.ptr(ovar),
+                                  _lib.stream_ptr())
+    _lib.check(rc, "ssp_gmm_map_adapt")
+    torch.cuda.current_stream().synchronize()
+    return ow, omu, ovar
+
+
+def identify(utts, speakers, ubm=None, precision="tf32", device=None):
+    """LLR matrix and decisions for all (utterance, speaker) pairs (GMM_UBM.py:191-197).
+
+    ``speakers``: :class:`ModelSet`, or list of fitted GaussianMixture-likes.  ``ubm``: fitted
+    GaussianMixture-like or None.  Returns ``(pred (N,S) float64 numpy, argmax (N,) int64)``.
+    The UBM term is constant per utterance, so decisions depend on the speaker scores only
+    (SURVEY F9); it is evaluated ONCE per utterance, not once per speaker.
+    """
+    torch = _lib.require_cuda()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    feats, offs = concat_utterances(utts, dev)
+    if isinstance(speakers, ModelSet):
+        ms = speakers
+    else:
+        ms = ModelSet(np.stack([np.asarray(m.weights_) for m in speakers]), np.stack([np.asarray(m.means_) for m in speakers]),
+                      np.stack([np.asarray(m.covariances_) for m in speakers]), device=dev)
+    scores, _ = ms.score(feats, offs, precision=precision)
+    if ubm is not None:
+        ums = ubm if isinstance(ubm, ModelSet) else ModelSet(ubm.weights_, ubm.means_, ubm.covariances_, device=dev)
+        base, _ = ums.score(feats, offs, precision=precision)
+        scores = scores - base
+    pred = scores.cpu().numpy()
+    return pred, pred.argmax(axis=1)
+
+
+label_encoder: dict = {}
+
+
+def GMM(train, x_train, y_train, x_test, y_test, n_components=16, model=False, label_encoder=None, random_state=None,
+        precision="tf32"):
+    """``GMM_UBM.GMM`` (GMM_UBM.py:134-199) on the GPU; prints the reference's result line and
+    returns ``(acc_train, acc_test, pred_test)`` (the reference returns None).
+
+    ``label_encoder`` defaults to this module's global of the same name, like the reference's
+    (GMM_UBM.py:21,154); if that is empty the speakers are the sorted keys of ``train``.
+    """
+    print("Train GMM-UBM model !")
+    t0 = time.time()
+    enc = label_encoder if label_encoder is not None else globals()["label_encoder"]
+    speakers = list(enc.values()) if enc else sorted(train.keys())
+    if model:
+        print("load model from file...")
+        with open("Model/GMM_MFCC_model.pkl", "rb") as f:
+            gmms = [GaussianMixture.from_sklearn(g) if not isinstance(g, GaussianMixture) else g for g in pkl.load(f)]
+        with open("Model/UBM_MFCC_model.pkl", "rb") as f:
+            u = pkl.load(f)
+            ubm = GaussianMixture.from_sklearn(u) if not isinstance(u, GaussianMixture) else u
+    else:
+        print("Train GMM!")
+        gmms = []
+        for spk in speakers:
+            gmms.append(GaussianMixture(n_components=n_components, covariance_type="diag", random_state=random_state).fit(train[spk]))
+        print("Train UBM!")
+        ubm_train = np.vstack([train[spk] for spk in speakers])
+        ubm = GaussianMixture(n_components=n_components, covariance_type="diag", random_state=random_state).fit(ubm_train)
+        os.makedirs("Model", exist_ok=True)
+        with open("Model/GMM_MFCC_model.pkl", "wb") as f:
+            pkl.dump([g.to_sklearn() for g in gmms], f)
+        with open("Model/UBM_MFCC_model.pkl", "wb") as f:
+            pkl.dump(ubm.to_sklearn(), f)
+    valid, arg_train = identify(x_train, gmms, ubm, precision=precision)
+    acc_train = float((arg_train == np.array(y_train)).sum() / len(x_train))
+    pred, arg = identify(x_test, gmms, ubm, precision=precision)
+    acc = float((arg == np.array(y_test)).sum() / len(x_test))
+    print("spend {:.2f}s, train acc {:.2%}, test acc {:.2%}".format(time.time() - t0, acc_train, acc))
+    return acc_train, acc, pred
+
+
+def install(gmm_ubm_module, delta_order: int = 1):
+    """Rebind the names GMM_UBM.py:16-20 imports so the reference script runs on the GPU:
+
+        import GMM_UBM, speech_signal_processing_b200 as ssp
+        ssp.install(GMM_UBM)
+        GMM_UBM.main()
+
+    ``mfcc`` returns the cepstra array (the contract ``delta(mfcc(x))`` at GMM_UBM.py:89-90 needs;
+    the stock sidekit list return raises there -- SURVEY F6).
+    """
+    def mfcc_cepstra(sig, **kw):
+        return fe.mfcc(sig, **kw)[0]
+
+    gmm_ubm_module.mfcc = mfcc_cepstra
+    gmm_ubm_module.delta = fe.delta
+    gmm_ubm_module.preprocessing = fe.preprocessing
+    gmm_ubm_module.GaussianMixture = GaussianMixture
+    return gmm_ubm_module

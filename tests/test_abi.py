@@ -1,0 +1,73 @@
+"""The C-ABI library builds, loads and exports every symbol include/ssp_b200.h declares.
+No compute calls: runs without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from speech_signal_processing_b200 import _lib, build
+
+    build.build()  # no-op when up to date; nvcc cross-compiles sm_100a without a GPU
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ssp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ssp_b200.h but not exported"
+
+
+def test_binding_covers_header(lib):
+    from speech_signal_processing_b200 import _lib
+
+    assert set(_lib.PROTOTYPES) == set(declared_symbols())
+    assert lib.ssp_abi_version() == 1
+
+
+def test_host_only_entry_points(lib):
+    """Pure host helpers of the ABI: frame counting rules and pack sizing."""
+    from speech_signal_processing_b200 import _lib
+
+    def cfg(framing):
+        return _lib.FrontendCfg(400, 160, 512, 24, 13, framing, 1, 0.97, 0, 1.0, 0, 0.0, 0.0, 1, 1, 2, 1, 0)
+
+    c0, c1, c2 = cfg(0), cfg(1), cfg(2)
+    # 1 s @ 16 kHz -> 98 frames (report/final.pdf p.5); psf 99+1; enframe ceil(N/step)
+    assert lib.ssp_frontend_num_frames(C.byref(c0), 16000) == 98
+    assert lib.ssp_frontend_num_frames(C.byref(c0), 48000) == 298
+    assert lib.ssp_frontend_num_frames(C.byref(c0), 399) == 0
+    assert lib.ssp_frontend_num_frames(C.byref(c1), 48000) == 299
+    assert lib.ssp_frontend_num_frames(C.byref(c1), 10) == 1
+    assert lib.ssp_frontend_num_frames(C.byref(c2), 48000) == 300
+    assert lib.ssp_frontend_num_frames(C.byref(c2), 0) == 0
+    assert lib.ssp_frontend_max_frames(C.byref(c0)) > 2998  # a 30 s utterance fits the fused kernel
+    bad = cfg(0)
+    bad.nfft = 400
+    assert lib.ssp_frontend_num_frames(C.byref(bad), 48000) == 0
+    d = _lib.GmmDims(1001, 1024, 39)
+    nbytes = lib.ssp_gmm_pack_bytes(C.byref(d))
+    assert nbytes >= 1001 * 1024 * (80 + 80 + 1) * 4  # tensor tiles + exact rows + constants
+    assert lib.ssp_gmm_pack_bytes(C.byref(_lib.GmmDims(1, 16, 81))) == 0
+    assert lib.ssp_gmm_pack_bytes(C.byref(_lib.GmmDims(0, 16, 13))) == 0
+
+
+def test_null_arguments_fail_without_touching_the_gpu(lib):
+    from speech_signal_processing_b200 import _lib
+
+    d = _lib.GmmDims(1, 16, 13)
+    assert lib.ssp_gmm_pack_models(None, None, None, C.byref(d), None, None) == -1
+    assert b"null" in lib.ssp_last_error()
+    assert lib.ssp_delta(None, 10, 13, 0, None, None) == -1

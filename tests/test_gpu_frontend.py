@@ -1,0 +1,132 @@
+"""Parity of the fused front-end kernel (through the C ABI) with the oracle / reference fixtures."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import speech_signal_processing_b200 as ssp  # noqa: E402
+from oracle import frontend as ofe  # noqa: E402
+from speech_signal_processing_b200 import synth  # noqa: E402
+
+# |delta| <= 1e-4 * max(1, |c|) against the float64 restatement
+def assert_ceps_close(got, want, tol=1e-4):
+    assert got.shape == want.shape
+    err = np.abs(got.astype(np.float64) - want) / np.maximum(1.0, np.abs(want))
+    assert err.max() <= tol, f"max scaled error {err.max():.3e}"
+
+
+def test_processing_MFCC_matches_reference_outputs(golden):
+    """utils.processing.MFCC run unmodified (fixtures) vs the kernel with the 'processing' tables."""
+    g = golden("processing_mfcc.npz")
+    for tag in "abd":
+        fs, fsz, step = (int(v) for v in g[f"{tag}_cfg"])
+        got = ssp.MFCC(g[f"{tag}_sig"], fs, fsz, step)
+        assert got.dtype == np.float64
+        assert_ceps_close(got, g[f"{tag}_mfcc"])
+    fs, fsz, step = (int(v) for v in g["c_cfg"])
+    with pytest.raises(NotImplementedError):
+        ssp.MFCC(g["c_sig"], fs, fsz, step)  # frameSize 400: FFT length must be a power of two
+
+
+@pytest.mark.parametrize("n_samples", [16000, 48000, 400, 12345])
+def test_sidekit_mfcc_matches_oracle(n_samples):
+    sig = synth.synth_utterance(5, n_samples % 97, n_samples)
+    out = ssp.mfcc(sig)
+    want = ofe.sidekit_mfcc(sig)
+    assert isinstance(out, list) and len(out) == 4 and out[2] is None and out[3] is None
+    assert out[0].dtype == np.float32
+    assert_ceps_close(out[0], want[0])
+    np.testing.assert_allclose(out[1], want[1], rtol=1e-5)
+
+
+def test_sidekit_shape_witness():
+    assert ssp.mfcc(synth.synth_utterance(1, 1, 16000))[0].shape == (98, 13)  # report/final.pdf p.5
+
+
+def test_too_short_utterance_gives_zero_frames():
+    out = ssp.mfcc(synth.synth_utterance(1, 2, 399))
+    assert out[0].shape == (0, 13) and out[1].shape == (0,)
+
+
+def test_float_pcm_equals_int16_pcm():
+    sig = synth.synth_utterance(7, 3, 16000)
+    a = ssp.mfcc(sig)[0]
+    b = ssp.mfcc(sig.astype(np.float64))[0]
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
+
+
+def test_psf_recipe_matches_oracle():
+    sig = synth.synth_utterance(9, 0, 16000 + 77)
+    fe = ssp.FrontEnd(ssp.psf_recipe())
+    feats, offs, _ = fe.extract([sig])
+    want = ofe.psf_mfcc(sig)
+    assert offs[-1] == want.shape[0]
+    assert_ceps_close(feats.cpu().numpy(), want)
+
+
+def test_delta_matches_reference(golden):
+    g = golden("delta.npz")
+    i = 0
+    while f"x{i}" in g.files:
+        got = ssp.delta(g[f"x{i}"], int(g[f"n{i}"]))
+        np.testing.assert_allclose(got, g[f"d{i}"], atol=2e-6)
+        i += 1
+    with pytest.raises(ValueError):
+        ssp.delta(g["x0"], 0)
+
+
+def test_scale_matches_sklearn(golden):
+    g = golden("sklearn_gmm.npz")
+    got = ssp.scale(g["scale_x"])
+    np.testing.assert_allclose(got, g["scale_y"], atol=2e-5)
+    assert np.all(got[:, 3] == 0)  # constant column: std 0 -> divisor 1
+
+
+def test_extract_feature_matches_reference_pipeline(golden):
+    """GMM_UBM.extract_feature (run unmodified with the sidekit restatement as mfcc) vs ONE launch."""
+    g = golden("pipeline.npz")
+    x = list(g["x_test"])
+    feature, y = ssp.extract_feature(x, list(g["y_test"]))
+    assert len(feature) == len(x)
+    for j in range(len(x)):
+        assert feature[j].shape == (98, 26)
+        np.testing.assert_allclose(feature[j], g["feat_test"][j], atol=2e-4)
+    train, feature, y = ssp.extract_feature(list(g["x_train"]), list(g["y_train"]), is_train=True)
+    assert sorted(train) == sorted(set(g["y_train"].tolist()))
+    lab0 = int(g["y_train"][0])
+    np.testing.assert_allclose(train[lab0][:98], g["feat_train0"], atol=2e-4)
+
+
+def test_39_dim_features_ragged_batch():
+    """c + delta + delta-delta with CMVN on a ragged batch == oracle per utterance."""
+    lens = [16000, 400, 20000, 399, 4321, 48000]
+    sigs = [synth.synth_utterance(3 + i, i, n) for i, n in enumerate(lens)]
+    fe = ssp.FrontEnd(ssp.sidekit_recipe(), delta_order=2, cmvn=True)
+    feats, offs, _ = fe.extract(sigs)
+    feats = feats.cpu().numpy()
+    assert feats.shape[1] == 39
+    for i, s in enumerate(sigs):
+        got = feats[offs[i] : offs[i + 1]]
+        if len(s) < 400:
+            assert got.shape[0] == 0
+            continue
+        want = ofe.features(s, preset="sidekit", delta_order=2, cmvn=True)
+        assert got.shape == want.shape
+        if got.shape[0] > 1:
+            np.testing.assert_allclose(got, want, atol=5e-4)
+
+
+def test_long_utterance_30s():
+    sig = synth.synth_utterance(2, 5, 480000)
+    fe = ssp.FrontEnd(ssp.sidekit_recipe(), delta_order=2, cmvn=False)
+    feats, offs, _ = fe.extract([sig])
+    assert offs[-1] == 2998
+    c = ofe.sidekit_mfcc(sig)[0]
+    want = np.hstack([c, ofe.delta(c), ofe.delta(ofe.delta(c))])
+    assert_ceps_close(feats.cpu().numpy(), want)
+
+
+def test_utterance_beyond_fused_bound_raises():
+    sig = synth.synth_utterance(2, 6, 16000 * 60)
+    with pytest.raises(NotImplementedError):
+        ssp.mfcc(sig)

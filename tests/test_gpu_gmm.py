@@ -1,0 +1,207 @@
+"""Parity of the GMM kernels (through the C ABI) with sklearn fixtures and the oracle."""
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import speech_signal_processing_b200 as ssp  # noqa: E402
+from oracle import gmm as ogmm  # noqa: E402
+from speech_signal_processing_b200 import synth  # noqa: E402
+
+# north-star tolerance: log-likelihoods within 1e-4 relative; fp32 path is held to 2e-6
+REL = {"fp32": 2e-6, "tf32": 1e-4}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("tag", ["s", "m", "l"])
+def test_score_matches_sklearn(golden, tag, precision):
+    g = golden("sklearn_gmm.npz")
+    gm = ssp.GaussianMixture.from_params(g[f"{tag}_w"], g[f"{tag}_mu"], g[f"{tag}_var"], precision=precision)
+    x = g[f"{tag}_x"]
+    want = g[f"{tag}_score_samples"]
+    got = gm.score_samples(x)
+    assert got.shape == want.shape
+    # per-frame: TF32 operand rounding gives ~1e-3 absolute on |L| ~ 50
+    tol = 5e-5 if precision == "fp32" else 3e-2
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+    s = gm.score(x)
+    assert isinstance(s, float)
+    assert abs(s - float(g[f"{tag}_score"])) <= REL[precision] * abs(float(g[f"{tag}_score"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_score_matrix_ragged_matches_oracle(precision):
+    k, d, n_spk = 64, 39, 5
+    w, mu, var = synth.synth_ubm(k, d, seed=3)
+    spk_mu = synth.synth_speaker_means(mu, n_spk, seed=4)
+    lens = [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 298, 500]
+    utts = [synth.sample_gmm(w, spk_mu[i % n_spk], var, n, seed=100 + i) for i, n in enumerate(lens)]
+    models = [ssp.GaussianMixture.from_params(w, spk_mu[i], var) for i in range(n_spk)]
+    got = ssp.score_matrix(utts, models, precision=precision)
+    want = np.array([[ogmm.score(u, w, spk_mu[i], var) for i in range(n_spk)] for u in utts])
+    np.testing.assert_allclose(got, want, rtol=REL[precision] * (10 if precision == "tf32" else 1), atol=0)
+    long_enough = np.array(lens) >= 31
+    np.testing.assert_allclose(got[long_enough], want[long_enough], rtol=REL[precision], atol=0)
+    assert (got.argmax(axis=1) == want.argmax(axis=1))[long_enough].all()
+
+
+def test_tf32_matches_fp32_kernel_1024_components():
+    """Property at scale: the tensor-core and CUDA-core kernels agree; argmax identical."""
+    k, d, n_spk = 1024, 39, 24
+    w, mu, var = synth.synth_ubm(k, d, seed=5)
+    spk_mu = synth.synth_speaker_means(mu, n_spk, seed=6, shift=0.25)
+    ms = ssp.ModelSet(np.tile(w, (n_spk, 1)), spk_mu, np.tile(var, (n_spk, 1, 1)))
+    lens = [298] * 40 + [98, 777, 5]
+    utts = [synth.sample_gmm(w, spk_mu[i % n_spk], var, n, seed=i) for i, n in enumerate(lens)]
+    a = ssp.score_matrix(utts, ms, precision="fp32")
+    b = ssp.score_matrix(utts, ms, precision="tf32")
+    np.testing.assert_allclose(b[:42], a[:42], rtol=1e-4, atol=0)
+    assert (a.argmax(axis=1) == b.argmax(axis=1))[:42].all()
+    assert (a.argmax(axis=1)[:40] == np.arange(40) % n_spk).all()
+    # oracle spot check on a few pairs (float64)
+    for j in (0, 17, 41):
+        for i in (0, 5):
+            ref = ogmm.score(utts[j], w, spk_mu[i], var)
+            assert abs(a[j, i] - ref) <= 2e-6 * abs(ref)
+            assert abs(b[j, i] - ref) <= 1e-4 * abs(ref)
+
+
+def test_split_utterance_property():
+    """score(whole) == frame-weighted mean of score(parts) (mean of per-frame log-likelihoods)."""
+    k, d = 128, 26
+    w, mu, var = synth.synth_ubm(k, d, seed=8)
+    x = synth.sample_gmm(w, mu, var, 1000, seed=9)
+    ms = ssp.ModelSet(w, mu, var)
+    for precision in ("fp32", "tf32"):
+        whole = ssp.score_matrix([x], ms, precision=precision)[0, 0]
+        parts = ssp.score_matrix([x[:300], x[300:], x[:0]], ms, precision=precision)[:, 0]
+        assert abs(whole - (0.3 * parts[0] + 0.7 * parts[1])) < 1e-6 * abs(whole)
+        assert parts[2] == 0.0  # empty utterance: no frames, score left at 0
+
+
+@pytest.mark.parametrize("k,d", [(8, 5), (64, 26), (200, 39), (16, 13), (32, 60)])
+def test_stats_match_oracle(k, d):
+    w, mu, var = synth.synth_ubm(k, d, seed=k + d)
+    lens = [0, 700, 64, 1, 130, 0, 2048 + 17]
+    x = synth.sample_gmm(w, mu * 0.8, var * 1.2, sum(lens), seed=1)
+    seg = np.concatenate([[0], np.cumsum(lens)])
+    ms = ssp.ModelSet(w, mu, var)
+    import torch
+
+    n, f, s, ll = ms.stats(torch.as_tensor(x, device="cuda"), seg)
+    n, f, s, ll = (t.cpu().numpy() for t in (n, f, s, ll))
+    for i, ln in enumerate(lens):
+        xs = x[seg[i] : seg[i + 1]].astype(np.float64)
+        if ln == 0:
+            assert np.all(n[i] == 0) and np.all(f[i] == 0) and ll[i] == 0
+            continue
+        rn, rf, rs_, rll = ogmm.suff_stats(xs, w, mu, var)
+        np.testing.assert_allclose(n[i], rn, rtol=2e-4, atol=2e-4 * ln / k)
+        np.testing.assert_allclose(f[i], rf, rtol=2e-4, atol=5e-4 * ln / k)
+        np.testing.assert_allclose(s[i], rs_, rtol=2e-4, atol=1e-3 * ln / k)
+        assert abs(ll[i] - rll) <= 2e-6 * abs(rll)
+        assert abs(n[i].sum() - ln) < 1e-3 * ln  # posteriors sum to one per frame
+
+
+@pytest.mark.parametrize("tag", ["s", "m"])
+@pytest.mark.parametrize("iters", [1, 3, 100])
+def test_em_trajectory_matches_sklearn(golden, tag, iters):
+    """Same initial parameters in => same EM trajectory out."""
+    import warnings
+
+    g = golden("sklearn_gmm.npz")
+    w, mu, var, x = g[f"{tag}_w"], g[f"{tag}_mu"], g[f"{tag}_var"], g[f"{tag}_x"]
+    gm = ssp.GaussianMixture(n_components=len(w), covariance_type="diag", weights_init=w, means_init=mu,
+                             precisions_init=1.0 / var, max_iter=iters)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gm.fit(x)
+    assert gm.n_iter_ == int(g[f"{tag}_fit{iters}_niter"])
+    assert gm.converged_ == bool(g[f"{tag}_fit{iters}_conv"])
+    assert abs(gm.lower_bound_ - float(g[f"{tag}_fit{iters}_lb"])) < 2e-5 * abs(float(g[f"{tag}_fit{iters}_lb"]))
+    loose = 1.0 if iters == 100 else 0.1  # fp32 E-step differences compound over ~dozens of iterations
+    np.testing.assert_allclose(gm.weights_, g[f"{tag}_fit{iters}_w"], rtol=1e-2 * loose, atol=1e-4 * loose)
+    np.testing.assert_allclose(gm.means_, g[f"{tag}_fit{iters}_mu"], rtol=0, atol=2e-2 * loose)
+    np.testing.assert_allclose(gm.covariances_, g[f"{tag}_fit{iters}_var"], rtol=5e-2 * loose, atol=1e-3)
+    np.testing.assert_allclose(gm.precisions_cholesky_, 1 / np.sqrt(gm.covariances_))
+
+
+def test_fit_default_init_and_errors():
+    w, mu, var = synth.synth_ubm(8, 6, seed=21, spread=4.0)
+    x = synth.sample_gmm(w, mu, var * 0.3, 4000, seed=22)
+    gm = ssp.GaussianMixture(n_components=8, covariance_type="diag", random_state=0).fit(x)
+    assert gm.converged_ and gm.weights_.shape == (8,) and np.isclose(gm.weights_.sum(), 1.0)
+    truth = ogmm.score(x, w, mu, var * 0.3)
+    assert gm.score(x) > truth - 0.25  # well-separated clusters: EM from k-means gets near the truth
+    assert all(b2 >= b1 - 1e-4 for b1, b2 in zip(gm.lower_bounds_, gm.lower_bounds_[1:]))  # EM is monotone
+    with pytest.raises(ValueError, match="n_samples >= n_components"):
+        ssp.GaussianMixture(n_components=64).fit(x[:10])
+    with pytest.raises(NotImplementedError):
+        ssp.GaussianMixture(n_components=2, covariance_type="full").fit(x)
+    g2 = pickle.loads(pickle.dumps(gm))
+    assert abs(g2.score(x) - gm.score(x)) < 1e-9
+    sk = gm.to_sklearn()
+    assert abs(sk.score(x.astype(np.float64)) - gm.score(x)) < 1e-4 * abs(gm.score(x))
+
+
+def test_map_adapt_matches_oracle():
+    k, d, n_spk = 32, 13, 6
+    w, mu, var = synth.synth_ubm(k, d, seed=31)
+    ubm = ssp.GaussianMixture.from_params(w, mu, var)
+    spk_mu = synth.synth_speaker_means(mu, n_spk, seed=32, shift=0.5)
+    frames = [synth.sample_gmm(w, spk_mu[i], var, 300 + 50 * i, seed=40 + i) for i in range(n_spk)]
+    for adapt in (("means",), ("means", "weights", "variances")):
+        ow, omu, ovar = (t.cpu().numpy() for t in ssp.map_adapt(ubm, frames, relevance=16.0, adapt=adapt))
+        for i in range(n_spk):
+            n, f, s, _ = ogmm.suff_stats(frames[i].astype(np.float64), w, mu, var)
+            rw, rmu, rvar = ogmm.map_adapt(n, f, s, w, mu, var, len(frames[i]), 16.0, adapt)
+            np.testing.assert_allclose(omu[i], rmu, atol=2e-4)
+            np.testing.assert_allclose(ow[i], rw, atol=1e-5)
+            np.testing.assert_allclose(ovar[i], rvar, rtol=1e-3, atol=1e-3)
+
+
+def test_reference_pipeline_decisions(golden, tmp_path, monkeypatch):
+    """GMM_UBM.GMM(model=True): models trained by the unmodified reference, scored on the GPU:
+    the pred matrix matches GMM_UBM.py:194 and every argmax decision is identical."""
+    from sklearn.mixture import GaussianMixture as SkGM
+
+    g = golden("pipeline.npz")
+
+    def sk(wt, m, v):
+        e = SkGM(n_components=len(wt), covariance_type="diag")
+        e.weights_, e.means_, e.covariances_ = wt, m, v
+        e.precisions_cholesky_ = 1 / np.sqrt(v)
+        return e
+
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "Model").mkdir()
+    with open("Model/GMM_MFCC_model.pkl", "wb") as f:
+        pickle.dump([sk(g["gmm_w"][i], g["gmm_mu"][i], g["gmm_var"][i]) for i in range(4)], f)
+    with open("Model/UBM_MFCC_model.pkl", "wb") as f:
+        pickle.dump(sk(g["ubm_w"], g["ubm_mu"], g["ubm_var"]), f)
+    feats = [x.astype(np.float32) for x in g["feat_test"]]
+    for precision in ("fp32", "tf32"):
+        acc_tr, acc, pred = ssp.GMM({}, feats, list(g["y_test"]), feats, list(g["y_test"]), n_components=4, model=True,
+                                    precision=precision)
+        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=2e-4 if precision == "fp32" else 2e-3)
+        assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
+        assert f"test acc {acc:.2%}" in str(g["printed"])
+
+
+def test_GMM_trains_and_identifies(tmp_path, monkeypatch):
+    """End to end on the GPU: audio -> extract_feature -> GMM() (train + identify), config 1 shape."""
+    monkeypatch.chdir(tmp_path)
+    x, y = synth.synth_corpus(4, 8, 16000)
+    idx = np.random.RandomState(0).permutation(len(x))
+    tr, te = idx[:22], idx[22:]
+    train, f_tr, y_tr = ssp.extract_feature([x[i] for i in tr], [y[i] for i in tr], is_train=True)
+    f_te, y_te = ssp.extract_feature([x[i] for i in te], [y[i] for i in te])
+    acc_tr, acc, pred = ssp.GMM(train, f_tr, y_tr, f_te, y_te, n_components=4, random_state=0)
+    assert acc_tr >= 0.9 and acc >= 0.6
+    assert (tmp_path / "Model" / "GMM_MFCC_model.pkl").exists()
+    with open(tmp_path / "Model" / "UBM_MFCC_model.pkl", "rb") as f:
+        ubm = pickle.load(f)  # a stock sklearn estimator the reference GUIs can consume
+    assert type(ubm).__module__.startswith("sklearn")
+    assert np.isfinite(ubm.score(f_te[0].astype(np.float64)))
