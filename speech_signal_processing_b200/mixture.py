@@ -145,13 +145,19 @@ class GaussianMixture:
     ``random_state=None``, so its own runs are not reproducible either -- SURVEY F7); parity with
     sklearn is defined for given ``weights_init/means_init/precisions_init``.
 
+    ``precision`` selects the scoring kernel of ``score`` / ``score_samples``: ``"fp32"`` (default: CUDA-core
+    FMA, ~1e-7 relative, safe for any data) or ``"tf32"`` (tcgen05 tensor cores; meant for CMVN-normalised
+    features, where the single-pass TF32 operand rounding stays within 1e-4 relative of the utterance score --
+    on un-normalised data with |x - mu| >> sigma the expanded form loses digits).  The batched
+    :func:`score_matrix` / ``identify`` default to ``"tf32"``.
+
     ``comm``: optional :class:`speech_signal_processing_b200.dist.Comm`; when given, ``fit`` treats X as
     this rank's shard of the frames and all-reduces the statistics tensor each EM iteration (NCCL).
     """
 
     def __init__(self, n_components=1, *, covariance_type="diag", tol=1e-3, reg_covar=1e-6, max_iter=100, n_init=1,
                  init_params="kmeans", weights_init=None, means_init=None, precisions_init=None, random_state=None,
-                 warm_start=False, verbose=0, verbose_interval=10, precision="auto", comm=None):
+                 warm_start=False, verbose=0, verbose_interval=10, precision="fp32", comm=None):
         self.n_components = n_components
         self.covariance_type = covariance_type
         self.tol = tol
@@ -225,12 +231,26 @@ class GaussianMixture:
         k = self.n_components
         comm = self.comm if (self.comm is not None and self.comm.world_size > 1) else None
 
-        def seed_rows(count):
-            """`count` random frames, identical on every rank (rank 0 draws from its shard)."""
+        def seed_rows(count, avoid=None):
+            """`count` seed frames, identical on every rank (rank 0 draws from its shard): k-means++
+            D^2 sampling (the seeding sklearn's KMeans uses) over a random subsample of <= 20k frames;
+            control logic on device tensors, no host round trip per seed."""
             rows = torch.zeros((count, d), dtype=torch.float64, device=feats.device)
             if comm is None or comm.rank == 0:
-                pick = rs.choice(n_frames, size=count, replace=False)
-                rows = feats[torch.as_tensor(pick, device=feats.device)].to(torch.float64)
+                m = int(min(n_frames, max(20 * k, 4096)))
+                sub = feats[torch.as_tensor(rs.choice(n_frames, size=m, replace=False), device=feats.device)].to(torch.float64)
+                u = torch.as_tensor(rs.uniform(size=count), device=feats.device)
+                if avoid is None:
+                    rows[0] = sub[int(rs.randint(m))]
+                    d2 = ((sub - rows[0]) ** 2).sum(dim=1)
+                    start = 1
+                else:
+                    d2 = torch.cdist(sub, avoid).min(dim=1).values ** 2
+                    start = 0
+                for i in range(start, count):
+                    j = torch.searchsorted(d2.cumsum(0), u[i] * d2.sum()).clamp_(max=m - 1)
+                    rows[i] = sub[j]
+                    d2 = torch.minimum(d2, ((sub - rows[i]) ** 2).sum(dim=1))
             return comm.broadcast(rows.contiguous()) if comm is not None else rows
 
         def reduced(t):
@@ -241,7 +261,8 @@ class GaussianMixture:
         m1 = reduced(feats.to(torch.float64).sum(dim=0)) / cnt
         m2 = reduced((feats.to(torch.float64) ** 2).sum(dim=0)) / cnt
         gvar = (m2 - m1 * m1).clamp_min(1e-12)
-        sharp = (0.02 * gvar)[None, None].expand(1, k, d).contiguous()
+        # one spherical variance: the hard assignment is then the nearest centre in Euclidean distance
+        sharp = (0.02 * gvar.mean()).expand(1, k, d).contiguous()
         w.fill_(1.0 / k)
         ms = ModelSet(w, mu, sharp, device=feats.device)
         for it in range(iters + 1):
@@ -258,7 +279,7 @@ class GaussianMixture:
             w.fill_(1.0 / k)
             empty = (n[0] < 0.5).nonzero().flatten()
             if empty.numel():
-                mu[0, empty] = seed_rows(int(empty.numel()))
+                mu[0, empty] = seed_rows(int(empty.numel()), avoid=mu[0])
 
     def fit(self, X, y=None):
         """Estimate parameters with EM (sklearn/mixture/_base.py:203-312)."""

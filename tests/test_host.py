@@ -1,0 +1,148 @@
+"""Host-side logic that needs no GPU: recipe tables, sharding, the N>1 reduction path over gloo,
+and the guarantees that the product never routes through the oracle or a CPU fallback."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import speech_signal_processing_b200 as ssp
+from oracle import frontend as ofe
+from oracle import gmm as ogmm
+from speech_signal_processing_b200 import dist as sdist
+from speech_signal_processing_b200 import frontend as pfe
+from speech_signal_processing_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_recipe_tables_match_oracle(golden):
+    r = ssp.sidekit_recipe()
+    assert (r.frame_len, r.frame_shift, r.nfft, r.framing, r.preemph_mode) == (400, 160, 512, 0, 1)
+    np.testing.assert_allclose(r.fbank, ofe.sidekit_trfbank(16000, 512, 100, 8000, 0, 24)[0], atol=1e-15)
+    np.testing.assert_allclose(r.dct, ofe.dct2_ortho_matrix(13, 24, first=1), atol=1e-15)
+    np.testing.assert_allclose(r.window, np.hanning(400), atol=1e-15)
+    p = ssp.psf_recipe()
+    np.testing.assert_allclose(p.fbank, ofe.psf_filterbanks(), atol=1e-15)
+    assert p.fbank.shape == (26, 257) and p.window.min() == 1.0 and p.energy_mode == 2
+    # the 'processing' filterbank is pinned by the reference's own mfccInitFilterBanks output
+    g = golden("processing_mfcc.npz")
+    for fs, key in ((16000, "fbank_16k_512"), (8000, "fbank_8k_512")):
+        two_sided = g[key]
+        folded = pfe.processing_filterbank(fs, 512)
+        x = np.abs(np.fft.fft(np.random.RandomState(0).standard_normal(512)))
+        np.testing.assert_allclose(folded @ x[:257], two_sided @ x, rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        ssp.processing_recipe(16000, 400, 160)
+
+
+def test_dct_rows_and_lifter():
+    np.testing.assert_allclose(pfe.dct_rows(13, 26), ofe.dct2_ortho_matrix(13, 26), atol=1e-15)
+    lift = 1 + 11 * np.sin(np.pi * np.arange(13) / 22)
+    np.testing.assert_allclose(ssp.psf_recipe().dct, ofe.dct2_ortho_matrix(13, 26) * lift[:, None], atol=1e-14)
+
+
+def test_shard_helpers():
+    for n, w in [(10, 3), (7, 8), (10000, 8), (0, 2)]:
+        spans = [sdist.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    lens = np.random.RandomState(1).randint(98, 2998, size=200)
+    parts = sdist.shard_by_load(lens, 8)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(200))
+    loads = [lens[p].sum() for p in parts]
+    assert (max(loads) - min(loads)) <= lens.max()
+
+
+def test_product_never_imports_the_oracle_or_reference():
+    pkg = os.path.join(ROOT, "speech_signal_processing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ssp.mfcc(np.zeros(16000, dtype=np.int16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ssp.GaussianMixture(n_components=2).fit(np.zeros((10, 3)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ssp.delta(np.zeros((10, 13)))
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+from speech_signal_processing_b200.dist import Comm, shard_range
+from speech_signal_processing_b200 import synth
+from oracle import gmm as ogmm
+comm = Comm("gloo")
+w, mu, var = synth.synth_ubm(16, 7, seed=5)
+x = synth.sample_gmm(w, mu, var, 1001, seed=6).astype(np.float64)
+lo, hi = shard_range(len(x), comm.rank, comm.world_size)
+n, f, s, ll = ogmm.suff_stats(x[lo:hi], w, mu, var)
+flat = torch.from_numpy(np.concatenate([n.ravel(), f.ravel(), s.ravel(), [ll, hi - lo]]))
+comm.allreduce_sum(flat)
+rn, rf, rs, rll = ogmm.suff_stats(x, w, mu, var)
+ref = np.concatenate([rn.ravel(), rf.ravel(), rs.ravel(), [rll, len(x)]])
+assert np.allclose(flat.numpy(), ref, rtol=1e-10, atol=1e-9), np.abs(flat.numpy() - ref).max()
+# replicated M-step from the reduced statistics == unsharded M-step
+k, d = 16, 7
+a = flat.numpy()
+w2, mu2, var2 = ogmm.m_step(a[:k], a[k:k + k * d].reshape(k, d), a[k + k * d:k + 2 * k * d].reshape(k, d))
+w1, mu1, var1 = ogmm.m_step(rn, rf, rs)
+assert np.allclose(mu1, mu2) and np.allclose(var1, var2) and np.allclose(w1, w2)
+rows = torch.arange(hi - lo, dtype=torch.float64)[:, None] + 100.0 * comm.rank
+full = comm.gather_rows(rows, [shard_range(len(x), r, comm.world_size)[1] - shard_range(len(x), r, comm.world_size)[0]
+                               for r in range(comm.world_size)])
+assert full.shape[0] == len(x)
+b = torch.tensor([float(comm.rank)])
+comm.broadcast(b, 0)
+assert b.item() == 0.0
+comm.barrier()
+print("rank", comm.rank, "ok")
+"""
+
+
+def test_sharded_statistics_allreduce_gloo_world2(tmp_path):
+    """N/F/S of frame shards all-reduced over gloo (world_size 2) == unsharded statistics; the M-step
+    from the reduced tensor == the unsharded M-step (UBM EM)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    port = 29600 + (os.getpid() % 300)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                      text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """bench.py --impl reference: one JSON line with the contract keys (tiny sizes)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--speakers", "6", "--components", "16", "--cpu-utts", "2"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
