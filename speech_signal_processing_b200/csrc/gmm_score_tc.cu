@@ -104,6 +104,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// one lane of a converged warp (the role loops below stay warp-uniform so that descriptors live in uniform
+// registers and each tcgen05.mma costs a handful of issue slots, not a divergent elect loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -118,6 +129,100 @@ __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// ---- epilogue building blocks --------------------------------------------------------------------------
+// tcgen05.ld without the wait, so that the next 32 columns are in flight while the current ones are consumed
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for all outstanding tcgen05.ld of this thread; the empty asms tie the registers to the wait so the
+// compiler cannot hoist arithmetic on them above it
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+               "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return d;
+}
+
+// Sum of 2^(v - m_stab) over 32 accumulator columns of one row, plus their maximum.
+//
+// m_stab is a stabiliser chosen BEFORE the tile is seen (the previous model's maximum for this frame: speaker
+// models adapted from one UBM peak within a few units of each other), so the exponentials do not depend on the
+// tile's own maximum and the whole tile is one dependency-free instruction stream; the caller checks the
+// maximum afterwards and redoes the tile on the (rare) rows where the stabiliser was off by more than 2^64.
+//
+// The MUFU (16 ex2/clk/SM) would otherwise be the binding pipe, so kPolyPairs of the 16 column pairs are
+// evaluated on the FMA pipe: 2^x = 2^n * p(f), n = round(x) via the 1.5*2^23 magic add, f = x - n in
+// [-0.5, 0.5], p = degree-4 minimax polynomial (max relative error 2.7e-6), 2^n applied by adding n to the
+// exponent field.  Packed FADD2 / FFMA2 halve the issue slots; FMNMX3 halves the max chain.
+constexpr int kPolyPairs = 6;
+__device__ __forceinline__ void chunk_sum(const uint32_t (&r)[32], float m_stab, float2& accp, float2& accm0, float2& accm1,
+                                          float& cmax) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  float cm = max3(v[0], v[1], v[2]);
+#pragma unroll
+  for (int i = 3; i < 31; i += 2) cm = max3(cm, v[i], v[i + 1]);
+  cmax = max3(cmax, cm, v[31]);
+  const float2 nm = make_float2(-m_stab, -m_stab);
+  const float MAGIC = 12582912.f;  // 1.5 * 2^23
+  const float2 mg = make_float2(MAGIC, MAGIC), nmg = make_float2(-MAGIC, -MAGIC), neg1 = make_float2(-1.f, -1.f);
+  const float2 c0 = make_float2(0.9999992847442627f, 0.9999992847442627f);
+  const float2 c1 = make_float2(0.6931218504905701f, 0.6931218504905701f);
+  const float2 c2 = make_float2(0.240247443318367f, 0.240247443318367f);
+  const float2 c3 = make_float2(0.05591766536235809f, 0.05591766536235809f);
+  const float2 c4 = make_float2(0.009570018388330936f, 0.009570018388330936f);
+#pragma unroll
+  for (int i = 0; i < kPolyPairs; ++i) {
+    float2 d = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), nm);
+    d.x = fmaxf(d.x, -126.f);
+    d.y = fmaxf(d.y, -126.f);
+    const float2 t = __fadd2_rn(d, mg);
+    const float2 nn = __fadd2_rn(t, nmg);
+    const float2 f = __ffma2_rn(nn, neg1, d);
+    float2 p = __ffma2_rn(c4, f, c3);
+    p = __ffma2_rn(p, f, c2);
+    p = __ffma2_rn(p, f, c1);
+    p = __ffma2_rn(p, f, c0);
+    float2 e;
+    e.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    accp = __fadd2_rn(accp, e);
+  }
+#pragma unroll
+  for (int i = kPolyPairs; i < 16; i += 2) {
+    const float2 d0 = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), nm);
+    const float2 d1 = __fadd2_rn(make_float2(v[2 * i + 2], v[2 * i + 3]), nm);
+    accm0 = __fadd2_rn(accm0, make_float2(ex2(d0.x), ex2(d0.y)));
+    accm1 = __fadd2_rn(accm1, make_float2(ex2(d1.x), ex2(d1.y)));
+  }
+}
+// plain MUFU version used by the redo path
+__device__ __forceinline__ float chunk_sum_exact(const uint32_t (&r)[32], float m) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    a0 += ex2(__uint_as_float(r[i]) - m);
+    a1 += ex2(__uint_as_float(r[i + 1]) - m);
+  }
+  return a0 + a1;
 }
 
 // K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, sm_100 "version 1"):
@@ -187,50 +292,55 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
 
   if (warp == 0) {
     // ===================== producer: stream every model's tiles, once per unit =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-        for (int t = 0; t < tiles_per_unit; ++t, ++it) {
-          const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-          mbar_wait(b_empty + stage, ph ^ 1u);
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int t = 0; t < tiles_per_unit; ++t, ++it) {
+        const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+        mbar_wait(b_empty + stage, ph ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(b_full + stage, tile_bytes);
           bulk_g2s(sB + (size_t)stage * tile_bytes, a.tiles + (size_t)t * tile_floats, tile_bytes, b_full + stage);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t lbo = BM * 16u, sbo = 128u;  // chunk stride = 128 rows x 16 B; 8-row groups are contiguous
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      uint32_t it = 0, q = 0, unit_idx = 0;
-      for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
-        mbar_wait(a_full, unit_idx & 1u);
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    constexpr uint32_t lbo = BM * 16u, sbo = 128u;  // chunk stride = 128 rows x 16 B; 8-row groups are contiguous
+    constexpr uint32_t kstep = (2u * lbo) >> 4;      // one K=8 step = two 16-byte chunks, in descriptor address units
+    const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo, sbo);
+    const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo, sbo);
+    const uint32_t tile_units = tile_bytes >> 4;
+    const int ksteps = KD >> 3;
+    uint32_t it = 0, q = 0, unit_idx = 0;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
+      mbar_wait(a_full, unit_idx & 1u);
+      tc_fence_after();
+      for (int t = 0; t < tiles_per_unit; ++t, ++it) {
+        const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+        mbar_wait(b_full + stage, ph);
         tc_fence_after();
-        for (int t = 0; t < tiles_per_unit; ++t, ++it) {
-          const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-          mbar_wait(b_full + stage, ph);
-          tc_fence_after();
+        const uint64_t bd0 = b_desc0 + (uint64_t)(stage * tile_units);
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb, ++q) {
-            const uint32_t slot = q % NSLOT, sph = (q / NSLOT) & 1u;
-            mbar_wait(t_empty + slot, sph ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + slot * BN;
-            for (int k = 0; k < (KD >> 3); ++k) {
-              const uint64_t ad = make_desc(a_base + mb * tile_bytes + k * 2u * lbo, lbo, sbo);
-              const uint64_t bd = make_desc(b_base + stage * tile_bytes + k * 2u * lbo, lbo, sbo);
-              tc_mma_tf32(d_tmem, ad, bd, kIdesc, k > 0 ? 1u : 0u);
-            }
+        for (int mb = 0; mb < MB; ++mb, ++q) {
+          const uint32_t slot = q % NSLOT, sph = (q / NSLOT) & 1u;
+          mbar_wait(t_empty + slot, sph ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + slot * BN;
+          const uint64_t ad0 = a_desc0 + (uint64_t)(mb * tile_units);
+          if (elect_one()) {
+            tc_mma_tf32(d_tmem, ad0, bd0, kIdesc, 0u);
+            for (int k = 1; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), kIdesc, 1u);
             tc_commit(t_full + slot);
           }
-          tc_commit(b_empty + stage);
+          __syncwarp();
         }
-        tc_commit(a_empty);
+        if (elect_one()) tc_commit(b_empty + stage);
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(a_empty);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== epilogue warps (also build the A operand) =====================
     const int etid = tid - 64;                 // 0..255: row of the unit this thread BUILDS
@@ -266,34 +376,54 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
       float wgt = 1.f;
       if (utt >= 0 && a.normalize) wgt = 1.f / (float)(a.offsets[utt + 1] - a.offsets[utt]);
 
+      float m_stab = -3.0e38f;  // carried from model to model (see chunk_sum)
       for (int model = 0; model < a.n_models; ++model) {
-        float m_run = -3.0e38f, s_run = 0.f;
+        float s_run = 0.f;
         for (int t = 0; t < a.tiles_per_model; ++t, ++n) {
           const uint32_t slot = 2u * (n & 1u) + (uint32_t)g, ph = (n >> 1) & 1u;
           mbar_wait(t_full + slot, ph);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + slot * BN;
+          // 4 x 32 columns, double-buffered through two register banks
+          uint32_t ra[32], rb[32];
+          float2 accp = make_float2(0.f, 0.f), accm0 = make_float2(0.f, 0.f), accm1 = make_float2(0.f, 0.f);
+          float cmax = -3.0e38f;
+          tc_ld32_issue(taddr, ra);
+          tc_ld_wait(ra);
+          tc_ld32_issue(taddr + 32, rb);
+          chunk_sum(ra, m_stab, accp, accm0, accm1, cmax);
+          tc_ld_wait(rb);
+          tc_ld32_issue(taddr + 64, ra);
+          chunk_sum(rb, m_stab, accp, accm0, accm1, cmax);
+          tc_ld_wait(ra);
+          tc_ld32_issue(taddr + 96, rb);
+          chunk_sum(ra, m_stab, accp, accm0, accm1, cmax);
+          tc_ld_wait(rb);
+          chunk_sum(rb, m_stab, accp, accm0, accm1, cmax);
+          const float2 tot = __fadd2_rn(__fadd2_rn(accm0, accm1), accp);
+          float s_tile = tot.x + tot.y;
+          // stabiliser check: too low (overflow risk) on any tile, too high (underflow of everything) on a
+          // model's first tile.  Warp-uniform branch: the redo re-reads TMEM with .sync.aligned loads.
+          const bool redo = (cmax > m_stab + 64.f) || (t == 0 && cmax < m_stab - 64.f);
+          if (__any_sync(0xffffffffu, redo)) {
+            float s_new = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            float v[32];
-            tc_ld32(taddr + c * 32, v);
-            float cmax = v[0];
-#pragma unroll
-            for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
-            const float m_new = fmaxf(m_run, cmax);
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              acc0 += ex2(v[i] - m_new);
-              acc1 += ex2(v[i + 1] - m_new);
+            for (int c = 0; c < BN / 32; ++c) {
+              tc_ld32_issue(taddr + c * 32, ra);
+              tc_ld_wait(ra);
+              s_new += chunk_sum_exact(ra, cmax);
             }
-            s_run = fmaf(s_run, ex2(m_run - m_new), acc0 + acc1);
-            m_run = m_new;
+            if (redo) {
+              s_run = (t == 0) ? 0.f : s_run * ex2(m_stab - cmax);
+              s_tile = s_new;
+              m_stab = cmax;
+            }
           }
           tc_fence_before();
           mbar_arrive(t_empty + slot);
+          s_run += s_tile;
         }
-        const float lse = (m_run + lg2(s_run)) * LN2;
+        const float lse = (m_stab + lg2(s_run)) * LN2;
         if (live && a.frame_lse) a.frame_lse[(int64_t)model * a.total_frames + fe] = lse;
         warp_segmented_atomic_add(a.scores, utt, a.n_models, model, lse * wgt, lane);
       }

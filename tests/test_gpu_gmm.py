@@ -72,6 +72,24 @@ def test_tf32_matches_fp32_kernel_1024_components():
             assert abs(b[j, i] - ref) <= 1e-4 * abs(ref)
 
 
+def test_tf32_stabiliser_redo_paths():
+    """The tensor kernel carries its exp stabiliser from model to model; models whose likelihood for the same
+    frames differs by thousands of nats (both directions) must take the redo path and still match float64."""
+    k, d = 256, 13
+    w, mu, var = synth.synth_ubm(k, d, seed=11)
+    far = mu + 25.0          # every component ~ 25 sigma away: log-lik ~ -5000
+    tight = var * 0.05       # sharp model: huge negative log-lik for most frames
+    models_mu = np.stack([mu, far, mu, mu, far, mu * 0.5])
+    models_var = np.stack([var, var, tight, var, var, var])
+    ms = ssp.ModelSet(np.tile(w, (6, 1)), models_mu, models_var)
+    utts = [synth.sample_gmm(w, mu, var, n, seed=200 + n) for n in (300, 257, 40)]
+    got = ssp.score_matrix(utts, ms, precision="tf32")
+    want = np.array([[ogmm.score(u, w, models_mu[i], models_var[i]) for i in range(6)] for u in utts])
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, want, rtol=5e-4)
+    assert (got.argmax(axis=1) == want.argmax(axis=1)).all()
+
+
 def test_split_utterance_property():
     """score(whole) == frame-weighted mean of score(parts) (mean of per-frame log-likelihoods)."""
     k, d = 128, 26
