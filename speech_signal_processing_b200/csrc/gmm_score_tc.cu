@@ -9,14 +9,21 @@
 // the same tile sequence, so each tile is read from HBM once per wave and served to the other SMs by L2.
 //
 //   warp 0      : producer   - one lane issues cp.async.bulk (global -> smem) + mbarrier expect_tx
-//   warp 1      : MMA issuer - one lane issues tcgen05.mma kind::tf32 (M128 x N128 x K8) into 4 TMEM slots,
-//                 tcgen05.commit signals "slot full" / "stage free"
-//   warps 2..9  : epilogue   - tcgen05.ld 32 lanes x 32 columns; thread == frame row; online (max, sum 2^x)
-//                 across a model's tiles -> per-frame log-likelihood -> warp-segmented per-utterance sum
-//                 -> one double atomic per (warp, utterance, model).  The T x K logits never leave the SM.
+//   warp 1      : MMA issuer - the warp walks the tile loop uniformly, one elected lane issues tcgen05.mma
+//                 kind::tf32 (M128 x N128 x K8) into 4 TMEM slots (descriptors stay in uniform registers;
+//                 a divergent single-lane loop cost ~135 cycles per 64-cycle MMA), tcgen05.commit signals
+//                 "slot full" / "stage free"
+//   warps 2..17 : epilogue   - 4 warps per SM sub-partition (2 row blocks x 2 column halves x 4 TMEM lane
+//                 quadrants); tcgen05.ld 32 lanes x 32 columns; thread == (frame row, 64 columns); sum of
+//                 2^(x - stabiliser) across a model's tiles (MUFU ex2 + a small FMA-pipe polynomial share),
+//                 the two column halves merged through shared memory -> per-frame log-likelihood ->
+//                 warp-segmented per-utterance sum -> one double atomic per (warp, utterance, model).
+//                 The T x K logits never leave the SM.
 //
 // The log-constant rides through the MMA as two TF32-exact pieces (c_hi + c_lo) against A columns of 1.0,
 // so the epilogue is max / ex2 / add only.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ssp {
@@ -28,9 +35,13 @@ constexpr int UNIT = BM * MB;
 constexpr int BN = kTileN;   // components per tile
 constexpr int NSTAGE = 3;
 constexpr int NSLOT = 4;     // TMEM accumulator slots (BN fp32 columns each) = all 512 columns
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;  // 4 per SM sub-partition: two row blocks x two 64-column halves x four lane quadrants
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int MAX_KD = 80;
+// Measured on B200 under the 1 kW cap (10k utts x 1001 models): pairs 0/2/4/6/8 -> 523/539/526/496/486 TFLOP/s.
+// The kernel is power-bound, not pipe-bound: a MUFU ex2 costs less energy than the ~7 FMA-pipe instructions that
+// replace it, so only a small share is worth moving.
+constexpr int kDefaultPolyPairs = 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -154,6 +165,13 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
   asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
                "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
 }
+__device__ __forceinline__ void tc_ld_wait2(uint32_t (&r)[32], uint32_t (&q)[32]) {
+  tc_ld_wait(r);
+  asm volatile("" : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+               "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15]));
+  asm volatile("" : "+r"(q[16]), "+r"(q[17]), "+r"(q[18]), "+r"(q[19]), "+r"(q[20]), "+r"(q[21]), "+r"(q[22]), "+r"(q[23]),
+               "+r"(q[24]), "+r"(q[25]), "+r"(q[26]), "+r"(q[27]), "+r"(q[28]), "+r"(q[29]), "+r"(q[30]), "+r"(q[31]));
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
@@ -171,7 +189,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // evaluated on the FMA pipe: 2^x = 2^n * p(f), n = round(x) via the 1.5*2^23 magic add, f = x - n in
 // [-0.5, 0.5], p = degree-4 minimax polynomial (max relative error 2.7e-6), 2^n applied by adding n to the
 // exponent field.  Packed FADD2 / FFMA2 halve the issue slots; FMNMX3 halves the max chain.
-constexpr int kPolyPairs = 6;
+template <int kPolyPairs>
 __device__ __forceinline__ void chunk_sum(const uint32_t (&r)[32], float m_stab, float2& accp, float2& accm0, float2& accm1,
                                           float& cmax) {
   float v[32];
@@ -207,6 +225,7 @@ __device__ __forceinline__ void chunk_sum(const uint32_t (&r)[32], float m_stab,
     accp = __fadd2_rn(accp, e);
   }
 #pragma unroll
+  static_assert(kPolyPairs % 2 == 0 && kPolyPairs <= 16, "pairs are consumed two at a time");
   for (int i = kPolyPairs; i < 16; i += 2) {
     const float2 d0 = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), nm);
     const float2 d1 = __fadd2_rn(make_float2(v[2 * i + 2], v[2 * i + 3]), nm);
@@ -251,6 +270,7 @@ struct Args {
   float* frame_lse;
 };
 
+template <int kPolyPairs>
 __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int KD = a.KD;
@@ -265,12 +285,13 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
   uint64_t* a_full = t_empty + NSLOT;
   uint64_t* a_empty = a_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+  float2* comb = reinterpret_cast<float2*>(tmem_slot + 4);  // [model parity][row block][row]: (m, s) of column half 1
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, BM); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 2 * BM); }
     mbar_init(a_full, EPI_WARPS * 32);
     mbar_init(a_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -343,23 +364,27 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
     }
   } else {
     // ===================== epilogue warps (also build the A operand) =====================
-    const int etid = tid - 64;                 // 0..255: row of the unit this thread BUILDS
-    const int g = (warp - 2) >> 2;             // row block this thread READS accumulators of
+    const int etid = tid - 64;                 // 0..511
+    const int ew = warp - 2;                   // 0..15
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int g = (ew >> 2) & 1;               // row block whose accumulators this thread reads
+    const int half = ew >> 3;                  // which 64 of the tile's 128 columns
     const int row = quad * 32 + lane;          // accumulator row within the row block
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float LN2 = 0.69314718055994530942f;
     uint32_t n = 0, unit_idx = 0;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
       const int64_t frame0 = u * UNIT;
-      // ---- A operand: row r of block mb at float index ((mb*KC + j/4)*BM + r)*4 + j%4
+      // ---- A operand: row r of block mb at float index ((mb*KC + j/4)*BM + r)*4 + j%4; two threads per row
       mbar_wait(a_empty, (unit_idx & 1u) ^ 1u);
       {
-        const int64_t fr = frame0 + etid;
+        const int brow = etid & (UNIT - 1), part = etid >> 8;
+        const int64_t fr = frame0 + brow;
         const bool live = fr < a.total_frames;
         const float* xr = a.feats + fr * a.D;
-        float* dst = sA + (size_t)(etid >> 7) * tile_floats + (size_t)(etid & (BM - 1)) * 4;
-        for (int j = 0; j < KD; ++j) {
+        float* dst = sA + (size_t)(brow >> 7) * tile_floats + (size_t)(brow & (BM - 1)) * 4;
+        const int j0 = part * (KD >> 1), j1 = j0 + (KD >> 1);
+        for (int j = j0; j < j1; ++j) {
           float v = 0.f;
           if (j < a.D) v = live ? rna_tf32(xr[j]) : 0.f;
           else if (j < 2 * a.D) { float x = live ? xr[j - a.D] : 0.f; v = rna_tf32(x * x); }
@@ -369,12 +394,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(a_full);
       }
-      // ---- the frame this thread scores
+      // ---- the frame this thread scores (column half 0 finalises the row)
       const int64_t fe = frame0 + (int64_t)g * BM + row;
       const bool live = fe < a.total_frames;
-      const int utt = live ? find_segment(a.offsets, a.n_utts, fe) : -1;
+      int utt = -1;
       float wgt = 1.f;
-      if (utt >= 0 && a.normalize) wgt = 1.f / (float)(a.offsets[utt + 1] - a.offsets[utt]);
+      if (half == 0) {
+        utt = live ? find_segment(a.offsets, a.n_utts, fe) : -1;
+        if (utt >= 0 && a.normalize) wgt = 1.f / (float)(a.offsets[utt + 1] - a.offsets[utt]);
+      }
 
       float m_stab = -3.0e38f;  // carried from model to model (see chunk_sum)
       for (int model = 0; model < a.n_models; ++model) {
@@ -383,23 +411,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
           const uint32_t slot = 2u * (n & 1u) + (uint32_t)g, ph = (n >> 1) & 1u;
           mbar_wait(t_full + slot, ph);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + lane_addr + slot * BN;
-          // 4 x 32 columns, double-buffered through two register banks
+          const uint32_t taddr = tmem_base + lane_addr + slot * BN + half * 64;
           uint32_t ra[32], rb[32];
           float2 accp = make_float2(0.f, 0.f), accm0 = make_float2(0.f, 0.f), accm1 = make_float2(0.f, 0.f);
           float cmax = -3.0e38f;
           tc_ld32_issue(taddr, ra);
-          tc_ld_wait(ra);
           tc_ld32_issue(taddr + 32, rb);
-          chunk_sum(ra, m_stab, accp, accm0, accm1, cmax);
-          tc_ld_wait(rb);
-          tc_ld32_issue(taddr + 64, ra);
-          chunk_sum(rb, m_stab, accp, accm0, accm1, cmax);
-          tc_ld_wait(ra);
-          tc_ld32_issue(taddr + 96, rb);
-          chunk_sum(ra, m_stab, accp, accm0, accm1, cmax);
-          tc_ld_wait(rb);
-          chunk_sum(rb, m_stab, accp, accm0, accm1, cmax);
+          tc_ld_wait2(ra, rb);
+          chunk_sum<kPolyPairs>(ra, m_stab, accp, accm0, accm1, cmax);
+          chunk_sum<kPolyPairs>(rb, m_stab, accp, accm0, accm1, cmax);
           const float2 tot = __fadd2_rn(__fadd2_rn(accm0, accm1), accp);
           float s_tile = tot.x + tot.y;
           // stabiliser check: too low (overflow risk) on any tile, too high (underflow of everything) on a
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
           if (__any_sync(0xffffffffu, redo)) {
             float s_new = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < 2; ++c) {
               tc_ld32_issue(taddr + c * 32, ra);
               tc_ld_wait(ra);
               s_new += chunk_sum_exact(ra, cmax);
@@ -423,9 +443,18 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
           mbar_arrive(t_empty + slot);
           s_run += s_tile;
         }
-        const float lse = (m_stab + lg2(s_run)) * LN2;
-        if (live && a.frame_lse) a.frame_lse[(int64_t)model * a.total_frames + fe] = lse;
-        warp_segmented_atomic_add(a.scores, utt, a.n_models, model, lse * wgt, lane);
+        // ---- merge the two column halves of the row: half 1 publishes (m, s), half 0 finalises
+        float2* cb = comb + ((model & 1) * MB + g) * BM;
+        if (half == 1) cb[row] = make_float2(m_stab, s_run);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(2 * BM) : "memory");
+        if (half == 0) {
+          const float2 o = cb[row];
+          const float m = fmaxf(m_stab, o.x);
+          const float ssum = s_run * ex2(m_stab - m) + o.y * ex2(o.x - m);
+          const float lse = (m + lg2(ssum)) * LN2;
+          if (live && a.frame_lse) a.frame_lse[(int64_t)model * a.total_frames + fe] = lse;
+          warp_segmented_atomic_add(a.scores, utt, a.n_models, model, lse * wgt, lane);
+        }
       }
     }
   }
@@ -463,17 +492,32 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.scores = scores;
   a.frame_lse = frame_lse;
   const size_t tile_bytes = (size_t)BN * L.KD * 4;
-  const size_t smem = (MB + NSTAGE) * tile_bytes + (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16;
+  const size_t smem = (MB + NSTAGE) * tile_bytes + (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 +
+                      2 * MB * BM * sizeof(float2);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     SSP_CUDA_OK(cudaGetDevice(&dev));
     SSP_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_units = (total_frames + UNIT - 1) / UNIT;
   const unsigned grid = (unsigned)(n_units < num_sms ? n_units : num_sms);
-  gmm_score_tc_kernel<<<grid, THREADS, smem, st>>>(a);
+  // share of the exponentials evaluated on the FMA pipe (pairs out of 16 per 32 columns); tuning knob
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("SSP_TC_POLY_PAIRS");
+    poly = e ? atoi(e) : kDefaultPolyPairs;
+  }
+#define SSP_TC_LAUNCH(pp)                                                                                              \
+  case pp:                                                                                                             \
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gmm_score_tc_kernel<pp><<<grid, THREADS, smem, st>>>(a);                                                           \
+    break;
+  switch (poly) {
+    SSP_TC_LAUNCH(0) SSP_TC_LAUNCH(2) SSP_TC_LAUNCH(4) SSP_TC_LAUNCH(6) SSP_TC_LAUNCH(8)
+    default: SSP_REQUIRE(false, "SSP_TC_POLY_PAIRS must be 0, 2, 4, 6 or 8 (got %d)", poly);
+  }
+#undef SSP_TC_LAUNCH
   SSP_LAUNCH_CHECK("gmm_score_tc_kernel");
   return SSP_OK;
 }
