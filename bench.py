@@ -381,9 +381,20 @@ def run_b200(a):
     print(json.dumps(line), flush=True)
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 if __name__ == "__main__":
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+        _shutdown()
