@@ -6,56 +6,9 @@
 //
 // Conventions are data (tables + ssp_frontend_cfg), not code: the same kernel serves the sidekit
 // recipe GMM_UBM.py:89 calls, python_speech_features' and utils/processing.py:110-144.
-#include "common.cuh"
+#include "frontend_common.cuh"
 
 namespace ssp {
-
-struct FrontendArgs {
-  ssp_frontend_cfg cfg;
-  const void* pcm;
-  const int64_t* sample_offsets;
-  const float* window;
-  const int32_t* fb_start;
-  const int32_t* fb_len;
-  const int32_t* fb_offset;
-  const float* fb_weights;
-  const float* dct;
-  const int64_t* frame_offsets;
-  float* out_feats;
-  float* out_log_energy;
-  int max_frames;  // shared-memory rows reserved for cepstra
-};
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-
-template <typename PcmT>
-__device__ __forceinline__ float load_pcm(const void* p, int64_t i) {
-  return (float)reinterpret_cast<const PcmT*>(p)[i];
-}
-
-// value of output feature j (0..OD-1) at frame t from the cepstra kept in shared memory;
-// GMM_UBM.py:53-69 (delta, edge padding) applied once or twice.
-__device__ __forceinline__ float delta_at(const float* __restrict__ ceps, int NC, int T, int t, int jj, int N, float inv_den) {
-  float acc = 0.f;
-  for (int n = 1; n <= N; ++n) {
-    const int hi = min(t + n, T - 1), lo = max(t - n, 0);
-    acc = fmaf((float)n, ceps[hi * NC + jj] - ceps[lo * NC + jj], acc);
-  }
-  return acc * inv_den;
-}
-__device__ __forceinline__ float feat_at(const float* __restrict__ ceps, int NC, int T, int t, int j, int N, float inv_den) {
-  const int order = j / NC, jj = j - order * NC;
-  if (order == 0) return ceps[t * NC + jj];
-  if (order == 1) return delta_at(ceps, NC, T, t, jj, N, inv_den);
-  float acc = 0.f;
-  for (int n = 1; n <= N; ++n) {
-    const int hi = min(t + n, T - 1), lo = max(t - n, 0);
-    acc = fmaf((float)n, delta_at(ceps, NC, T, hi, jj, N, inv_den) - delta_at(ceps, NC, T, lo, jj, N, inv_den), acc);
-  }
-  return acc * inv_den;
-}
 
 template <typename PcmT>
 __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
@@ -374,7 +327,7 @@ extern "C" int64_t ssp_frontend_num_frames(const ssp_frontend_cfg* c, int64_t n)
 
 extern "C" int64_t ssp_frontend_max_frames(const ssp_frontend_cfg* c) {
   if (!ssp::frontend_cfg_ok(c)) return 0;
-  const size_t fixed = ssp::frontend_smem(*c, 0);
+  const size_t fixed = ssp::frontend_fast_supported(*c) ? ssp::frontend_fast_smem(*c, 0, false) : ssp::frontend_smem(*c, 0);
   if (fixed >= ssp::kFrontendSmemMax) return 0;
   return (int64_t)((ssp::kFrontendSmemMax - fixed) / (sizeof(float) * c->n_ceps));
 }
@@ -410,6 +363,7 @@ extern "C" int ssp_frontend_batch(const void* pcm, const int64_t* sample_offsets
   a.out_feats = out_feats;
   a.out_log_energy = out_log_energy;
   a.max_frames = (int)max_frames_per_utt;
+  if (frontend_fast_supported(*cfg)) return launch_frontend_fast(a, n_utts, nullptr, (cudaStream_t)stream);
   const size_t smem = frontend_smem(*cfg, (int)max_frames_per_utt);
   const int threads = 32 * frontend_warps(cfg->nfft);
   cudaStream_t st = (cudaStream_t)stream;

@@ -1,0 +1,439 @@
+// Fast path of the fused front-end for nfft = 512 (25 ms frames at 16 kHz, the reference's setting).
+//
+// Same contract as frontend_kernel (frontend.cu) with a cheaper per-frame pipeline:
+//   * the samples of 8 consecutive frames (one per warp) are staged once in shared memory as floats,
+//     so each PCM sample is read from global memory once per CTA instead of 2 x 2.5 times;
+//   * the 256-point complex FFT of the packed frame lives in REGISTERS: 8 points per lane, radix-8
+//     butterfly, one shared-memory transpose (bank-conflict-free, row stride 36), second radix-8, and the
+//     last radix-4 across lane quadruples with warp shuffles -- 2 shared-memory round trips instead of 4
+//     Stockham passes;
+//   * the real-FFT split handles bins k and 256-k together;
+//   * the triangular filterbank is cut into segments of bounded width so that the 32 lanes share the
+//     ~2 x 257 weights evenly (a lane per filter is bound by the widest triangle), deterministic order;
+//   * delta and delta-delta are materialised once in shared memory when the utterance is short enough,
+//     and the CMVN statistics / output passes read them instead of re-deriving 16 taps per element.
+#include <cstdlib>
+
+#include "frontend_common.cuh"
+
+namespace ssp {
+
+namespace ff {
+constexpr int W = 8;          // warps per CTA == frames per batch
+constexpr int NH = 256;       // complex FFT length
+constexpr int EXS = 36;       // float2 row stride of the transpose buffer (conflict-free for 64-bit accesses)
+constexpr int EXN = 8 * EXS;  // 288 float2 >= 268 needed for the padded spectrum
+constexpr int MAXSEG = 96;
+constexpr int MAXW = 2048;    // filterbank weights cached in shared memory
+constexpr int MAXF = 64;      // filters
+constexpr int MAXC = 32;      // cepstra
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), d = csub(a1, a3);
+  const float2 s3 = make_float2(d.y, -d.x);  // (a1 - a3) * (-i)
+  a0 = cadd(s0, s2);
+  a1 = cadd(s1, s3);
+  a2 = csub(s0, s2);
+  a3 = csub(s1, s3);
+}
+// in-place 8-point DFT, natural order in and out (decimation in frequency)
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  const float R = 0.70710678118654752440f;
+  float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+  float2 b0 = csub(v[0], v[4]);
+  const float2 t1 = csub(v[1], v[5]), t2 = csub(v[2], v[6]), t3 = csub(v[3], v[7]);
+  float2 b1 = make_float2((t1.x + t1.y) * R, (t1.y - t1.x) * R);   // * (1 - i)/sqrt2
+  float2 b2 = make_float2(t2.y, -t2.x);                           // * (-i)
+  float2 b3 = make_float2((t3.y - t3.x) * R, -(t3.x + t3.y) * R);  // * (-1 - i)/sqrt2
+  dft4(a0, a1, a2, a3);
+  dft4(b0, b1, b2, b3);
+  v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+  v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+__host__ __device__ inline size_t carve_floats(const ssp_frontend_cfg& c, int max_frames, bool mat, int* per_warp_out,
+                                                int* stg_out) {
+  const int FLp = (c.frame_len + 3) & ~3;
+  const int stg = ((W - 1) * c.frame_shift + c.frame_len + 1 + 3) & ~3;
+  const int per_warp = 2 * EXN + 260 + MAXSEG + MAXF;
+  if (per_warp_out) *per_warp_out = per_warp;
+  if (stg_out) *stg_out = stg;
+  size_t f = 2 * (NH + 2) + FLp + ((c.n_ceps * (c.n_filt | 1) + 3) & ~3) + MAXW + 3 * MAXSEG + (MAXF + 4) + 4 + 256 + 64 + 64 + stg +
+             (size_t)W * per_warp;
+  f += (size_t)max_frames * c.n_ceps * (mat ? (1 + c.delta_order) : 1);
+  return f;
+}
+
+template <typename PcmT>
+__global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, const int materialize) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ssp_frontend_cfg& cfg = a.cfg;
+  const int NC = cfg.n_ceps, NF = cfg.n_filt, FL = cfg.frame_len, SH = cfg.frame_shift;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int OD = NC * (1 + cfg.delta_order);
+  // ---- carve-up (mirrors carve_floats)
+  int per_warp, stg;
+  carve_floats(cfg, 0, false, &per_warp, &stg);
+  float* p = reinterpret_cast<float*>(smem_raw);
+  float2* tw_real = reinterpret_cast<float2*>(p); p += 2 * (NH + 2);
+  float* win = p; p += (FL + 3) & ~3;
+  const int DS = NF | 1;  // odd row stride: lanes reading different rows hit different banks
+  float* dct = p; p += (NC * DS + 3) & ~3;
+  float* fbw = p; p += MAXW;
+  int* seg_start = reinterpret_cast<int*>(p); p += MAXSEG;
+  int* seg_len = reinterpret_cast<int*>(p); p += MAXSEG;
+  int* seg_woff = reinterpret_cast<int*>(p); p += MAXSEG;
+  int* filt_seg0 = reinterpret_cast<int*>(p); p += MAXF + 4;
+  int* meta = reinterpret_cast<int*>(p); p += 4;
+  float* red = p; p += 256;
+  float* mean = p; p += 64;
+  float* istd = p; p += 64;
+  float* stage = p; p += stg;
+  float* wb = p + (size_t)warp * per_warp; p += (size_t)W * per_warp;
+  float* ceps = p;
+  float2* ex = reinterpret_cast<float2*>(wb);
+  float* pw = wb + 2 * EXN;
+  float* segsum = pw + 260;
+  float* mel = segsum + MAXSEG;
+
+  const int u = blockIdx.x;
+  const int64_t s_begin = a.sample_offsets[u];
+  const int64_t n_samp = a.sample_offsets[u + 1] - s_begin;
+  const int64_t f_begin = a.frame_offsets[u];
+  const int T = (int)(a.frame_offsets[u + 1] - f_begin);
+  if (T <= 0) return;
+
+  // ---- per-CTA tables
+  for (int k = tid; k <= NH; k += 256) {
+    float s, c;
+    sincospif(-(float)k / 256.0f, &s, &c);  // e^{-2 pi i k / 512}
+    tw_real[k] = make_float2(c, s);
+  }
+  for (int i = tid; i < FL; i += 256) win[i] = a.window[i];
+  for (int i = tid; i < NC * NF; i += 256) dct[(i / NF) * DS + (i % NF)] = a.dct[i];
+  // filterbank CSR (3 x NF ints) is pulled in cooperatively; thread 0 then cuts the segments out of shared memory
+  int* csr = reinterpret_cast<int*>(stage);  // stage is free until the first batch
+  for (int i = tid; i < NF; i += 256) {
+    csr[i] = a.fb_len[i];
+    csr[MAXF + i] = a.fb_start[i];
+    csr[2 * MAXF + i] = a.fb_offset[i];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // cut every triangle into segments of at most `width` bins: ~24 segments' worth of work per 32 lanes
+    int total = 0;
+    for (int m = 0; m < NF; ++m) total += csr[m];
+    int width = (total + 23) / 24;
+    if (width < 8) width = 8;
+    int ns = 0;
+    for (;;) {
+      ns = 0;
+      for (int m = 0; m < NF; ++m) ns += max(1, (csr[m] + width - 1) / width);
+      if (ns <= MAXSEG) break;
+      width *= 2;
+    }
+    int s = 0;
+    for (int m = 0; m < NF; ++m) {
+      filt_seg0[m] = s;
+      const int len = csr[m], st = csr[MAXF + m], off = csr[2 * MAXF + m];
+      int done = 0;
+      do {
+        const int l = min(width, len - done);
+        seg_start[s] = st + done;
+        seg_len[s] = l;
+        seg_woff[s] = off + done;
+        done += l;
+        ++s;
+      } while (done < len);
+    }
+    filt_seg0[NF] = s;
+    meta[0] = s;
+    meta[1] = total <= MAXW ? 1 : 0;
+    meta[2] = total;
+  }
+  // per-lane twiddles, constant across frames
+  float2 tw1[8], tw2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float s, c;
+    sincospif(-(float)(lane * k) / 128.0f, &s, &c);  // W_256^{lane k}
+    tw1[k] = make_float2(c, s);
+    sincospif(-(float)((lane & 3) * k) / 16.0f, &s, &c);  // W_32^{b k}
+    tw2[k] = make_float2(c, s);
+  }
+  __syncthreads();
+  const int n_seg = meta[0];
+  const bool w_cached = meta[1] != 0;
+  if (w_cached)
+    for (int i = tid; i < meta[2]; i += 256) fbw[i] = a.fb_weights[i];
+  const float* fw = w_cached ? fbw : a.fb_weights;
+
+  const float pre = cfg.preemph;
+  const int pmode = cfg.preemph_mode;
+  const float LOG10_E = 0.43429448190325176f;
+  const int n_batches = (T + W - 1) / W;
+
+  // The staging loads of batch b+1 are issued before batch b is processed and only written to shared memory
+  // after it, so their global-memory latency hides behind a whole frame of FFT work.
+  constexpr int PF = 8;  // samples per thread per batch: (W-1)*shift + frame_len + 1 <= 256 * PF
+  float pf[PF];
+  auto prefetch = [&](int b) {
+    const int64_t g0 = (int64_t)b * W * SH - 1;
+#pragma unroll
+    for (int r = 0; r < PF; ++r) {
+      const int i = tid + 256 * r;
+      const int64_t g = g0 + i;
+      pf[r] = (i < stg && g >= 0 && g < n_samp) ? load_pcm<PcmT>(a.pcm, s_begin + g) : 0.f;
+    }
+  };
+  prefetch(0);
+  for (int b = 0; b < n_batches; ++b) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PF; ++r) {
+      const int i = tid + 256 * r;
+      if (i < stg) stage[i] = pf[r];
+    }
+    __syncthreads();
+    if (b + 1 < n_batches) prefetch(b + 1);
+    const int f = b * W + warp;
+    if (f >= T) continue;
+    const float* s = stage + 1 + warp * SH;              // s[i] = sample i of this frame, s[-1] the one before
+    const int64_t s0 = (int64_t)f * SH;
+    const int n_valid = (int)min((int64_t)FL, n_samp - s0);  // samples of the frame that exist (zero padded tail)
+
+    // ---- load + pre-emphasis + energy + window, packed z[n] = (x[2n], x[2n+1]); lane holds z[32 j + lane]
+    float2 v[8];
+    float energy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = 64 * j + 2 * lane;
+      float y0 = 0.f, y1 = 0.f;
+      if (i < n_valid) {
+        const float x0 = s[i];
+        float xm1 = s[i - 1];
+        if (i == 0 && pmode == 1) xm1 = x0;
+        y0 = pmode ? fmaf(-pre, xm1, x0) : x0;
+        if (i + 1 < n_valid) {
+          const float x1 = s[i + 1];
+          y1 = pmode ? fmaf(-pre, x0, x1) : x1;
+        }
+      }
+      energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+      const float w0 = i < FL ? win[i] : 0.f, w1 = i + 1 < FL ? win[i + 1] : 0.f;
+      v[j] = make_float2(y0 * w0, y1 * w1);
+    }
+    energy = warp_sum(energy);
+
+    // ---- 256-point FFT: n = 32 n1 + n2 (n2 = lane), k = k1 + 8 k2
+    dft8(v);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw1[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ex[k * EXS + lane] = v[k];
+    __syncwarp();
+    const int k1 = lane >> 2, bq = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ex[k1 * EXS + 4 * j + bq];
+    __syncwarp();
+    dft8(v);
+#pragma unroll
+    for (int c = 1; c < 8; ++c) v[c] = cmul(v[c], tw2[c]);
+    // radix-4 across the lane quadruple: after the two shuffle stages lane b holds output d = {0,2,1,3}[b]
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float2 q = shfl_xor2(v[c], 2);
+      v[c] = (lane & 2) ? csub(q, v[c]) : cadd(v[c], q);
+      if (bq == 3) v[c] = make_float2(v[c].y, -v[c].x);
+      q = shfl_xor2(v[c], 1);
+      v[c] = (lane & 1) ? csub(q, v[c]) : cadd(v[c], q);
+    }
+    {
+      const int d = ((bq & 1) << 1) | (bq >> 1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = k1 + 8 * c + 64 * d;
+        ex[k + 4 * (k >> 6)] = v[c];  // padded by 4 per 64 so the four d-blocks land in different banks
+      }
+    }
+    __syncwarp();
+
+    // ---- real-input split, bins k and 256 - k together; power / magnitude spectrum
+    float etot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 1 + lane + 32 * j, km = NH - k;  // k in 1..128
+      const float2 zk = ex[k + 4 * (k >> 6)], zm = ex[km + 4 * (km >> 6)];
+      const float2 t = tw_real[k];
+      const float2 xe = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+      const float2 xo = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+      const float2 x = cmul(t, xo);
+      // X[k] = xe + t xo ;  X[256-k] = conj(xe) + (-conj t) * conj(xo)... = conj(xe - t xo)
+      const float re = xe.x + x.x, im = xe.y + x.y;
+      const float re2 = xe.x - x.x, im2 = xe.y - x.y;
+      float p1 = fmaf(re, re, im * im), p2 = fmaf(re2, re2, im2 * im2);
+      if (cfg.spec_type == 1) { p1 = sqrtf(p1); p2 = sqrtf(p2); }
+      p1 *= cfg.spec_scale;
+      p2 *= cfg.spec_scale;
+      pw[k] = p1;
+      if (km != k) { pw[km] = p2; etot += p2; }
+      etot += p1;
+    }
+    if (lane == 0) {
+      const float2 z0 = ex[0];
+      float p0 = (z0.x + z0.y) * (z0.x + z0.y), pn = (z0.x - z0.y) * (z0.x - z0.y);
+      if (cfg.spec_type == 1) { p0 = sqrtf(p0); pn = sqrtf(pn); }
+      p0 *= cfg.spec_scale;
+      pn *= cfg.spec_scale;
+      pw[0] = p0;
+      pw[NH] = pn;
+      etot += p0 + pn;
+    }
+    if (cfg.energy_mode == 2) etot = warp_sum(etot);
+    __syncwarp();
+
+    // ---- filterbank: bounded-width segments spread over the lanes, then a fixed-order sum per filter
+    for (int sg = lane; sg < n_seg; sg += 32) {
+      const float* w = fw + seg_woff[sg];
+      const float* q = pw + seg_start[sg];
+      const int len = seg_len[sg];
+      float acc = 0.f;
+      for (int i = 0; i < len; ++i) acc = fmaf(w[i], q[i], acc);
+      segsum[sg] = acc;
+    }
+    __syncwarp();
+    for (int m = lane; m < NF; m += 32) {
+      float acc = 0.f;
+      for (int sg = filt_seg0[m]; sg < filt_seg0[m + 1]; ++sg) acc += segsum[sg];
+      if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
+      acc += cfg.log_add;
+      mel[m] = cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc);
+    }
+    __syncwarp();
+    // ---- DCT
+    for (int j = lane; j < NC; j += 32) {
+      const float* row = dct + j * DS;
+      float acc0 = 0.f, acc1 = 0.f;
+      int m = 0;
+      for (; m + 1 < NF; m += 2) {
+        acc0 = fmaf(row[m], mel[m], acc0);
+        acc1 = fmaf(row[m + 1], mel[m + 1], acc1);
+      }
+      if (m < NF) acc0 = fmaf(row[m], mel[m], acc0);
+      float acc = acc0 + acc1;
+      if (cfg.energy_mode == 2 && j == 0) {
+        float e = etot;
+        if (cfg.log_zero_floor > 0.f && e == 0.f) e = cfg.log_zero_floor;
+        acc = logf(e);
+      }
+      ceps[f * NC + j] = acc;
+    }
+    if (lane == 0 && a.out_log_energy && cfg.energy_mode == 1) a.out_log_energy[f_begin + f] = logf(energy);
+  }
+  __syncthreads();
+
+  // ---- delta / delta-delta / CMVN
+  const int N = cfg.delta_n;
+  float den = 0.f;
+  for (int n = 1; n <= N; ++n) den += 2.f * n * n;
+  const float inv_den = den > 0.f ? 1.f / den : 0.f;
+  float* out = a.out_feats + f_begin * OD;
+  const int total = T * OD;
+  const int j = tid & 63, g = tid >> 6;         // feature column / frame phase for the column passes
+  const int ord_j = j >= 2 * NC ? 2 : (j >= NC ? 1 : 0), jj_j = j - ord_j * NC;
+  if (materialize && cfg.delta_order > 0) {
+    // all orders laid out as [order][T][NC] right behind the cepstra; thread = (column tid % 16.., frame phase)
+    const int cols = NC <= 16 ? 16 : 32, jj = tid & (cols - 1), tg = tid / cols, tstep = 256 / cols;
+    for (int ord = 1; ord <= cfg.delta_order; ++ord) {
+      const float* src = ceps + (size_t)(ord - 1) * T * NC;
+      float* dst = ceps + (size_t)ord * T * NC;
+      if (jj < NC)
+        for (int t = tg; t < T; t += tstep) dst[t * NC + jj] = delta_at(src, NC, T, t, jj, N, inv_den);
+      __syncthreads();
+    }
+  }
+  auto value = [&](int t, int ord, int jj, int jfull) -> float {
+    if (materialize) return ceps[((size_t)ord * T + t) * NC + jj];
+    return feat_at(ceps, NC, T, t, jfull, N, inv_den);
+  };
+  if (cfg.cmvn) {
+    float part = 0.f;
+    if (j < OD)
+      for (int t = g; t < T; t += 4) part += value(t, ord_j, jj_j, j);
+    red[tid] = part;
+    __syncthreads();
+    if (tid < 64) mean[tid] = (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]) / (float)T;
+    __syncthreads();
+    part = 0.f;
+    if (j < OD) {
+      const float mu = mean[j];
+      for (int t = g; t < T; t += 4) {
+        const float d = value(t, ord_j, jj_j, j) - mu;
+        part = fmaf(d, d, part);
+      }
+    }
+    red[tid] = part;
+    __syncthreads();
+    if (tid < 64) {
+      float sd = sqrtf((red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]) / (float)T);
+      if (sd < 10.f * 1.1920929e-7f) sd = 1.f;  // sklearn/preprocessing/_data.py:127
+      istd[tid] = 1.f / sd;
+    }
+    __syncthreads();
+  }
+  // flattened, fully coalesced store; (t, column) advance incrementally: no integer division in the loop
+  {
+    const int dq = 256 / OD, dr = 256 - dq * OD;
+    int t = tid / OD, jc = tid - t * OD;
+    for (int idx = tid; idx < total; idx += 256) {
+      const int ord = jc >= 2 * NC ? 2 : (jc >= NC ? 1 : 0);
+      float val = value(t, ord, jc - ord * NC, jc);
+      if (cfg.cmvn) val = (val - mean[jc]) * istd[jc];
+      out[idx] = val;
+      t += dq;
+      jc += dr;
+      if (jc >= OD) { jc -= OD; ++t; }
+    }
+  }
+}
+
+}  // namespace ff
+
+bool frontend_fast_supported(const ssp_frontend_cfg& c) {
+  return c.nfft == 512 && c.n_filt <= ff::MAXF && c.n_ceps <= ff::MAXC && c.frame_len >= 2 && c.frame_shift >= 1 &&
+         (ff::W - 1) * c.frame_shift + c.frame_len + 1 <= 256 * 8;
+}
+
+size_t frontend_fast_smem(const ssp_frontend_cfg& c, int max_frames, bool mat) {
+  return ff::carve_floats(c, max_frames, mat, nullptr, nullptr) * sizeof(float);
+}
+
+int launch_frontend_fast(const FrontendArgs& a, int64_t n_utts, size_t* smem_out, cudaStream_t st) {
+  // materialise delta / delta-delta when that still leaves room for two CTAs per SM
+  const size_t with = frontend_fast_smem(a.cfg, a.max_frames, true);
+  static int force = -2;
+  if (force == -2) {
+    const char* e = getenv("SSP_FE_MATERIALIZE");  // tuning knob: 0 / 1 force, unset = heuristic
+    force = e ? atoi(e) : -1;
+  }
+  bool mat = a.cfg.delta_order > 0 && with <= 110 * 1024;
+  if (force >= 0) mat = force != 0 && a.cfg.delta_order > 0 && with <= 220 * 1024;
+  const size_t smem = mat ? with : frontend_fast_smem(a.cfg, a.max_frames, false);
+  if (smem_out) *smem_out = smem;
+  if (a.cfg.pcm_dtype == 0) {
+    SSP_CUDA_OK(cudaFuncSetAttribute(ff::frontend512_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ff::frontend512_kernel<int16_t><<<(unsigned)n_utts, 256, smem, st>>>(a, mat ? 1 : 0);
+  } else {
+    SSP_CUDA_OK(cudaFuncSetAttribute(ff::frontend512_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ff::frontend512_kernel<float><<<(unsigned)n_utts, 256, smem, st>>>(a, mat ? 1 : 0);
+  }
+  SSP_LAUNCH_CHECK("frontend512_kernel");
+  return SSP_OK;
+}
+
+}  // namespace ssp
