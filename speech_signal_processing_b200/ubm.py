@@ -79,6 +79,52 @@ def identify(utts, speakers, ubm=None, precision="tf32", device=None):
 label_encoder: dict = {}
 
 
+def load_data(path="dataset/ASR_GMM"):
+    """``GMM_UBM.load_data`` (GMM_UBM.py:24-50): walk ``path/<speaker>/<session>/<wav>``, read every file with
+    ``scipy.io.wavfile.read`` (utils/tools.py:45-47), encode speakers in directory order into the module-level
+    ``label_encoder``.  Returns ``(x, y)``: list of int16 arrays, list of labels.  Stereo files keep their
+    first channel (the handling MFCC_DTW.py:141-144 applies)."""
+    from scipy.io import wavfile
+
+    t0 = time.time()
+    print("Loading data...")
+    x, y = [], []
+    for num, speaker in enumerate(os.listdir(path)):
+        label_encoder[speaker] = num
+        spk_dir = os.path.join(path, speaker)
+        for session in os.listdir(spk_dir):
+            ses_dir = os.path.join(spk_dir, session)
+            for wav in os.listdir(ses_dir):
+                _, audio = wavfile.read(os.path.join(ses_dir, wav))
+                if audio.ndim == 2:
+                    audio = audio[:, 0]
+                x.append(audio)
+                y.append(num)
+    print("Complete! Spend {:.2f}s".format(time.time() - t0))
+    return x, y
+
+
+def load_extract(test_size=0.3, path="dataset/ASR_GMM", delta_order=1):
+    """``GMM_UBM.load_extract`` (GMM_UBM.py:121-131): load, split per utterance with ``random_state=0``
+    (sklearn's ``train_test_split`` permutation: ``RandomState(0).permutation(n)``, test = first ceil(test_size*n)),
+    then ONE front-end launch per split."""
+    x, y = load_data(path)
+    n = len(x)
+    n_test = int(np.ceil(test_size * n))
+    perm = np.random.RandomState(0).permutation(n)
+    test_idx, train_idx = perm[:n_test], perm[n_test:]
+    train_data, x_train, y_train = fe.extract_feature([x[i] for i in train_idx], [y[i] for i in train_idx], is_train=True,
+                                                      delta_order=delta_order)
+    x_test, y_test = fe.extract_feature([x[i] for i in test_idx], [y[i] for i in test_idx], delta_order=delta_order)
+    return train_data, x_train, y_train, x_test, y_test
+
+
+def main(path="dataset/ASR_GMM"):
+    """``GMM_UBM.main`` (GMM_UBM.py:202-204)."""
+    train_data, x_train, y_train, x_test, y_test = load_extract(path=path)
+    return GMM(train_data, x_train, y_train, x_test, y_test, model=False)
+
+
 def GMM(train, x_train, y_train, x_test, y_test, n_components=16, model=False, label_encoder=None, random_state=None,
         precision="tf32"):
     """``GMM_UBM.GMM`` (GMM_UBM.py:134-199) on the GPU; prints the reference's result line and

@@ -227,3 +227,68 @@ def test_GMM_trains_and_identifies(tmp_path, monkeypatch):
         ubm = pickle.load(f)  # a stock sklearn estimator the reference GUIs can consume
     assert type(ubm).__module__.startswith("sklearn")
     assert np.isfinite(ubm.score(f_te[0].astype(np.float64)))
+
+
+def test_main_from_wav_tree(tmp_path, monkeypatch):
+    """GMM_UBM.main() equivalent: WAV tree -> load_data -> split -> extract_feature -> GMM()."""
+    from scipy.io import wavfile
+
+    from speech_signal_processing_b200 import ubm as subm
+
+    root = tmp_path / "dataset" / "ASR_GMM"
+    for s in range(3):
+        d = root / f"spk{s}" / "session0"
+        d.mkdir(parents=True)
+        for u in range(7):
+            sig = synth.synth_utterance(s, u, 16000)
+            if u == 0:
+                sig = np.stack([sig, sig], axis=1)  # a stereo file: first channel is used
+            wavfile.write(str(d / f"utt{u}.wav"), 16000, sig)
+    monkeypatch.chdir(tmp_path)
+    subm.label_encoder.clear()
+    x, y = ssp.load_data(str(root))
+    assert len(x) == 21 and all(a.ndim == 1 and a.dtype == np.int16 for a in x) and sorted(set(y)) == [0, 1, 2]
+    acc_tr, acc, pred = subm.main(str(root))
+    assert pred.shape == (7, 3) and acc_tr >= 0.9
+    subm.label_encoder.clear()
+
+
+def test_full_size_identify_properties():
+    """BASELINE config 4 at full size (10 000 utterances x 298 frames vs 1 000 speakers + UBM, K = 1024, D = 39)
+    through size-independent properties: utterance permutation permutes rows, a sub-sample agrees with the FP32
+    CUDA-core kernel and the float64 oracle, the planted speaker wins."""
+    import torch
+
+    k, d, s, n, t = 1024, 39, 1000, 10000, 298
+    w, mu, var = synth.synth_ubm(k, d, seed=0)
+    dev = torch.device("cuda")
+    t_mu = torch.as_tensor(synth.synth_speaker_means(mu, s, seed=1, shift=0.25), device=dev)
+    t_var = torch.as_tensor(var, device=dev)
+    truth = torch.arange(n, device=dev) % s
+    feats = synth.synth_features_torch(n * t, d, t_mu, t_var, truth.repeat_interleave(t), seed=3, device=dev)
+    offs = np.arange(n + 1, dtype=np.int64) * t
+    ms = ssp.ModelSet(torch.cat([torch.as_tensor(np.tile(w, (s, 1)), device=dev), torch.as_tensor(w, device=dev)[None]]),
+                      torch.cat([t_mu, torch.as_tensor(mu, device=dev)[None]]),
+                      torch.cat([t_var[None].expand(s, k, d), t_var[None]]))
+    scores, _ = ms.score(feats, offs, precision="tf32")
+    assert scores.shape == (n, s + 1) and bool(torch.isfinite(scores).all())
+    llr = scores[:, :s] - scores[:, s:]
+    assert bool((llr.argmax(dim=1) == truth).all())
+    # permutation of whole utterances permutes the rows (bitwise up to the fp32 partial-sum order)
+    perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    feats_p = feats.view(n, t, d)[perm].reshape(n * t, d).contiguous()
+    scores_p, _ = ms.score(feats_p, offs, precision="tf32")
+    assert float((scores_p - scores[perm]).abs().max()) < 2e-5
+    # sub-sample against the FP32 kernel and the oracle
+    sub = [0, 1234, 9999]
+    sub_feats = torch.cat([feats[i * t : (i + 1) * t] for i in sub])
+    s32, _ = ms.score(sub_feats, np.arange(len(sub) + 1) * t, precision="fp32")
+    rel = ((scores[sub] - s32).abs() / s32.abs()).max()
+    assert float(rel) < 1e-4
+    host_mu = t_mu.cpu().numpy()
+    for r, i in enumerate(sub):
+        x = feats[i * t : (i + 1) * t].cpu().numpy()
+        for m in (int(truth[i]), 7):
+            ref = ogmm.score(x, w, host_mu[m], var)
+            assert abs(float(s32[r, m]) - ref) <= 2e-6 * abs(ref)
+            assert abs(float(scores[i, m]) - ref) <= 1e-4 * abs(ref)
