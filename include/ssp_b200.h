@@ -151,7 +151,11 @@ int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, int64_t n_ut
  */
 int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs,
                   int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n,
-                  double* out_f, double* out_s, double* out_loglik, void* stream);
+                  double* out_f, double* out_s, double* out_loglik, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+/* Scratch bytes ssp_gmm_stats needs for these dims (0: none).  The tensor-core path (3xTF32 tcgen05, D <= 39)
+ * keeps per-component-tile log-sum-exp partials there; without enough workspace the FP32 CUDA-core path runs. */
+int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames);
 
 /*
  * M-step on device (sklearn _gaussian_mixture.py:312-313,250-252,898): from (all-reduced)

@@ -1,6 +1,7 @@
 // extern "C" entry points that are not tied to one kernel file: error string, launch counter,
 // packing and the score / stats dispatch.
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -57,9 +58,25 @@ extern "C" int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, i
   SSP_REQUIRE(false, "ssp_gmm_score: unknown precision %d", precision);
 }
 
+static bool stats_use_tc(const ssp::PackLayout& L, int64_t total_frames, int64_t workspace_bytes, const void* workspace) {
+  static int impl = -1;  // SSP_STATS_IMPL=simt forces the FP32 CUDA-core kernels (A/B testing)
+  if (impl < 0) {
+    const char* e = getenv("SSP_STATS_IMPL");
+    impl = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return impl == 1 && ssp::stats_tc_supported(L) && workspace &&
+         workspace_bytes >= ssp::stats_tc_workspace_bytes(L, total_frames);
+}
+
+extern "C" int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames) {
+  ssp::PackLayout L;
+  if (!ssp::make_layout(dims, &L) || total_frames < 0) return 0;
+  return ssp::stats_tc_workspace_bytes(L, total_frames);
+}
+
 extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
                              const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n, double* out_f,
-                             double* out_s, double* out_loglik, void* stream) {
+                             double* out_s, double* out_loglik, void* workspace, int64_t workspace_bytes, void* stream) {
   ssp::PackLayout L;
   SSP_REQUIRE(ssp::make_layout(dims, &L), "ssp_gmm_stats: unsupported dims");
   SSP_REQUIRE(dims->n_models == 1, "ssp_gmm_stats: statistics are taken under ONE model (got %d)", dims->n_models);
@@ -67,10 +84,12 @@ extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int
   SSP_REQUIRE(n_segs >= 0 && total_frames >= 0, "ssp_gmm_stats: negative size");
   if (n_segs == 0) return SSP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  // pass 1: per-frame log-likelihood (FP32 exact; posteriors are exp(L - lse) so TF32 logits are not enough) and
-  // the per-segment sum of frame log-likelihoods (the EM lower bound numerator, sklearn _base.py:558)
+  if (stats_use_tc(L, total_frames, workspace_bytes, workspace))
+    return ssp::launch_stats_tc(feats, seg_offsets, n_segs, total_frames, pack, L, frame_lse, out_n, out_f, out_s, out_loglik,
+                                workspace, st);
+  // FP32 CUDA-core path.  pass 1: per-frame log-likelihood and the per-segment sum of frame log-likelihoods (the EM
+  // lower bound numerator, sklearn _base.py:558); pass 2: posteriors and N/F/S
   int rc = ssp::launch_score_simt(feats, seg_offsets, n_segs, total_frames, pack, L, false, out_loglik, frame_lse, st);
   if (rc != SSP_OK) return rc;
-  // pass 2: posteriors and N/F/S
   return ssp::launch_stats_simt(feats, seg_offsets, n_segs, total_frames, pack, L, frame_lse, out_n, out_f, out_s, st);
 }

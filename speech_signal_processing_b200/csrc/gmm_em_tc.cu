@@ -1,0 +1,605 @@
+// EM / MAP sufficient statistics on the tensor cores (sm_100a): posteriors and N/F/S as two chained GEMMs.
+//
+// Posteriors need FP32-grade logits (a 4e-3 logit error is a 0.4 % responsibility error), so the logit GEMM runs
+// as 3xTF32: hi.hi + lo.hi + hi.lo with the frame operand [x, x^2, 1, 1] and the model operand
+// log2(e) [mu/var, -1/(2var), c...] both split into TF32 hi + lo pieces (the constant rides as three exact
+// pieces), FP32 accumulation in TMEM.  kind::tf32 only takes K-major shared-memory operands (an MN-major
+// descriptor silently yields zeros on sm_100a), so every operand is laid out with its contraction index
+// contiguous.
+//
+//   grid = (frame chunks, component tiles of 128); the CTA's model tile (hi + lo) stays resident in shared memory
+//   and frame blocks stream through.  Two passes (the per-frame normaliser needs ALL component tiles):
+//
+//   pass LSE   (gmm_em_lse_kernel, 128-frame blocks): logits[frame, comp] -> thread == frame row ->
+//              per-tile (max, sum 2^x) partials to the workspace.
+//   pass STATS (gmm_em_stats_kernel, 64-frame blocks): TRANSPOSED logits[comp, frame] = B . F^T, so that
+//              thread == component row: gamma = 2^(L2 - lse2[frame]) (lse2 from the partials, broadcast from
+//              shared memory) is written 16 bytes at a time, conflict-free, straight into the K-major
+//              [component][frame] operand of GEMM 2:  stats[comp, :] += gamma . [x, x^2, 1, 1] over the frames,
+//              accumulated in TMEM across all blocks of a segment (lane == component), hi + lo passes of the
+//              frame-contiguous feature operand Xt.  At a segment end the 128 x (2D+2) accumulator is added
+//              to the double-precision N / F / S outputs.
+// Blocks never straddle a segment, so one kernel pair serves UBM EM (one segment) and batched MAP enrolment
+// (one segment per speaker).
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace ssp {
+namespace em {
+
+using namespace tc;
+
+constexpr int BN = 128;   // components per CTA
+constexpr int BM1 = 128;  // frames per block, pass LSE
+constexpr int BM2 = 64;   // frames per block, pass STATS
+constexpr int EPI = 128;
+constexpr int THREADS = 64 + EPI;
+constexpr int MAX_KD = 80;
+constexpr uint32_t TMEM_COLS = 256;  // [0,128): logits, [128, 128+N2): statistics accumulator
+constexpr uint32_t STAT_COL = 128;
+
+struct Args {
+  const float* feats;
+  const int64_t* seg;
+  int64_t n_segs, total_frames, chunk;
+  const float* tiles_hi;  // [Kp/128][KD/4][128] float4
+  const float* tiles_lo;
+  int K, D, KD, n_tiles;
+  float2* partial;        // [n_tiles][total_frames]: (max, sum 2^(x-max)) in the log2 domain
+  float* frame_lse;       // natural-log per-frame likelihood (written by tile 0 in the STATS pass)
+  double* out_n;
+  double* out_f;
+  double* out_s;
+  double* out_loglik;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Every role walks the same block sequence: [t0, t0 + nt) inside one segment and inside this CTA's chunk.
+template <int BM>
+struct Walk {
+  const int64_t* seg;
+  int64_t n_segs, end, t0, seg_end;
+  int cur;
+  __device__ bool start(const int64_t* s, int64_t n, int64_t b, int64_t e) {
+    seg = s; n_segs = n; end = e; t0 = b;
+    if (b >= e) return false;
+    cur = find_segment(seg, n_segs, t0);
+    if (cur < 0) return false;
+    seg_end = seg[cur + 1];
+    return true;
+  }
+  __device__ int nt() const { return (int)min((int64_t)BM, min(end, seg_end) - t0); }
+  // advance; returns false when the chunk is exhausted.  `flush`: the block just finished was the last one of its
+  // segment inside this chunk.
+  __device__ bool next(int n, bool& flush) {
+    t0 += n;
+    flush = (t0 >= seg_end) || (t0 >= end);
+    if (t0 >= end) return false;
+    if (t0 >= seg_end) {
+      cur = find_segment(seg, n_segs, t0);
+      if (cur < 0) return false;
+      seg_end = seg[cur + 1];
+    }
+    return true;
+  }
+};
+
+// [x, x^2, 1, 1, 0..] element j of a frame row held in shared memory, split into TF32 hi / lo
+__device__ __forceinline__ void feat_split(const float* xr, int j, int D, bool live, float& hi, float& lo) {
+  float v = 0.f;
+  if (live) {
+    if (j < D) v = xr[j];
+    else if (j < 2 * D) { const float x = xr[j - D]; v = x * x; }
+    else if (j < 2 * D + 2) v = 1.f;
+  }
+  hi = rna_tf32(v);
+  lo = rna_tf32(v - hi);
+}
+
+// Each of the 128 builder threads keeps its share of the NEXT block's features in registers: the global loads are
+// issued right after the current block's operands are handed to the MMA warp and land while the tensor core and
+// the epilogue work, instead of being waited for at the top of every block.
+template <int R>
+__device__ __forceinline__ void prefetch_block(const float* __restrict__ src, int n, int et, float (&pf)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int idx = et + EPI * r;
+    pf[r] = idx < n ? __ldg(src + idx) : 0.f;
+  }
+}
+template <int R>
+__device__ __forceinline__ void store_block(float* dst, int n, int et, const float (&pf)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int idx = et + EPI * r;
+    if (idx < n) dst[idx] = pf[r];
+  }
+}
+
+// ================================================================================================ pass LSE
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int BM = BM1;
+  const int KD = a.KD, KC = KD >> 2;
+  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
+  float* sBhi = reinterpret_cast<float*>(smem);
+  float* sBlo = sBhi + BN * KD;
+  float* sAhi = sBlo + BN * KD;
+  float* sAlo = sAhi + BM * KD;
+  float* sX = sAlo + BM * KD;  // feature staging: BM x D floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + BM * MAX_KD / 2);
+  uint64_t* b_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* l_full = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.y;
+  if (tid == 0) {
+    mbar_init(b_full, 1);
+    mbar_init(a_full, EPI);
+    mbar_init(l_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
+  const int64_t end = min(begin + a.chunk, a.total_frames);
+
+  if (warp == 0) {
+    if (begin < end && elect_one()) {
+      mbar_arrive_expect_tx(b_full, 2u * tile_bytes);
+      bulk_g2s(sBhi, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_full);
+      bulk_g2s(sBlo, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_full);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr uint32_t lbo = BM * 16u, sbo = 128u;
+      constexpr uint32_t kstep = (2u * lbo) >> 4;
+      const uint64_t ahi = make_desc(smem_u32(sAhi), lbo, sbo), alo = make_desc(smem_u32(sAlo), lbo, sbo);
+      const uint64_t bhi = make_desc(smem_u32(sBhi), lbo, sbo), blo = make_desc(smem_u32(sBlo), lbo, sbo);
+      const int ksteps = KD >> 3;
+      const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+      mbar_wait(b_full, 0);
+      uint32_t i = 0;
+      bool more = true;
+      while (more) {
+        const int nt = w.nt();
+        mbar_wait(a_full, i & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, ahi + (uint64_t)(k * kstep), bhi + (uint64_t)(k * kstep), idesc, k > 0);
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, alo + (uint64_t)(k * kstep), bhi + (uint64_t)(k * kstep), idesc, 1u);
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, ahi + (uint64_t)(k * kstep), blo + (uint64_t)(k * kstep), idesc, 1u);
+          tc_commit(l_full);
+        }
+        __syncwarp();
+        bool flush;
+        more = w.next(nt, flush);
+        ++i;
+      }
+    }
+  } else {
+    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == frame row
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int et = tid - 64;
+    const int D = a.D;
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
+      float pf[R];
+      prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
+      uint32_t i = 0;
+      bool more = true;
+      while (more) {
+        const int nt = w.nt();
+        const int64_t t0 = w.t0;
+        store_block<R>(sX, nt * D, et, pf);
+        named_bar_sync(1, EPI);
+        {
+          Walk<BM> wn = w;
+          bool fl;
+          if (wn.next(nt, fl)) prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
+        }
+        const bool live = row < nt;
+        {
+          const float* xr = sX + row * D;
+          float4* dhi = reinterpret_cast<float4*>(sAhi) + row;
+          float4* dlo = reinterpret_cast<float4*>(sAlo) + row;
+          for (int jc = 0; jc < KC; ++jc) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) feat_split(xr, 4 * jc + e, D, live, h[e], l[e]);
+            dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
+            dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        named_bar_sync(1, EPI);  // staged rows consumed before the next block overwrites them
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(a_full);
+        mbar_wait(l_full, i & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr;
+        float m_run = -3.0e38f, s_run = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tc_ld32_issue(taddr + c * 32, r);
+          tc_ld_wait(r);
+          float cmax = __uint_as_float(r[0]);
+#pragma unroll
+          for (int e = 1; e < 32; ++e) cmax = fmaxf(cmax, __uint_as_float(r[e]));
+          const float m_new = fmaxf(m_run, cmax);
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            acc0 += ex2(__uint_as_float(r[e]) - m_new);
+            acc1 += ex2(__uint_as_float(r[e + 1]) - m_new);
+          }
+          s_run = fmaf(s_run, ex2(m_run - m_new), acc0 + acc1);
+          m_run = m_new;
+        }
+        if (live) a.partial[(size_t)tile * a.total_frames + t0 + row] = make_float2(m_run, s_run);
+        tc_fence_before();
+        bool flush;
+        more = w.next(nt, flush);
+        ++i;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+}
+
+// ================================================================================================ pass STATS
+struct StatsCarve {
+  int kd, n2, xrows;
+  size_t o_bhi, o_blo, o_fhi, o_flo, o_xhi, o_xlo, o_g, o_lse, o_bar, bytes;
+};
+__host__ __device__ inline StatsCarve stats_carve(int KD) {
+  StatsCarve c;
+  c.kd = KD;
+  c.n2 = (KD + 15) & ~15;
+  c.xrows = c.n2 + 1;  // odd row count: the 16 K-chunks of the frame-contiguous operand start in different banks
+  size_t o = 0;
+  c.o_bhi = o; o += (size_t)BN * KD * 4;
+  c.o_blo = o; o += (size_t)BN * KD * 4;
+  c.o_fhi = o; o += (size_t)BM2 * KD * 4;
+  c.o_flo = o; o += (size_t)BM2 * KD * 4;
+  c.o_xhi = o; o += (size_t)(BM2 / 4) * c.xrows * 16;
+  c.o_xlo = o; o += (size_t)(BM2 / 4) * c.xrows * 16;
+  c.o_g = o; o += (size_t)BN * BM2 * 4;  // gamma [BM2/4][BN][4]; doubles as the feature staging buffer
+  c.o_lse = o; o += BM2 * 4;
+  c.o_bar = o; o += 64;
+  c.bytes = o;
+  return c;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int BM = BM2;
+  const int KD = a.KD, KC = KD >> 2, D = a.D;
+  const StatsCarve cv = stats_carve(KD);
+  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
+  float* sBhi = reinterpret_cast<float*>(smem + cv.o_bhi);
+  float* sBlo = reinterpret_cast<float*>(smem + cv.o_blo);
+  float* sFhi = reinterpret_cast<float*>(smem + cv.o_fhi);  // [KC][BM][4]: frames as rows (N operand of GEMM 1)
+  float* sFlo = reinterpret_cast<float*>(smem + cv.o_flo);
+  float* sXhi = reinterpret_cast<float*>(smem + cv.o_xhi);  // [BM/4][xrows][4]: features as rows, frames contiguous
+  float* sXlo = reinterpret_cast<float*>(smem + cv.o_xlo);
+  float* sG = reinterpret_cast<float*>(smem + cv.o_g);
+  float* sLse = reinterpret_cast<float*>(smem + cv.o_lse);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.o_bar);
+  uint64_t* b_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* l_full = bars + 2;
+  uint64_t* g_full = bars + 3;
+  uint64_t* a_free = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.y;
+  if (tid == 0) {
+    mbar_init(b_full, 1);
+    mbar_init(a_full, EPI);
+    mbar_init(l_full, 1);
+    mbar_init(g_full, EPI);
+    mbar_init(a_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
+  const int64_t end = min(begin + a.chunk, a.total_frames);
+
+  if (warp == 0) {
+    if (begin < end && elect_one()) {
+      mbar_arrive_expect_tx(b_full, 2u * tile_bytes);
+      bulk_g2s(sBhi, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_full);
+      bulk_g2s(sBlo, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_full);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      // GEMM 1 (transposed logits): A = model tile (M = 128 components), B = frame block (N = 64 frames), K = features
+      constexpr uint32_t lbo_b = BN * 16u, lbo_f = BM * 16u, sbo = 128u;
+      constexpr uint32_t ks_b = (2u * lbo_b) >> 4, ks_f = (2u * lbo_f) >> 4;
+      const uint64_t bhi = make_desc(smem_u32(sBhi), lbo_b, sbo), blo = make_desc(smem_u32(sBlo), lbo_b, sbo);
+      const uint64_t fhi = make_desc(smem_u32(sFhi), lbo_f, sbo), flo = make_desc(smem_u32(sFlo), lbo_f, sbo);
+      // GEMM 2: A = gamma (M = 128 components, K = frames), B = Xt (N = n2 feature rows, K = frames)
+      const uint32_t lbo_x = (uint32_t)cv.xrows * 16u;
+      const uint32_t ks_g = (2u * lbo_b) >> 4, ks_x = (2u * lbo_x) >> 4;
+      const uint64_t gd = make_desc(smem_u32(sG), lbo_b, sbo);
+      const uint64_t xhi = make_desc(smem_u32(sXhi), lbo_x, sbo), xlo = make_desc(smem_u32(sXlo), lbo_x, sbo);
+      const int ksteps = KD >> 3;
+      const uint32_t idesc1 = make_idesc_tf32(BN, BM, 0, 0);
+      const uint32_t idesc2 = make_idesc_tf32(BN, cv.n2, 0, 0);
+      mbar_wait(b_full, 0);
+      uint32_t i = 0;
+      bool first_in_seg = true, more = true;
+      while (more) {
+        const int nt = w.nt();
+        mbar_wait(a_full, i & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, bhi + (uint64_t)(k * ks_b), fhi + (uint64_t)(k * ks_f), idesc1, k > 0);
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, bhi + (uint64_t)(k * ks_b), flo + (uint64_t)(k * ks_f), idesc1, 1u);
+          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, blo + (uint64_t)(k * ks_b), fhi + (uint64_t)(k * ks_f), idesc1, 1u);
+          tc_commit(l_full);
+        }
+        __syncwarp();
+        mbar_wait(g_full, i & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int k = 0; k < BM / 8; ++k)
+            tc_mma_tf32(tmem_base + STAT_COL, gd + (uint64_t)(k * ks_g), xhi + (uint64_t)(k * ks_x), idesc2,
+                        (first_in_seg && k == 0) ? 0u : 1u);
+          for (int k = 0; k < BM / 8; ++k)
+            tc_mma_tf32(tmem_base + STAT_COL, gd + (uint64_t)(k * ks_g), xlo + (uint64_t)(k * ks_x), idesc2, 1u);
+          tc_commit(a_free);
+        }
+        __syncwarp();
+        bool flush;
+        more = w.next(nt, flush);
+        first_in_seg = flush;
+        ++i;
+      }
+    }
+  } else {
+    // ===================== operand builder (thread == frame) and epilogue (thread == component) =====================
+    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == component row within the tile
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int et = tid - 64;                   // 0..127
+    const int fr = et & (BM - 1), half = et >> 6;  // frame row this thread builds, and which half of its columns
+    const float LN2 = 0.69314718055994530942f;
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
+      constexpr int PT = 8;                                        // component tiles whose partials are prefetched
+      float pf[R];
+      float2 pp[PT];
+      auto prefetch_partials = [&](int64_t t0n, int ntn) {
+        if (half == 1 && fr < ntn) {
+#pragma unroll
+          for (int y = 0; y < PT; ++y)
+            if (y < a.n_tiles) pp[y] = a.partial[(size_t)y * a.total_frames + t0n + fr];
+        }
+      };
+      prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
+      prefetch_partials(w.t0, w.nt());
+      uint32_t i = 0;
+      bool more = true;
+      float ll_acc = 0.f;
+      while (more) {
+        const int nt = w.nt();
+        const int64_t t0 = w.t0;
+        const int seg_id = w.cur;
+        mbar_wait(a_free, (i & 1u) ^ 1u);  // GEMM 2 of the previous block is done with gamma / Xt / F
+        store_block<R>(sG, nt * D, et, pf);
+        // per-frame normaliser from the per-tile partials of pass LSE (log2 domain), from the prefetched registers
+        float lse2 = 3.0e38f;  // dead frames: gamma = 2^(x - huge) = 0
+        if (half == 1 && fr < nt) {
+          float m = -3.0e38f;
+#pragma unroll
+          for (int y = 0; y < PT; ++y)
+            if (y < a.n_tiles) m = fmaxf(m, pp[y].x);
+          for (int y = PT; y < a.n_tiles; ++y) m = fmaxf(m, a.partial[(size_t)y * a.total_frames + t0 + fr].x);
+          float ssum = 0.f;
+#pragma unroll
+          for (int y = 0; y < PT; ++y)
+            if (y < a.n_tiles) ssum += pp[y].y * ex2(pp[y].x - m);
+          for (int y = PT; y < a.n_tiles; ++y) {
+            const float2 p = a.partial[(size_t)y * a.total_frames + t0 + fr];
+            ssum += p.y * ex2(p.x - m);
+          }
+          lse2 = m + lg2(ssum);
+          if (tile == 0) {
+            const float lse = lse2 * LN2;
+            a.frame_lse[t0 + fr] = lse;
+            ll_acc += lse;
+          }
+        }
+        if (half == 1) sLse[fr] = lse2;
+        named_bar_sync(1, EPI);
+        {
+          // frame-row operand F (K-major, frames as rows) and frame-contiguous operand Xt (features as rows)
+          const bool live = fr < nt;
+          const float* xr = sG + fr * D;
+          float4* dhi = reinterpret_cast<float4*>(sFhi) + fr;
+          float4* dlo = reinterpret_cast<float4*>(sFlo) + fr;
+          float* xth = sXhi + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
+          float* xtl = sXlo + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
+          for (int jc = half; jc < KC; jc += 2) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              feat_split(xr, 4 * jc + e, D, live, h[e], l[e]);
+              xth[(4 * jc + e) * 4] = h[e];
+              xtl[(4 * jc + e) * 4] = l[e];
+            }
+            dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
+            dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
+          }
+          // rows KD..n2-1 of Xt feed accumulator columns nobody reads, but must be finite
+          if (half == 0)
+            for (int j = KD; j < cv.n2; ++j) { xth[j * 4] = 0.f; xtl[j * 4] = 0.f; }
+        }
+        named_bar_sync(1, EPI);  // staging consumed, sLse visible
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(a_full);
+        {
+          Walk<BM> wn = w;
+          bool fl;
+          if (wn.next(nt, fl)) {
+            prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
+            prefetch_partials(wn.t0, wn.nt());
+          }
+        }
+        // ---- transposed logits: lane == component, columns == frames
+        mbar_wait(l_full, i & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr;
+        float4* g4 = reinterpret_cast<float4*>(sG) + row;
+#pragma unroll 1
+        for (int c = 0; c < BM / 32; ++c) {
+          uint32_t r[32];
+          tc_ld32_issue(taddr + c * 32, r);
+          tc_ld_wait(r);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ls = *reinterpret_cast<const float4*>(sLse + 32 * c + 4 * q);
+            const float g0 = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
+            const float g1 = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
+            const float g2 = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
+            const float g3 = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
+            g4[(8 * c + q) * BN] = make_float4(g0, g1, g2, g3);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(g_full);
+        bool flush;
+        more = w.next(nt, flush);
+        if (flush) {
+          // ---- segment (or chunk) end: drain the statistics accumulator; lane == component
+          mbar_wait(a_free, i & 1u);  // GEMM 2 of this block has completed
+          tc_fence_after();
+          const int comp = tile * BN + row;
+          const uint32_t saddr = tmem_base + lane_addr + STAT_COL;
+#pragma unroll 1
+          for (int c0 = 0; c0 < KD; c0 += 16) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(saddr + c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (comp < a.K) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int j = c0 + e;
+                const double v = (double)__uint_as_float(r[e]);
+                if (j < D) atomicAdd(a.out_f + ((int64_t)seg_id * a.K + comp) * D + j, v);
+                else if (j < 2 * D) atomicAdd(a.out_s + ((int64_t)seg_id * a.K + comp) * D + (j - D), v);
+                else if (j == 2 * D) atomicAdd(a.out_n + (int64_t)seg_id * a.K + comp, v);
+              }
+            }
+          }
+          if (tile == 0) {
+            // ll_acc lives in the `half == 1` builder threads (warps 4, 5 of the CTA)
+            const float tot = warp_sum(ll_acc);
+            if (lane == 0 && tot != 0.f) atomicAdd(a.out_loglik + seg_id, (double)tot);
+            ll_acc = 0.f;
+          }
+          tc_fence_before();
+        }
+        ++i;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace em
+
+bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_lo != 0 && L.n_models == 1; }
+
+int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames) {
+  return stats_tc_supported(L) ? (int64_t)sizeof(float2) * (L.Kp / em::BN) * total_frames : 0;
+}
+
+int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames, const void* pack,
+                    const PackLayout& L, float* frame_lse, double* out_n, double* out_f, double* out_s, double* out_loglik,
+                    void* workspace, cudaStream_t st) {
+  using namespace em;
+  SSP_CUDA_OK(cudaMemsetAsync(out_loglik, 0, sizeof(double) * n_segs, st));
+  if (total_frames == 0) return SSP_OK;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    SSP_CUDA_OK(cudaGetDevice(&dev));
+    SSP_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  Args a;
+  a.feats = feats;
+  a.seg = seg_offsets;
+  a.n_segs = n_segs;
+  a.total_frames = total_frames;
+  a.n_tiles = L.Kp / BN;
+  int64_t gx = num_sms / a.n_tiles;
+  if (gx < 1) gx = 1;
+  int64_t chunk = (total_frames + gx - 1) / gx;
+  chunk = (chunk + BM1 - 1) / BM1 * BM1;
+  gx = (total_frames + chunk - 1) / chunk;
+  a.chunk = chunk;
+  a.tiles_hi = (const float*)((const char*)pack + L.off_tile);
+  a.tiles_lo = (const float*)((const char*)pack + L.off_tile_lo);
+  a.K = L.K;
+  a.D = L.D;
+  a.KD = L.KD;
+  a.partial = (float2*)workspace;
+  a.frame_lse = frame_lse;
+  a.out_n = out_n;
+  a.out_f = out_f;
+  a.out_s = out_s;
+  a.out_loglik = out_loglik;
+  const size_t smem1 = (size_t)(2 * BN * L.KD + 2 * BM1 * L.KD + BM1 * MAX_KD / 2) * sizeof(float) + 64;
+  const size_t smem2 = stats_carve(L.KD).bytes;
+  dim3 grid((unsigned)gx, (unsigned)a.n_tiles);
+  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  gmm_em_lse_kernel<<<grid, THREADS, smem1, st>>>(a);
+  SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
+  gmm_em_stats_kernel<<<grid, THREADS, smem2, st>>>(a);
+  SSP_LAUNCH_CHECK("gmm_em_stats_kernel");
+  return SSP_OK;
+}
+
+}  // namespace ssp

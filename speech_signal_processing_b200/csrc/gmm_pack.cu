@@ -15,7 +15,8 @@ __device__ __forceinline__ float to_tf32(float x) {
 // which is the contraction [x, x^2, 1] . [mu p, -p/2, cst_c].
 __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __restrict__ mu,
                                 const double* __restrict__ var, int n_models, int K, int Kp, int D, int DP, int KD,
-                                float2* __restrict__ ab, float* __restrict__ cst, float* __restrict__ tiles) {
+                                float2* __restrict__ ab, float* __restrict__ cst, float* __restrict__ tiles,
+                                float* __restrict__ tiles_lo) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_models * Kp) return;
   int m = (int)(idx / Kp), c = (int)(idx % Kp);
@@ -24,12 +25,17 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   float* tile = tiles + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KD;
   const int n = c % kTileN;
   auto tile_at = [&](int j) -> float& { return tile[((j >> 2) * kTileN + n) * 4 + (j & 3)]; };
+  // residual image (same layout): B = hi + lo to ~2^-22, used by the 3xTF32 EM kernels
+  float* tlo = tiles_lo ? tiles_lo + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KD : nullptr;
+  auto lo_at = [&](int j) -> float& { return tlo[((j >> 2) * kTileN + n) * 4 + (j & 3)]; };
   const double LOG2E = 1.4426950408889634074;
   if (c >= K) {
     for (int d = 0; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
     cst[idx] = -1e30f;
     for (int j = 0; j < KD; ++j) tile_at(j) = 0.f;
     tile_at(2 * D) = to_tf32(-1e30f);
+    if (tlo)
+      for (int j = 0; j < KD; ++j) lo_at(j) = 0.f;
     return;
   }
   const double* mu_r = mu + ((int64_t)m * K + c) * D;
@@ -41,8 +47,13 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
     quad += mu_r[d] * mu_r[d] * p;
     logdet += log(p);
     ab_row[d] = make_float2((float)a1, (float)a2);
-    tile_at(d) = to_tf32((float)(a1 * LOG2E));
-    tile_at(D + d) = to_tf32((float)(a2 * LOG2E));
+    const float h1 = to_tf32((float)(a1 * LOG2E)), h2 = to_tf32((float)(a2 * LOG2E));
+    tile_at(d) = h1;
+    tile_at(D + d) = h2;
+    if (tlo) {
+      lo_at(d) = to_tf32((float)(a1 * LOG2E - (double)h1));
+      lo_at(D + d) = to_tf32((float)(a2 * LOG2E - (double)h2));
+    }
   }
   for (int d = D; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
   double cc = log(w[(int64_t)m * K + c]) - 0.5 * (D * 1.8378770664093454836 + quad) + 0.5 * logdet;
@@ -55,6 +66,10 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   tile_at(2 * D) = hi;
   tile_at(2 * D + 1) = lo;
   for (int j = 2 * D + 2; j < KD; ++j) tile_at(j) = 0.f;
+  if (tlo) {
+    lo_at(2 * D) = to_tf32((float)(c2 - (double)hi - (double)lo));  // third piece of the constant
+    for (int j = 2 * D + 1; j < KD; ++j) lo_at(j) = 0.f;
+  }
 }
 
 int launch_pack(const double* w, const double* mu, const double* var, const PackLayout& L, void* pack, cudaStream_t st) {
@@ -64,7 +79,8 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
   int64_t blocks = (n + threads - 1) / threads;
   gmm_pack_kernel<<<(unsigned)blocks, threads, 0, st>>>(w, mu, var, L.n_models, L.K, L.Kp, L.D, L.DP, L.KD,
                                                        (float2*)(base + L.off_ab), (float*)(base + L.off_cst),
-                                                       (float*)(base + L.off_tile));
+                                                       (float*)(base + L.off_tile),
+                                                       L.off_tile_lo ? (float*)(base + L.off_tile_lo) : nullptr);
   SSP_LAUNCH_CHECK("gmm_pack_kernel");
   return SSP_OK;
 }

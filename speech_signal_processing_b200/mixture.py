@@ -113,9 +113,13 @@ class ModelSet:
         ll = torch.zeros(n_segs, dtype=torch.float64, device=self.device)
         lse = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
         d_off = torch.as_tensor(seg_offsets, device=self.device)
+        ws_bytes = int(self.lib.ssp_gmm_stats_workspace_bytes(C.byref(self.dims), total))
+        ws = getattr(self, "_ws", None)
+        if ws_bytes and (ws is None or ws.numel() < ws_bytes):
+            ws = self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         rc = self.lib.ssp_gmm_stats(_lib.ptr(feats), _lib.ptr(d_off), n_segs, total, _lib.ptr(self.pack),
                                     C.byref(self.dims), _lib.ptr(lse), _lib.ptr(n), _lib.ptr(f), _lib.ptr(s), _lib.ptr(ll),
-                                    _lib.stream_ptr())
+                                    _lib.ptr(ws) if ws_bytes else None, ws_bytes, _lib.stream_ptr())
         _lib.check(rc, "ssp_gmm_stats")
         self._keep = (d_off, lse)
         return n, f, s, ll
