@@ -33,7 +33,7 @@ using namespace tc;
 constexpr int BN = 128;   // components per CTA
 constexpr int BM1 = 128;  // frames per block, pass LSE
 constexpr int BM2 = 64;   // frames per block, pass STATS
-constexpr int EPI = 128;
+constexpr int EPI = 256;  // 8 builder / epilogue warps: two per TMEM lane quadrant, each owning half of the columns
 constexpr int THREADS = 64 + EPI;
 constexpr int MAX_KD = 80;
 constexpr uint32_t TMEM_COLS = 256;  // [0,128): logits, [128, 128+N2): statistics accumulator
@@ -46,7 +46,7 @@ struct Args {
   const float* tiles_hi;  // [Kp/128][KD/4][128] float4
   const float* tiles_lo;
   int K, D, KD, n_tiles;
-  float2* partial;        // [n_tiles][total_frames]: (max, sum 2^(x-max)) in the log2 domain
+  float2* partial;        // [2 * n_tiles][total_frames]: (max, sum 2^(x-max)) per 64-component half tile, log2 domain
   float* frame_lse;       // natural-log per-frame likelihood (written by tile 0 in the STATS pass)
   double* out_n;
   double* out_f;
@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   } else {
     const int row = ((warp & 3) << 5) | lane;  // TMEM lane == frame row
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int et = tid - 64;
+    const int et = tid - 64;                   // 0..255
+    const int chalf = (warp - 2) >> 2;         // which 64 of the tile's 128 component columns this warp reduces
+    const int brow = et & (BM - 1), bpart = et >> 7;  // row built by this thread, and which half of its K chunks
     const int D = a.D;
     Walk<BM> w;
     if (w.start(a.seg, a.n_segs, begin, end)) {
@@ -212,15 +214,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
           bool fl;
           if (wn.next(nt, fl)) prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
         }
-        const bool live = row < nt;
         {
-          const float* xr = sX + row * D;
-          float4* dhi = reinterpret_cast<float4*>(sAhi) + row;
-          float4* dlo = reinterpret_cast<float4*>(sAlo) + row;
-          for (int jc = 0; jc < KC; ++jc) {
+          const bool blive = brow < nt;
+          const float* xr = sX + brow * D;
+          float4* dhi = reinterpret_cast<float4*>(sAhi) + brow;
+          float4* dlo = reinterpret_cast<float4*>(sAlo) + brow;
+          for (int jc = bpart; jc < KC; jc += 2) {
             float h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) feat_split(xr, 4 * jc + e, D, live, h[e], l[e]);
+            for (int e = 0; e < 4; ++e) feat_split(xr, 4 * jc + e, D, blive, h[e], l[e]);
             dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
             dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
           }
@@ -231,10 +233,10 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
         mbar_arrive(a_full);
         mbar_wait(l_full, i & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr;
+        const uint32_t taddr = tmem_base + lane_addr + chalf * 64;
         float m_run = -3.0e38f, s_run = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
           tc_ld32_issue(taddr + c * 32, r);
           tc_ld_wait(r);
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
           s_run = fmaf(s_run, ex2(m_run - m_new), acc0 + acc1);
           m_run = m_new;
         }
-        if (live) a.partial[(size_t)tile * a.total_frames + t0 + row] = make_float2(m_run, s_run);
+        if (row < nt) a.partial[(size_t)(2 * tile + chalf) * a.total_frames + t0 + row] = make_float2(m_run, s_run);
         tc_fence_before();
         bool flush;
         more = w.next(nt, flush);
@@ -391,20 +393,23 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
     // ===================== operand builder (thread == frame) and epilogue (thread == component) =====================
     const int row = ((warp & 3) << 5) | lane;  // TMEM lane == component row within the tile
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int et = tid - 64;                   // 0..127
-    const int fr = et & (BM - 1), half = et >> 6;  // frame row this thread builds, and which half of its columns
+    const int et = tid - 64;                   // 0..255
+    const int chalf = (warp - 2) >> 2;         // which 32 of the block's 64 frame columns this warp turns into gamma
+    const int fr = et & (BM - 1), part = et >> 6;  // frame row this thread builds, and which quarter of its K chunks
+    const bool norm_thread = part == 3;        // these 64 threads also own the per-frame normaliser
     const float LN2 = 0.69314718055994530942f;
+    const int n_part = 2 * a.n_tiles;
     Walk<BM> w;
     if (w.start(a.seg, a.n_segs, begin, end)) {
       constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
-      constexpr int PT = 8;                                        // component tiles whose partials are prefetched
+      constexpr int PT = 8;                                        // half-tile partials kept in registers
       float pf[R];
       float2 pp[PT];
       auto prefetch_partials = [&](int64_t t0n, int ntn) {
-        if (half == 1 && fr < ntn) {
+        if (norm_thread && fr < ntn) {
 #pragma unroll
           for (int y = 0; y < PT; ++y)
-            if (y < a.n_tiles) pp[y] = a.partial[(size_t)y * a.total_frames + t0n + fr];
+            if (y < n_part) pp[y] = a.partial[(size_t)y * a.total_frames + t0n + fr];
         }
       };
       prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
@@ -418,30 +423,32 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         const int seg_id = w.cur;
         mbar_wait(a_free, (i & 1u) ^ 1u);  // GEMM 2 of the previous block is done with gamma / Xt / F
         store_block<R>(sG, nt * D, et, pf);
-        // per-frame normaliser from the per-tile partials of pass LSE (log2 domain), from the prefetched registers
-        float lse2 = 3.0e38f;  // dead frames: gamma = 2^(x - huge) = 0
-        if (half == 1 && fr < nt) {
-          float m = -3.0e38f;
+        // per-frame normaliser from the half-tile partials of pass LSE (log2 domain), from the prefetched registers
+        if (norm_thread) {
+          float lse2 = 3.0e38f;  // dead frames: gamma = 2^(x - huge) = 0
+          if (fr < nt) {
+            float m = -3.0e38f;
 #pragma unroll
-          for (int y = 0; y < PT; ++y)
-            if (y < a.n_tiles) m = fmaxf(m, pp[y].x);
-          for (int y = PT; y < a.n_tiles; ++y) m = fmaxf(m, a.partial[(size_t)y * a.total_frames + t0 + fr].x);
-          float ssum = 0.f;
+            for (int y = 0; y < PT; ++y)
+              if (y < n_part) m = fmaxf(m, pp[y].x);
+            for (int y = PT; y < n_part; ++y) m = fmaxf(m, a.partial[(size_t)y * a.total_frames + t0 + fr].x);
+            float ssum = 0.f;
 #pragma unroll
-          for (int y = 0; y < PT; ++y)
-            if (y < a.n_tiles) ssum += pp[y].y * ex2(pp[y].x - m);
-          for (int y = PT; y < a.n_tiles; ++y) {
-            const float2 p = a.partial[(size_t)y * a.total_frames + t0 + fr];
-            ssum += p.y * ex2(p.x - m);
+            for (int y = 0; y < PT; ++y)
+              if (y < n_part) ssum += pp[y].y * ex2(pp[y].x - m);
+            for (int y = PT; y < n_part; ++y) {
+              const float2 p = a.partial[(size_t)y * a.total_frames + t0 + fr];
+              ssum += p.y * ex2(p.x - m);
+            }
+            lse2 = m + lg2(ssum);
+            if (tile == 0) {
+              const float lse = lse2 * LN2;
+              a.frame_lse[t0 + fr] = lse;
+              ll_acc += lse;
+            }
           }
-          lse2 = m + lg2(ssum);
-          if (tile == 0) {
-            const float lse = lse2 * LN2;
-            a.frame_lse[t0 + fr] = lse;
-            ll_acc += lse;
-          }
+          sLse[fr] = lse2;
         }
-        if (half == 1) sLse[fr] = lse2;
         named_bar_sync(1, EPI);
         {
           // frame-row operand F (K-major, frames as rows) and frame-contiguous operand Xt (features as rows)
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
           float4* dlo = reinterpret_cast<float4*>(sFlo) + fr;
           float* xth = sXhi + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
           float* xtl = sXlo + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
-          for (int jc = half; jc < KC; jc += 2) {
+          for (int jc = part; jc < KC; jc += 4) {
             float h[4], l[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
             dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
           }
           // rows KD..n2-1 of Xt feed accumulator columns nobody reads, but must be finite
-          if (half == 0)
+          if (part == 0)
             for (int j = KD; j < cv.n2; ++j) { xth[j * 4] = 0.f; xtl[j * 4] = 0.f; }
         }
         named_bar_sync(1, EPI);  // staging consumed, sLse visible
@@ -478,24 +485,22 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
             prefetch_partials(wn.t0, wn.nt());
           }
         }
-        // ---- transposed logits: lane == component, columns == frames
+        // ---- transposed logits: lane == component, columns == frames (this warp: 32 of them)
         mbar_wait(l_full, i & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr;
-        float4* g4 = reinterpret_cast<float4*>(sG) + row;
-#pragma unroll 1
-        for (int c = 0; c < BM / 32; ++c) {
+        {
           uint32_t r[32];
-          tc_ld32_issue(taddr + c * 32, r);
+          tc_ld32_issue(tmem_base + lane_addr + chalf * 32, r);
           tc_ld_wait(r);
+          float4* g4 = reinterpret_cast<float4*>(sG) + row;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 ls = *reinterpret_cast<const float4*>(sLse + 32 * c + 4 * q);
+            const float4 ls = *reinterpret_cast<const float4*>(sLse + 32 * chalf + 4 * q);
             const float g0 = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
             const float g1 = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
             const float g2 = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
             const float g3 = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
-            g4[(8 * c + q) * BN] = make_float4(g0, g1, g2, g3);
+            g4[(8 * chalf + q) * BN] = make_float4(g0, g1, g2, g3);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -504,13 +509,14 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         bool flush;
         more = w.next(nt, flush);
         if (flush) {
-          // ---- segment (or chunk) end: drain the statistics accumulator; lane == component
+          // ---- segment (or chunk) end: drain the statistics accumulator; lane == component, the two warps of a
+          // lane quadrant take alternate 16-column groups
           mbar_wait(a_free, i & 1u);  // GEMM 2 of this block has completed
           tc_fence_after();
           const int comp = tile * BN + row;
           const uint32_t saddr = tmem_base + lane_addr + STAT_COL;
 #pragma unroll 1
-          for (int c0 = 0; c0 < KD; c0 += 16) {
+          for (int c0 = 16 * chalf; c0 < KD; c0 += 32) {
             uint32_t r[16];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
             }
           }
           if (tile == 0) {
-            // ll_acc lives in the `half == 1` builder threads (warps 4, 5 of the CTA)
+            // ll_acc lives in the norm_thread warps; the others contribute zero
             const float tot = warp_sum(ll_acc);
             if (lane == 0 && tot != 0.f) atomicAdd(a.out_loglik + seg_id, (double)tot);
             ll_acc = 0.f;
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
 bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_lo != 0 && L.n_models == 1; }
 
 int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames) {
-  return stats_tc_supported(L) ? (int64_t)sizeof(float2) * (L.Kp / em::BN) * total_frames : 0;
+  return stats_tc_supported(L) ? (int64_t)sizeof(float2) * 2 * (L.Kp / em::BN) * total_frames : 0;
 }
 
 int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames, const void* pack,
