@@ -142,6 +142,29 @@ int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, int64_t n_ut
                   double* out_scores, float* out_frame_lse, void* stream);
 
 /*
+ * Scoring of model sets that SHARE weights and variances and differ in their means only -- what mean-only
+ * relevance-MAP enrolment from a UBM produces (ssp_gmm_map_adapt with flags == 1), i.e. the speaker models of
+ * GMM_UBM.py:182-197 when they are adapted instead of trained from scratch.  The log-likelihood splits into a part
+ * common to all models ([x^2, 1] . [-1/(2 var), const]) computed once per frame block and a per-model part linear
+ * in the frame ([x, 1] . [mu/var, const]), so the per-model tensor-core contraction is D + 2 long instead of
+ * 2D + 2.  Same results as ssp_gmm_score(SSP_PREC_TF32) on the expanded set, to TF32 rounding.
+ *
+ * dims->n_models = number of mean sets S; weights double[K], variances double[K*D], means double[S*K*D] (device).
+ * ref_model      index of the mean set whose per-frame maximum logit stabilises the exponentials (the UBM's own
+ *                means if they are part of the set, else any member).
+ * workspace      device, ssp_gmm_score_shared_workspace_bytes() bytes; may be NULL when that is 0 (this build keeps
+ *                its partial sums in shared memory and needs none).
+ */
+int64_t ssp_gmm_shared_pack_bytes(const ssp_gmm_dims* dims);
+int ssp_gmm_pack_shared(const double* weights, const double* variances, const double* means,
+                        const ssp_gmm_dims* dims, void* out_pack, void* stream);
+int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims);
+int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64_t n_utts,
+                         int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, int32_t ref_model,
+                         double* out_scores, float* out_frame_lse, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
+/*
  * Posterior-weighted sufficient statistics of ONE model (dims->n_models must be 1) over
  * segments of frames (one segment = all frames for UBM EM; one segment per speaker for MAP
  * enrolment):  N[s,c] = sum_t g_tc, F[s,c,:] = sum_t g_tc x_t, S[s,c,:] = sum_t g_tc x_t^2,

@@ -57,6 +57,30 @@ struct PackLayout {
   size_t tile_floats() const { return (size_t)kTileN * KD; }
 };
 
+// Shared-variance model sets (gmm_score_sv.cu): every model has the base model's weights and variances and its own
+// means.  One buffer of tcgen05 shared-memory images, [Kp/64 tiles][1 + n_models][KS/4][64] float4:
+//   image 0      = common part   log2(e) [-1/(2 var), cq_hi, cq_lo, 0..],  cq = log w - D/2 log 2pi - 1/2 sum log var
+//   image 1 + s  = model s       log2(e) [mu_s/var,   ck_hi, ck_lo, 0..],  ck = -1/2 sum mu_s^2 / var
+constexpr int kSvTileN = 64;
+constexpr int kSvMaxKS = 64;
+struct SvLayout {
+  int n_models, K, D;
+  int Kp;  // K rounded up to kSvTileN
+  int KS;  // contraction length: roundup(D + 2, 8)
+  size_t bytes;
+};
+inline bool make_sv_layout(const ssp_gmm_dims* dims, SvLayout* L) {
+  if (!dims || dims->n_models < 1 || dims->n_comp < 1 || dims->n_feat < 1) return false;
+  L->n_models = dims->n_models;
+  L->K = dims->n_comp;
+  L->D = dims->n_feat;
+  L->Kp = (L->K + kSvTileN - 1) / kSvTileN * kSvTileN;
+  L->KS = (L->D + 2 + 7) / 8 * 8;
+  if (L->KS > kSvMaxKS) return false;
+  L->bytes = (size_t)(L->Kp / kSvTileN) * (size_t)(L->n_models + 1) * kSvTileN * L->KS * sizeof(float);
+  return true;
+}
+
 inline int pad_feat(int d) {
   if (d <= 16) return 16;
   if (d <= 32) return 32;
@@ -143,6 +167,11 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
                     const PackLayout& L, float* frame_lse, double* out_n, double* out_f, double* out_s, double* out_loglik,
                     void* workspace, cudaStream_t st);
 bool stats_tc_supported(const PackLayout& L);
+int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, void* pack, cudaStream_t st);
+int64_t score_sv_workspace_bytes(const SvLayout& L);
+int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
+                    const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* workspace,
+                    cudaStream_t st);
 int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames);
 int launch_stats_simt(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
                       const void* pack, const PackLayout& L, const float* frame_lse, double* out_n, double* out_f,

@@ -85,6 +85,57 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
   return SSP_OK;
 }
 
+// Shared-variance pack (SvLayout): one thread per (image, padded component).
+__global__ void gmm_pack_sv_kernel(const double* __restrict__ w, const double* __restrict__ var, const double* __restrict__ mu,
+                                   int S, int K, int Kp, int D, int KS, float* __restrict__ tiles) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)(S + 1) * Kp) return;
+  const int image = (int)(idx / Kp), c = (int)(idx % Kp);
+  const int n = c % kSvTileN;
+  float* tile = tiles + ((int64_t)(c / kSvTileN) * (S + 1) + image) * (int64_t)kSvTileN * KS;
+  auto tile_at = [&](int j) -> float& { return tile[((j >> 2) * kSvTileN + n) * 4 + (j & 3)]; };
+  for (int j = 0; j < KS; ++j) tile_at(j) = 0.f;
+  const double LOG2E = 1.4426950408889634074;
+  if (c >= K) {
+    if (image == 0) tile_at(D) = to_tf32(-1e30f);  // padded components never contribute
+    return;
+  }
+  const double* var_r = var + (int64_t)c * D;
+  double cc;
+  if (image == 0) {
+    double logdet = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double p = 1.0 / var_r[d];
+      logdet += log(p);
+      tile_at(d) = to_tf32((float)(-0.5 * p * LOG2E));
+    }
+    cc = log(w[c]) - 0.5 * D * 1.8378770664093454836 + 0.5 * logdet;
+    if (!(cc > -1e30)) cc = -1e30;  // w == 0
+  } else {
+    const double* mu_r = mu + ((int64_t)(image - 1) * K + c) * D;
+    double quad = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double p = 1.0 / var_r[d];
+      quad += mu_r[d] * mu_r[d] * p;
+      tile_at(d) = to_tf32((float)(mu_r[d] * p * LOG2E));
+    }
+    cc = -0.5 * quad;
+  }
+  const double c2 = cc * LOG2E;
+  const float hi = to_tf32((float)c2);
+  tile_at(D) = hi;
+  tile_at(D + 1) = to_tf32((float)(c2 - (double)hi));
+}
+
+int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, void* pack, cudaStream_t st) {
+  const int64_t n = (int64_t)(L.n_models + 1) * L.Kp;
+  const int threads = 128;
+  gmm_pack_sv_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(w, var, mu, L.n_models, L.K, L.Kp, L.D, L.KS,
+                                                                              (float*)pack);
+  SSP_LAUNCH_CHECK("gmm_pack_sv_kernel");
+  return SSP_OK;
+}
+
 // ------------------------------------------------------------------------------------------ M-step
 // sklearn _gaussian_mixture.py:312-313 (nk = resp.sum + 10 eps), :250-252 (diag covariance),
 // :898 (weights /= weights.sum()).  One block; K*D is small.

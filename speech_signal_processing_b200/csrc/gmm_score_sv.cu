@@ -1,0 +1,583 @@
+// GMM-UBM scoring for model sets that SHARE weights and variances (sm_100a, tcgen05 + TMEM).
+//
+// Mean-only relevance-MAP enrolment (Reynolds 2000; the north-star's "MAP adaptation + scoring" workload) gives
+// every speaker the UBM's weights and variances and its own means.  The diagonal-Gaussian log-likelihood
+// (sklearn _gaussian_mixture.py:536-553) then splits into a part that is common to all speakers and a part that is
+// linear in the frame:
+//
+//     L2[t, s, c] = q[t, c] + r[t, s, c]
+//     q[t, c]     = [x_t^2, 1, 1] . [-1/(2 var_c), cq_hi, cq_lo] * log2(e)      cq = log w_c - D/2 log 2pi - 1/2 sum log var_c
+//     r[t, s, c]  = [x_t,   1, 1] . [mu_sc/var_c,  ck_hi, ck_lo] * log2(e)      ck = -1/2 sum mu_sc^2 / var_c
+//
+// so the per-speaker contraction has K = D + 2 (48 after padding at D = 39) instead of 2D + 2 (80): 40 % fewer
+// tensor-core cycles, and the common part is computed once per (256 frames, 64 components) and kept in registers.
+//
+//   one persistent CTA per SM, unit = 256 frames (two 128-row blocks), component tile = 64
+//   loop order per unit:  chunk of 32 models (outer)  x  component tile j  x  model in the chunk (inner)
+//   warp 0      : producer   - cp.async.bulk of the 12 KB tile images through an 8-stage ring
+//   warps 1, 2  : MMA issuers, one per row block - r-tiles: tcgen05.mma kind::tf32 with the FRAME operand in TMEM
+//                 (written once per unit by tcgen05.st, thread == row) and the model tile in shared memory -> no
+//                 shared-memory traffic for the frames at all; q-tiles: both operands in shared memory.
+//                 M128 x N64 x K8, 6 accumulator slots (3 per row block) so the tensor core runs ahead of the epilogue
+//   (warps 0..3 shrink to 32 registers, the epilogue warps grow to 120: setmaxnreg)
+//   warps 4..19 : epilogue   - thread == (frame row, 32 of the tile's 64 columns); keeps q[t, its 32 columns] - m_t in
+//                 registers across the models of a chunk, per tile: tcgen05.ld, release the slot, d = r + (q - m_t),
+//                 sum 2^d (MUFU ex2 + an FMA-pipe polynomial share), added to the (model, frame) partial sum in
+//                 shared memory
+//   per-frame stabiliser m_t = round(max_c logit of a reference model), found in a short pre-pass, fixed for the whole
+//   unit, so partial sums of different component tiles simply add.  After a chunk's last tile the partial sums become
+//   per-frame log-likelihoods, are summed per utterance inside the warp and added to the (utterance, model) scores.
+//   A sum outside [2^-100, 2^100] (a model nowhere near the reference) turns the score into NaN and
+//   sv_fixup_kernel re-scores that (utterance, model) pair with a plain FP32 online log-sum-exp.
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace ssp {
+namespace sv {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int MB = 2;
+constexpr int UNIT = BM * MB;
+constexpr int BN = kSvTileN;
+constexpr int NSTAGE = 8;
+constexpr int NSLOT = 6;                 // 3 per row block
+constexpr int EPI_WARPS = 16;
+constexpr int EPI = EPI_WARPS * 32;
+constexpr int CTRL = 128;                // warpgroup 0: producer, two MMA issuers, one idle warp (setmaxnreg is per warpgroup)
+constexpr int THREADS = CTRL + EPI;
+constexpr int CTRL_REGS = 32, EPI_REGS = 112;  // launched at 96: 128 x (96 - 32) registers released == 512 x (112 - 96) acquired
+constexpr int CHUNK = 32;                // models per chunk: partial sums [2 column halves][CHUNK][UNIT] fp32 = 64 KB
+constexpr uint32_t ACC_COL0 = 128;       // TMEM: [0, 2 KS) frame operand of the two row blocks, [128, 512) accumulators
+constexpr int kDefaultPolyPairs = 6;
+constexpr int kDefaultPolyDeg = 4;
+
+struct Args {
+  const float* feats;
+  const int64_t* offsets;
+  int64_t n_utts, total_frames;
+  const float* tiles;  // [n_tiles][1 + n_models][KS/4][BN] float4 images; image 0 of a tile is the common q part
+  int n_models, n_tiles, D, KS, ref_model, normalize;
+  double* scores;
+  float* frame_lse;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Barriers are addressed by their 32-bit shared-memory address, computed once per thread: going through generic
+// pointers re-derives the shared window (S2UR + ULEA) at every use, which is most of a wait's instructions.
+__device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// spin on an mbarrier phase; a protocol bug must trap (after ~1 s), not hang the GPU.  No printf here: a call would
+// cost the control warps more registers than setmaxnreg leaves them.
+__device__ __forceinline__ void bar_spin(uint32_t bar, uint32_t parity) {
+  if (bar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!bar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 31)) __trap();
+  }
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// sum over 32 accumulator columns of 2^(r + qm).  kPoly of the 16 column pairs go to the FMA pipe:
+// 2^d = 2^n p(f), n = round(d) by the 1.5 * 2^23 magic add, f = d - n in [-0.5, 0.5], p = minimax polynomial
+// (degree 4: 2.7e-6 relative, degree 3: 7.5e-5), 2^n applied by adding n to the exponent field; the rest is MUFU ex2.
+template <int kPoly, int kDeg>
+__device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float (&qm)[32]) {
+  static_assert(kPoly % 2 == 0 && kPoly <= 16, "pairs are consumed two at a time");
+  const float MAGIC = 12582912.f;  // 1.5 * 2^23
+  const float2 mg = make_float2(MAGIC, MAGIC), nmg = make_float2(-MAGIC, -MAGIC), neg1 = make_float2(-1.f, -1.f);
+  float2 accp = make_float2(0.f, 0.f), accm0 = accp, accm1 = accp;
+#pragma unroll
+  for (int i = 0; i < kPoly; ++i) {
+    float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(qm[2 * i], qm[2 * i + 1]));
+    d.x = fmaxf(d.x, -126.f);
+    d.y = fmaxf(d.y, -126.f);
+    const float2 t = __fadd2_rn(d, mg);
+    const float2 nn = __fadd2_rn(t, nmg);
+    const float2 f = __ffma2_rn(nn, neg1, d);
+    float2 p;
+    if (kDeg == 4) {
+      p = __ffma2_rn(make_float2(0.009570102207362652f, 0.009570102207362652f), f, make_float2(0.05591785907745361f, 0.05591785907745361f));
+      p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
+      p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
+      p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
+    } else {
+      p = __ffma2_rn(make_float2(0.0551716685295105f, 0.0551716685295105f), f, make_float2(0.2426111251115799f, 0.2426111251115799f));
+      p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+      p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    }
+    float2 e;
+    e.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    accp = __fadd2_rn(accp, e);
+  }
+#pragma unroll
+  for (int i = kPoly; i < 16; i += 2) {
+    const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(qm[2 * i], qm[2 * i + 1]));
+    const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3])), make_float2(qm[2 * i + 2], qm[2 * i + 3]));
+    accm0 = __fadd2_rn(accm0, make_float2(ex2(d0.x), ex2(d0.y)));
+    accm1 = __fadd2_rn(accm1, make_float2(ex2(d1.x), ex2(d1.y)));
+  }
+  const float2 tot = __fadd2_rn(__fadd2_rn(accm0, accm1), accp);
+  return tot.x + tot.y;
+}
+
+template <int kPoly, int kDeg, int KSTEPS>
+__global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int KS = KSTEPS * 8;
+  constexpr uint32_t tile_bytes = (uint32_t)BN * KS * 4u;       // one model tile image
+  constexpr uint32_t aq_block_bytes = (uint32_t)BM * KS * 4u;   // q operand of one row block
+  float* sAq = reinterpret_cast<float*>(smem);                                  // [MB][KS/4][BM][4]
+  unsigned char* sB = smem + (size_t)MB * aq_block_bytes;                       // [NSTAGE][KS/4][BN][4]
+  float* sPart = reinterpret_cast<float*>(sB + (size_t)NSTAGE * tile_bytes);    // [2][CHUNK][UNIT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * CHUNK * UNIT);
+  const uint32_t b_full = smem_u32(bars);  // barrier i of a group at +8 i
+  const uint32_t b_empty = b_full + 8u * NSTAGE;
+  const uint32_t t_full = b_empty + 8u * NSTAGE;
+  const uint32_t t_empty = t_full + 8u * NSLOT;
+  const uint32_t a_full = t_empty + 8u * NSLOT;
+  const uint32_t a_empty = a_full + 8u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NSLOT + 2);
+  float* mx = reinterpret_cast<float*>(tmem_slot + 4);  // [2][UNIT] row maxima of the two column halves
+  float* mstab = mx + 2 * UNIT;                          // [UNIT] per-frame stabiliser
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars + i, 1); mbar_init(bars + NSTAGE + i, MB); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(bars + 2 * NSTAGE + i, 1); mbar_init(bars + 2 * NSTAGE + NSLOT + i, EPI_WARPS / MB); }
+    mbar_init(bars + 2 * NSTAGE + 2 * NSLOT, EPI);
+    mbar_init(bars + 2 * NSTAGE + 2 * NSLOT + 1, MB);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid >= CTRL)
+    for (int i = tid - CTRL; i < 2 * CHUNK * UNIT; i += EPI) sPart[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t n_units = (a.total_frames + UNIT - 1) / UNIT;
+  const int S = a.n_models, NT = a.n_tiles;
+  constexpr size_t tile_floats = (size_t)BN * KS;
+
+  if (warp < CTRL / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
+  if (warp == 0) {
+    // ===================== producer =====================
+    const uint32_t sB_u32 = smem_u32(sB);
+    uint32_t stage = 0, ph = 0;
+    auto load = [&](const float* src) {
+      bar_spin(b_empty + 8u * stage, ph ^ 1u);
+      if (elect_one()) {
+        bar_arrive_expect_tx(b_full + 8u * stage, tile_bytes);
+        bulk_g2s_u32(sB_u32 + stage * tile_bytes, src, tile_bytes, b_full + 8u * stage);
+      }
+      __syncwarp();
+      if (++stage == NSTAGE) { stage = 0; ph ^= 1u; }
+    };
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int j = 0; j < NT; ++j) {
+        const float* tj = a.tiles + (size_t)j * (S + 1) * tile_floats;
+        load(tj);
+        load(tj + (size_t)(1 + a.ref_model) * tile_floats);
+      }
+      for (int m0 = 0; m0 < S; m0 += CHUNK) {
+        const int nm = min(CHUNK, S - m0);
+        for (int j = 0; j < NT; ++j) {
+          const float* tj = a.tiles + (size_t)j * (S + 1) * tile_floats;
+          load(tj);
+          const float* src = tj + (size_t)(1 + m0) * tile_floats;
+          for (int m = 0; m < nm; ++m, src += tile_floats) load(src);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 owns row block 0, warp 2 row block 1 =====================
+    const int g = warp - 1;
+    constexpr uint32_t lbo_a = BM * 16u, lbo_b = BN * 16u, sbo = 128u;
+    constexpr uint32_t ks_a = (2u * lbo_a) >> 4, ks_b = (2u * lbo_b) >> 4;  // one K = 8 step in descriptor units
+    constexpr uint32_t tile_units = tile_bytes >> 4;
+    const uint64_t aq_desc = make_desc(smem_u32(sAq) + (uint32_t)g * aq_block_bytes, lbo_a, sbo);
+    const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_b, sbo);
+    const uint32_t at = tmem_base + (uint32_t)(g * KS);
+    const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+    uint32_t stage = 0, bph = 0, s3 = 0, sph = 0, unit_idx = 0;
+    auto next_stage = [&]() { if (++stage == NSTAGE) { stage = 0; bph ^= 1u; } };
+    auto next_slot = [&]() { if (++s3 == 3) { s3 = 0; sph ^= 1u; } };
+    // one accumulator job of this row block: r part only (frame operand in TMEM)
+    auto job_r = [&]() {
+      bar_spin(b_full + 8u * stage, bph);
+      const uint32_t slot = (uint32_t)g + 2u * s3;
+      bar_spin(t_empty + 8u * slot, sph ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
+        const uint64_t bd = b_desc0 + (uint64_t)(stage * tile_units);
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : 0u);
+        bar_commit(t_full + 8u * slot);
+        bar_commit(b_empty + 8u * stage);
+      }
+      __syncwarp();
+      next_stage();
+      next_slot();
+    };
+    // q part (both operands in shared memory), optionally followed by the reference model's r part
+    auto job_q = [&](bool with_r) {
+      bar_spin(b_full + 8u * stage, bph);
+      const uint32_t stage_q = stage;
+      next_stage();
+      if (with_r) bar_spin(b_full + 8u * stage, bph);
+      const uint32_t slot = (uint32_t)g + 2u * s3;
+      bar_spin(t_empty + 8u * slot, sph ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
+        const uint64_t bq = b_desc0 + (uint64_t)(stage_q * tile_units);
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32(d_tmem, aq_desc + (uint64_t)(k * ks_a), bq + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : 0u);
+        if (with_r) {
+          const uint64_t br = b_desc0 + (uint64_t)(stage * tile_units);
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, br + (uint64_t)(k * ks_b), idesc, 1u);
+        }
+        bar_commit(t_full + 8u * slot);
+        bar_commit(b_empty + 8u * stage_q);
+        if (with_r) bar_commit(b_empty + 8u * stage);
+      }
+      __syncwarp();
+      if (with_r) next_stage();
+      next_slot();
+    };
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
+      bar_spin(a_full, unit_idx & 1u);
+      tc_fence_after();
+      for (int j = 0; j < NT; ++j) job_q(true);   // pre-pass: full logits of the reference model
+      for (int m0 = 0; m0 < S; m0 += CHUNK) {
+        const int nm = min(CHUNK, S - m0);
+        for (int j = 0; j < NT; ++j) {
+          job_q(false);                           // common part of tile j
+#pragma unroll 1
+          for (int m = 0; m < nm; ++m) job_r();
+        }
+      }
+      if (elect_one()) bar_commit(a_empty);
+      __syncwarp();
+    }
+  }
+  } else {
+    // ===================== epilogue warps (also build the frame operands) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    const int etid = tid - CTRL;               // 0..511
+    const int ew = warp - CTRL / 32;           // 0..15
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int g = (ew >> 2) & 1;               // row block
+    const int half = ew >> 3;                  // which 32 of the tile's 64 columns
+    const int row = quad * 32 + lane;          // accumulator row within the row block
+    const int urow = g * BM + row;             // row within the unit
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int frow = etid & (UNIT - 1), fpart = etid >> 8;  // finalisation role: frame row, model parity
+    const float LN2 = 0.69314718055994530942f;
+    float* my_part = sPart + (size_t)half * CHUNK * UNIT + urow;
+    uint32_t s3 = 0, sph = 0, unit_idx = 0;
+
+    // wait for the next accumulator job of this row block, pull this thread's 32 columns, free the slot
+    const uint32_t my_tmem = tmem_base + lane_addr + ACC_COL0 + (uint32_t)(g * BN + half * 32);  // slot s3 at + 2 BN s3
+    const uint32_t my_full = t_full + 8u * g, my_empty = t_empty + 8u * g;                       // slot s3 at + 16 s3
+    const bool lane0 = lane == 0;
+    auto fetch = [&](uint32_t (&r)[32]) {
+      bar_spin(my_full + 16u * s3, sph);
+      tc_fence_after();
+      tc_ld32_issue(my_tmem + 2u * BN * s3, r);
+      tc_ld_wait(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane0) bar_arrive(my_empty + 16u * s3);
+      if (++s3 == 3) { s3 = 0; sph ^= 1u; }
+    };
+
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
+      const int64_t frame0 = u * UNIT;
+      bar_spin(a_empty, (unit_idx & 1u) ^ 1u);
+      tc_fence_after();
+      {
+        // ---- q operand [x^2, 1, 1, 0..] in shared memory: row r of block mb at ((mb*KS/4 + j/4)*BM + r)*4 + j%4
+        const int64_t fr = frame0 + frow;
+        const bool live = fr < a.total_frames;
+        const float* xr = a.feats + fr * a.D;
+        float* dst = sAq + (size_t)(frow >> 7) * (BM * KS) + (size_t)(frow & (BM - 1)) * 4;
+        const int j0 = fpart * (KS >> 1), j1 = j0 + (KS >> 1);
+        for (int j = j0; j < j1; ++j) {
+          float v = 0.f;
+          if (j < a.D) { const float x = live ? xr[j] : 0.f; v = rna_tf32(x * x); }
+          else if (j < a.D + 2) v = 1.f;
+          dst[(size_t)(j >> 2) * (BM * 4) + (j & 3)] = v;
+        }
+      }
+      {
+        // ---- r operand [x, 1, 1, 0..] straight into TMEM: lane == row, column == contraction index
+        const int64_t fe = frame0 + urow;
+        const bool live = fe < a.total_frames;
+        const float* xr = a.feats + fe * a.D;
+        for (int c = half; c < KSTEPS; c += 2) {
+          uint32_t v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = 8 * c + e;
+            float x = 0.f;
+            if (j < a.D) x = live ? rna_tf32(xr[j]) : 0.f;
+            else if (j < a.D + 2) x = 1.f;
+            v[e] = __float_as_uint(x);
+          }
+          tc_st8(tmem_base + lane_addr + (uint32_t)(g * KS + 8 * c), v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      bar_arrive(a_full);
+
+      // ---- finalisation bookkeeping for frame `frow`
+      const int64_t ff = frame0 + frow;
+      const bool flive = ff < a.total_frames;
+      const int futt = flive ? find_segment(a.offsets, a.n_utts, ff) : -1;
+      float fwgt = 1.f;
+      if (futt >= 0 && a.normalize) fwgt = 1.f / (float)(a.offsets[futt + 1] - a.offsets[futt]);
+
+      // ---- pre-pass: per-frame maximum logit of the reference model -> stabiliser
+      float rmax = -3.0e38f;
+      for (int j = 0; j < NT; ++j) {
+        uint32_t r[32];
+        fetch(r);
+        float cm = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+        for (int i = 3; i < 31; i += 2) cm = max3(cm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        rmax = max3(rmax, cm, __uint_as_float(r[31]));
+      }
+      mx[half * UNIT + urow] = rmax;
+      named_bar_sync(1 + g, 2 * BM);
+      const float m_t = rintf(fmaxf(mx[urow], mx[UNIT + urow]));
+      if (half == 0) mstab[urow] = m_t;
+
+      // ---- main pass, a chunk of models at a time
+      for (int m0 = 0; m0 < S; m0 += CHUNK) {
+        const int nm = min(CHUNK, S - m0);
+        for (int j = 0; j < NT; ++j) {
+          float qm[32];
+          {
+            uint32_t r[32];
+            fetch(r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) qm[i] = __uint_as_float(r[i]) - m_t;
+          }
+          float* dst = my_part;
+#pragma unroll 1
+          for (int m = 0; m < nm; ++m, dst += UNIT) {
+            uint32_t r[32];
+            fetch(r);
+            *dst += exp_sum32<kPoly, kDeg>(r, qm);
+          }
+        }
+        // ---- partial sums of this chunk -> per-frame log-likelihood -> per-utterance score
+        named_bar_sync(3, EPI);
+        {
+          const float mf = mstab[frow];
+          float* p0 = sPart + (size_t)fpart * UNIT + frow;
+          for (int m = fpart; m < nm; m += 2, p0 += 2 * UNIT) {
+            const float v = p0[0] + p0[CHUNK * UNIT];
+            p0[0] = 0.f;
+            p0[CHUNK * UNIT] = 0.f;
+            float lse = (mf + lg2(v)) * LN2;
+            if (!(v > 7.9e-31f && v < 1.2e30f)) lse = __int_as_float(0x7fc00000);  // outside [2^-100, 2^100]: sv_fixup_kernel
+            if (flive && a.frame_lse) a.frame_lse[(int64_t)(m0 + m) * a.total_frames + ff] = lse;
+            warp_segmented_atomic_add(a.scores, futt, S, m0 + m, lse * fwgt, lane);
+          }
+        }
+        named_bar_sync(3, EPI);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// Re-score the (utterance, model) pairs the tensor kernel gave up on (NaN score): one warp per pair, FP32 online
+// log-sum-exp over the same TF32-rounded model tiles, exact frames.
+__global__ void __launch_bounds__(256) sv_fixup_kernel(const Args a, int64_t n_pairs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int S = a.n_models, KS = a.KS, D = a.D;
+  const size_t tile_floats = (size_t)BN * KS;
+  const float LN2 = 0.69314718055994530942f;
+  for (int64_t p = warp0; p < n_pairs; p += n_warps) {
+    const double cur = a.scores[p];
+    if (cur == cur && fabs(cur) < 1.0e300) continue;
+    const int64_t utt = p / S;
+    const int m = (int)(p % S);
+    const int64_t t0 = a.offsets[utt], t1 = a.offsets[utt + 1];
+    double total = 0.0;
+    for (int64_t t = t0; t < t1; ++t) {
+      const float* xr = a.feats + t * D;
+      float mrun = -3.0e38f, srun = 0.f;
+      for (int c = lane; c < a.n_tiles * BN; c += 32) {
+        const float* tq = a.tiles + ((size_t)(c / BN) * (S + 1)) * tile_floats;
+        const float* tr = tq + (size_t)(1 + m) * tile_floats;
+        const int n = c % BN;
+        auto at = [&](const float* tile, int j) { return tile[((size_t)(j >> 2) * BN + n) * 4 + (j & 3)]; };
+        float l = at(tq, D) + at(tq, D + 1) + at(tr, D) + at(tr, D + 1);
+        for (int j = 0; j < D; ++j) {
+          const float x = xr[j];
+          l = fmaf(x, at(tr, j), l);
+          l = fmaf(x * x, at(tq, j), l);
+        }
+        const float mn = fmaxf(mrun, l);
+        srun = srun * exp2f(mrun - mn) + exp2f(l - mn);
+        mrun = mn;
+      }
+      const float mall = warp_max(mrun);
+      const float sall = warp_sum(srun * exp2f(mrun - mall));
+      const float lse = (mall + log2f(sall)) * LN2;
+      if (lane == 0 && a.frame_lse) a.frame_lse[(int64_t)m * a.total_frames + t] = lse;
+      total += (double)lse;
+    }
+    if (lane == 0) a.scores[p] = a.normalize && t1 > t0 ? total / (double)(t1 - t0) : total;
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int kPoly, int kDeg, int KSTEPS>
+static int launch_one(const Args& a, unsigned grid, cudaStream_t st) {
+  constexpr size_t tile_bytes = (size_t)BN * KSTEPS * 8 * 4, aq_bytes = (size_t)UNIT * KSTEPS * 8 * 4;
+  constexpr size_t smem = aq_bytes + NSTAGE * tile_bytes + (size_t)2 * CHUNK * UNIT * sizeof(float) +
+                          (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 + 3 * UNIT * sizeof(float);
+  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_sv_kernel<kPoly, kDeg, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gmm_score_sv_kernel<kPoly, kDeg, KSTEPS><<<grid, THREADS, smem, st>>>(a);
+  return SSP_OK;
+}
+template <int kPoly, int kDeg>
+static int launch_ks(const Args& a, unsigned grid, cudaStream_t st) {
+  switch (a.KS) {
+    case 8: return launch_one<kPoly, kDeg, 1>(a, grid, st);
+    case 16: return launch_one<kPoly, kDeg, 2>(a, grid, st);
+    case 24: return launch_one<kPoly, kDeg, 3>(a, grid, st);
+    case 32: return launch_one<kPoly, kDeg, 4>(a, grid, st);
+    case 40: return launch_one<kPoly, kDeg, 5>(a, grid, st);
+    case 48: return launch_one<kPoly, kDeg, 6>(a, grid, st);
+    case 56: return launch_one<kPoly, kDeg, 7>(a, grid, st);
+    case 64: return launch_one<kPoly, kDeg, 8>(a, grid, st);
+  }
+  set_error("ssp_gmm_score_shared: contraction length %d is not a multiple of 8 in [8, 64]", a.KS);
+  return SSP_EINVAL;
+}
+
+}  // namespace sv
+
+int64_t score_sv_workspace_bytes(const SvLayout&) { return 0; }
+
+int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
+                    const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* /*workspace*/,
+                    cudaStream_t st) {
+  using namespace sv;
+  SSP_CUDA_OK(cudaMemsetAsync(scores, 0, sizeof(double) * n_utts * L.n_models, st));
+  if (total_frames == 0) return SSP_OK;
+  Args a;
+  a.feats = feats;
+  a.offsets = offsets;
+  a.n_utts = n_utts;
+  a.total_frames = total_frames;
+  a.tiles = (const float*)pack;
+  a.n_models = L.n_models;
+  a.n_tiles = L.Kp / BN;
+  a.D = L.D;
+  a.KS = L.KS;
+  a.ref_model = ref_model;
+  a.normalize = normalize ? 1 : 0;
+  a.scores = scores;
+  a.frame_lse = frame_lse;
+  const int64_t n_units = (total_frames + UNIT - 1) / UNIT;
+  const unsigned grid = (unsigned)(n_units < num_sms() ? n_units : num_sms());
+  static int poly = -1, deg = -1;
+  if (poly < 0) {
+    const char* e = getenv("SSP_SV_POLY_PAIRS");  // tuning knobs: share of the exponentials on the FMA pipe, degree
+    poly = e ? atoi(e) : kDefaultPolyPairs;
+    e = getenv("SSP_SV_POLY_DEG");
+    deg = e ? atoi(e) : kDefaultPolyDeg;
+  }
+  int rc = SSP_EINVAL;
+  if (deg == 4 && poly == 0) rc = launch_ks<0, 4>(a, grid, st);
+  else if (deg == 4 && poly == 2) rc = launch_ks<2, 4>(a, grid, st);
+  else if (deg == 4 && poly == 4) rc = launch_ks<4, 4>(a, grid, st);
+  else if (deg == 4 && poly == 6) rc = launch_ks<6, 4>(a, grid, st);
+  else if (deg == 4 && poly == 8) rc = launch_ks<8, 4>(a, grid, st);
+  else if (deg == 3 && poly == 6) rc = launch_ks<6, 3>(a, grid, st);
+  else if (deg == 3 && poly == 8) rc = launch_ks<8, 3>(a, grid, st);
+  else set_error("SSP_SV_POLY_PAIRS / SSP_SV_POLY_DEG: unsupported combination (%d, %d)", poly, deg);
+  if (rc != SSP_OK) return rc;
+  SSP_LAUNCH_CHECK("gmm_score_sv_kernel");
+  const int64_t n_pairs = n_utts * L.n_models;
+  const int64_t want = (n_pairs + 7) / 8, cap = 4 * (int64_t)num_sms();
+  sv_fixup_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a, n_pairs);
+  SSP_LAUNCH_CHECK("sv_fixup_kernel");
+  return SSP_OK;
+}
+
+}  // namespace ssp

@@ -125,6 +125,75 @@ class ModelSet:
         return n, f, s, ll
 
 
+class SharedModelSet:
+    """``n_models`` diagonal GMMs that share ONE weight vector and ONE variance matrix and differ in their means --
+    what mean-only MAP enrolment from a UBM yields (:func:`~speech_signal_processing_b200.ubm.map_adapt` with
+    ``adapt=("means",)``).  Scored by the shared-variance tensor kernel (``ssp_gmm_score_shared``): the part of the
+    log-likelihood common to all models is evaluated once per frame block, the per-model contraction is D + 2 long
+    instead of 2D + 2.  Results equal :class:`ModelSet` ``.score(precision="tf32")`` on the expanded set."""
+
+    def __init__(self, weights, variances, means, ref_model=-1, device=None):
+        torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+        def dev(a):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=self.device, dtype=torch.float64).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+
+        w, var, mu = dev(weights), dev(variances), dev(means)
+        if mu.dim() == 2:
+            mu = mu[None]
+        if w.dim() != 1 or var.dim() != 2 or mu.dim() != 3 or mu.shape[1:] != var.shape or w.shape[0] != var.shape[0]:
+            raise ValueError("expected weights (K,), variances (K,D), means (S,K,D)")
+        self.n_models, self.n_comp, self.n_feat = (int(v) for v in mu.shape)
+        self.ref_model = int(ref_model) % self.n_models
+        self.dims = _lib.GmmDims(self.n_models, self.n_comp, self.n_feat)
+        nbytes = int(self.lib.ssp_gmm_shared_pack_bytes(C.byref(self.dims)))
+        if nbytes <= 0:
+            raise ValueError(f"unsupported dims K={self.n_comp} D={self.n_feat} for the shared-variance kernel (need D <= 62)")
+        self.pack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.ssp_gmm_pack_shared(_lib.ptr(w), _lib.ptr(var), _lib.ptr(mu), C.byref(self.dims), _lib.ptr(self.pack),
+                                                _lib.stream_ptr()), "ssp_gmm_pack_shared")
+        self._params = (w, var, mu)
+        self._ws = torch.empty(int(self.lib.ssp_gmm_score_shared_workspace_bytes(C.byref(self.dims))), dtype=torch.uint8,
+                               device=self.device)
+
+    @staticmethod
+    def shares_base(weights, variances) -> bool:
+        """True if every model of an (S,K) / (S,K,D) parameter stack has the first model's weights and variances."""
+        torch = _lib.require_cuda()
+        if isinstance(weights, torch.Tensor):
+            return bool((weights == weights[:1]).all().item() and (variances == variances[:1]).all().item())
+        weights, variances = np.asarray(weights), np.asarray(variances)
+        return bool((weights == weights[:1]).all() and (variances == variances[:1]).all())
+
+    def score(self, feats, frame_offsets, precision="tf32", want_frame_lse=False):
+        """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None)."""
+        torch = _lib.require_cuda()
+        if precision not in ("tf32", "auto"):
+            raise ValueError("the shared-variance kernel computes in TF32; expand to a ModelSet for precision='fp32'")
+        frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
+        n_utts, total = len(frame_offsets) - 1, int(frame_offsets[-1])
+        if feats.shape[1] != self.n_feat:
+            raise ValueError(f"X has {feats.shape[1]} features, but the models expect {self.n_feat}")
+        d_off = torch.as_tensor(frame_offsets, device=self.device)
+        scores = torch.empty((n_utts, self.n_models), dtype=torch.float64, device=self.device)
+        lse = torch.empty((self.n_models, total), dtype=torch.float32, device=self.device) if want_frame_lse else None
+        rc = self.lib.ssp_gmm_score_shared(_lib.ptr(feats), _lib.ptr(d_off), n_utts, total, _lib.ptr(self.pack),
+                                           C.byref(self.dims), self.ref_model, _lib.ptr(scores), _lib.ptr(lse),
+                                           _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "ssp_gmm_score_shared")
+        self._keep = d_off
+        return scores, lse
+
+    def expand(self) -> "ModelSet":
+        """The same models as a general :class:`ModelSet` (weights and variances replicated)."""
+        w, var, mu = self._params
+        return ModelSet(w[None].expand(self.n_models, -1), mu, var[None].expand(self.n_models, -1, -1), device=self.device)
+
+
 def score_matrix(utts, models, precision="tf32", device=None):
     """``pred[j, i] = models[i].score(utts[j])`` for all pairs in one launch (GMM_UBM.py:182-185,
     191-194 without the Python double loop).  ``models``: list of fitted :class:`GaussianMixture`

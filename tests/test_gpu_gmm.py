@@ -292,3 +292,72 @@ def test_full_size_identify_properties():
             ref = ogmm.score(x, w, host_mu[m], var)
             assert abs(float(s32[r, m]) - ref) <= 2e-6 * abs(ref)
             assert abs(float(scores[i, m]) - ref) <= 1e-4 * abs(ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# shared-variance tensor kernel (mean-only MAP speaker sets): ssp_gmm_pack_shared / ssp_gmm_score_shared
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,d,n_spk", [(64, 39, 5), (100, 13, 3), (200, 26, 7), (1024, 39, 9)])
+def test_shared_variance_scoring_matches_oracle(k, d, n_spk):
+    import torch
+
+    w, mu, var = synth.synth_ubm(k, d, seed=11)
+    spk_mu = np.concatenate([synth.synth_speaker_means(mu, n_spk, seed=12, shift=0.3), mu[None]])  # last = UBM
+    lens = [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 298, 500]
+    utts = [synth.sample_gmm(w, spk_mu[i % n_spk], var, n, seed=200 + i) for i, n in enumerate(lens)]
+    sms = ssp.SharedModelSet(w, var, spk_mu)
+    feats, offs = ssp.mixture.concat_utterances(utts, sms.device)
+    got, lse = sms.score(feats, offs, want_frame_lse=True)
+    got, lse = got.cpu().numpy(), lse.cpu().numpy()
+    want = np.array([[ogmm.score(u, w, m, var) for m in spk_mu] for u in utts])
+    long_enough = np.array(lens) >= 31
+    np.testing.assert_allclose(got, want, rtol=6 * REL["tf32"], atol=0)
+    np.testing.assert_allclose(got[long_enough], want[long_enough], rtol=REL["tf32"], atol=0)
+    assert (got[:, :n_spk].argmax(axis=1) == want[:, :n_spk].argmax(axis=1))[long_enough].all()
+    # per-frame log-likelihoods (GaussianMixture.score_samples) of every model
+    x = np.concatenate(utts)
+    for i in (0, n_spk):
+        ref = ogmm.score_samples(x, w, spk_mu[i], var)
+        np.testing.assert_allclose(lse[i], ref, rtol=3e-3, atol=0)
+    # and it is the same thing as the general (FP32) kernel on the expanded set
+    gen, _ = sms.expand().score(feats, offs, precision="fp32")
+    np.testing.assert_allclose(got[long_enough], gen.cpu().numpy()[long_enough], rtol=REL["tf32"], atol=0)
+    torch.cuda.synchronize()
+
+
+def test_shared_variance_scoring_rescues_models_far_from_the_reference():
+    """A mean set nowhere near the reference model underflows the fixed per-frame stabiliser; the kernel marks the
+    pair and the FP32 fix-up pass re-scores it, so the result is still right."""
+    k, d = 64, 39
+    w, mu, var = synth.synth_ubm(k, d, seed=21)
+    far = mu + 40.0  # ~ -30000 nats per frame below the reference
+    means = np.stack([mu + 0.1, far, mu])
+    utts = [synth.sample_gmm(w, mu, var, n, seed=300 + n) for n in (64, 298)]
+    sms = ssp.SharedModelSet(w, var, means)
+    feats, offs = ssp.mixture.concat_utterances(utts, sms.device)
+    got = sms.score(feats, offs)[0].cpu().numpy()
+    want = np.array([[ogmm.score(u, w, m, var) for m in means] for u in utts])
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, want, rtol=REL["tf32"], atol=0)
+
+
+def test_shared_variance_many_units_and_models():
+    """More frames than one wave of 256-frame units x more models than accumulator slots; decisions equal FP32."""
+    k, d, n_spk = 256, 39, 33
+    w, mu, var = synth.synth_ubm(k, d, seed=31)
+    spk_mu = np.concatenate([synth.synth_speaker_means(mu, n_spk, seed=32, shift=0.25), mu[None]])
+    import torch
+
+    dev = torch.device("cuda")
+    n_utts, t = 400, 298  # 119 200 frames = 466 units > 148 SMs
+    labels = torch.arange(n_utts, device=dev).repeat_interleave(t) % n_spk
+    feats = synth.synth_features_torch(n_utts * t, d, torch.as_tensor(spk_mu[:n_spk], device=dev), torch.as_tensor(var, device=dev),
+                                       labels, seed=5, device=dev)
+    offs = np.arange(n_utts + 1, dtype=np.int64) * t
+    sms = ssp.SharedModelSet(w, var, spk_mu)
+    a = sms.score(feats, offs)[0].cpu().numpy()
+    b = sms.expand().score(feats, offs, precision="fp32")[0].cpu().numpy()
+    assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
+    assert (a[:, :n_spk].argmax(axis=1) == b[:, :n_spk].argmax(axis=1)).all()
+    a2 = sms.score(feats, offs)[0].cpu().numpy()  # the workspace is left clean: a second call gives the same answer
+    assert np.abs(a - a2).max() <= 1e-9 * np.abs(a).max()
