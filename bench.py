@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--speakers", type=int, default=N_SPK)
     ap.add_argument("--components", type=int, default=K_COMP)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--scorer", default="shared", choices=["shared", "general"],
+                    help="shared: the shared-variance tensor kernel (mean-only MAP speakers keep the UBM's weights and "
+                         "variances); general: the kernel for arbitrary model sets")
     ap.add_argument("--cpu-utts", type=int, default=0, help="reference arm: utterances per step (0 = auto-size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -256,6 +259,9 @@ def run_b200(a):
     models = ssp.ModelSet(torch.cat([sw, torch.as_tensor(w, device=dev)[None]]),
                           torch.cat([smu, torch.as_tensor(mu, device=dev)[None]]),
                           torch.cat([svar, t_var[None]]), device=dev)  # model S is the UBM
+    shared = a.scorer == "shared" and a.precision == "tf32"
+    scorer = ssp.SharedModelSet(torch.as_tensor(w, device=dev), t_var, torch.cat([smu, torch.as_tensor(mu, device=dev)[None]]),
+                                ref_model=S, device=dev) if shared else models
     del sw, smu, svar
     # ---- test audio: synthetic int16 PCM, distinct per rank, kept both in HBM and in pinned host memory
     g = torch.Generator(device=dev)
@@ -284,7 +290,7 @@ def run_b200(a):
         feats, foffs, _ = fe.extract_device(pcm_dev, sample_offsets)
         if timed:
             ev[2].record()
-        scores, _ = models.score(feats, foffs, precision=a.precision)
+        scores, _ = scorer.score(feats, foffs, precision=a.precision)
         if timed:
             ev[3].record()
         llr = scores[:, :S] - scores[:, S:]
@@ -342,7 +348,7 @@ def run_b200(a):
     # GPU-vs-GPU sanity on a sub-sample: tensor-core decisions == FP32 CUDA-core decisions
     sub = 64
     feats, foffs, _ = fe.extract_device(pcm[: sub * UTT_SAMPLES], sample_offsets[: sub + 1])
-    s_tc, _ = models.score(feats, foffs, precision=a.precision)
+    s_tc, _ = scorer.score(feats, foffs, precision=a.precision)
     s_fp, _ = models.score(feats, foffs, precision="fp32")
     dec_tc = (s_tc[:, :S] - s_tc[:, S:]).argmax(dim=1)
     dec_fp = (s_fp[:, :S] - s_fp[:, S:]).argmax(dim=1)
@@ -359,17 +365,28 @@ def run_b200(a):
         bound = "tensor"
     else:
         peak, peak_note, bound = 70.0, "nominal FP32 CUDA-core FMA peak (no measured figure)", "tensor"
+    kernel = "gmm_score_sv_kernel" if shared else ("gmm_score_tc_kernel" if a.precision == "tf32" else "gmm_score_simt_kernel")
+    roof_extra = {}
+    if shared:
+        # with the shared-variance shortcut the executed tensor work is smaller than the algorithmic 4DK:
+        # per (frame, model) 2 * KS * Kp with KS = roundup(D + 2, 8), plus the common part once per 32 models
+        ks, kp = (D + 2 + 7) // 8 * 8, (K + 63) // 64 * 64
+        exec_flop = 2.0 * ks * kp * (frames / a.steps) * (n_models * (1.0 + 1.0 / 32.0) + 2.0)
+        roof_extra = {"executed_tflops": exec_flop / (k_ms * 1e-3) / 1e12, "executed_frac": exec_flop / (k_ms * 1e-3) / 1e12 / peak,
+                      "note": "achieved = algorithmic 4*D*K FLOP per (frame, model); the shared-variance kernel executes "
+                              "2*(D+2 padded to 48)*K on the tensor pipe and is bound by the 3.05e12 exponentials of the "
+                              "log-sum-exp (MUFU ex2 + an FMA-pipe polynomial share), see profiles/"}
     line = {
         "metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32" if a.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "parallelism": f"utterances sharded x{world}, models replicated",
-                   "l2": "inputs per step (0.96 GB PCM, 0.33 GB model tiles) exceed the 126 MB L2",
+                   "l2": "inputs per step (0.96 GB PCM, 0.2-0.33 GB model tiles) exceed the 126 MB L2", "scorer": a.scorer,
                    "frames_x_models_per_s": total_frames * n_models / (dev_ms * 1e-3)},
         "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_pcm.numel() * 2),
                 "d2h_bytes_per_step": int(host_dec.numel() * 8), "ms_per_step": e2e_ms / a.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": bound, "kernel": "gmm_score_tc_kernel" if a.precision == "tf32" else "gmm_score_simt_kernel",
+        "roofline": {"bound": bound, "kernel": kernel, **roof_extra,
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (dev_ms / a.steps), "peak_source": peak_note,
                      "frac_of_bf16_peak": achieved / peaks["bf16_tflops_sustained"]},

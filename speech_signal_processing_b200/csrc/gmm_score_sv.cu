@@ -50,7 +50,7 @@ constexpr int THREADS = CTRL + EPI;
 constexpr int CTRL_REGS = 32, EPI_REGS = 112;  // launched at 96: 128 x (96 - 32) registers released == 512 x (112 - 96) acquired
 constexpr int CHUNK = 32;                // models per chunk: partial sums [2 column halves][CHUNK][UNIT] fp32 = 64 KB
 constexpr uint32_t ACC_COL0 = 128;       // TMEM: [0, 2 KS) frame operand of the two row blocks, [128, 512) accumulators
-constexpr int kDefaultPolyPairs = 6;
+constexpr int kDefaultPolyPairs = 4;  // measured on B200 (2000 utts x 1001 models): 0/4/6/8 pairs -> 163/136/142/155 ms
 constexpr int kDefaultPolyDeg = 4;
 
 struct Args {
@@ -112,16 +112,29 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_st32f(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+        "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+        "f"(v[30]), "f"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 
-// sum over 32 accumulator columns of 2^(r + qm).  kPoly of the 16 column pairs go to the FMA pipe:
+// sum over 32 accumulator columns of 2^(r + qm) (kAdd) or 2^r (the accumulator already held qm when the MMA ran).
+// kPoly of the 16 column pairs go to the FMA pipe:
 // 2^d = 2^n p(f), n = round(d) by the 1.5 * 2^23 magic add, f = d - n in [-0.5, 0.5], p = minimax polynomial
 // (degree 4: 2.7e-6 relative, degree 3: 7.5e-5), 2^n applied by adding n to the exponent field; the rest is MUFU ex2.
-template <int kPoly, int kDeg>
+template <int kPoly, int kDeg, bool kAdd>
 __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float (&qm)[32]) {
   static_assert(kPoly % 2 == 0 && kPoly <= 16, "pairs are consumed two at a time");
   const float MAGIC = 12582912.f;  // 1.5 * 2^23
@@ -129,7 +142,8 @@ __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float 
   float2 accp = make_float2(0.f, 0.f), accm0 = accp, accm1 = accp;
 #pragma unroll
   for (int i = 0; i < kPoly; ++i) {
-    float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(qm[2 * i], qm[2 * i + 1]));
+    float2 d = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    if (kAdd) d = __fadd2_rn(d, make_float2(qm[2 * i], qm[2 * i + 1]));
     d.x = fmaxf(d.x, -126.f);
     d.y = fmaxf(d.y, -126.f);
     const float2 t = __fadd2_rn(d, mg);
@@ -153,8 +167,12 @@ __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float 
   }
 #pragma unroll
   for (int i = kPoly; i < 16; i += 2) {
-    const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(qm[2 * i], qm[2 * i + 1]));
-    const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3])), make_float2(qm[2 * i + 2], qm[2 * i + 3]));
+    float2 d0 = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    float2 d1 = make_float2(__uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3]));
+    if (kAdd) {
+      d0 = __fadd2_rn(d0, make_float2(qm[2 * i], qm[2 * i + 1]));
+      d1 = __fadd2_rn(d1, make_float2(qm[2 * i + 2], qm[2 * i + 3]));
+    }
     accm0 = __fadd2_rn(accm0, make_float2(ex2(d0.x), ex2(d0.y)));
     accm1 = __fadd2_rn(accm1, make_float2(ex2(d1.x), ex2(d1.y)));
   }
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     auto next_stage = [&]() { if (++stage == NSTAGE) { stage = 0; bph ^= 1u; } };
     auto next_slot = [&]() { if (++s3 == 3) { s3 = 0; sph ^= 1u; } };
     // one accumulator job of this row block: r part only (frame operand in TMEM)
-    auto job_r = [&]() {
+    auto job_r = [&](uint32_t preinit) {
       bar_spin(b_full + 8u * stage, bph);
       const uint32_t slot = (uint32_t)g + 2u * s3;
       bar_spin(t_empty + 8u * slot, sph ^ 1u);
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
         const uint64_t bd = b_desc0 + (uint64_t)(stage * tile_units);
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : preinit);
         bar_commit(t_full + 8u * slot);
         bar_commit(b_empty + 8u * stage);
       }
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         for (int j = 0; j < NT; ++j) {
           job_q(false);                           // common part of tile j
 #pragma unroll 1
-          for (int m = 0; m < nm; ++m) job_r();
+          for (int m = 0; m < nm; ++m) job_r(m >= 2 ? 1u : 0u);
         }
       }
       if (elect_one()) bar_commit(a_empty);
@@ -332,11 +350,16 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     const uint32_t my_tmem = tmem_base + lane_addr + ACC_COL0 + (uint32_t)(g * BN + half * 32);  // slot s3 at + 2 BN s3
     const uint32_t my_full = t_full + 8u * g, my_empty = t_empty + 8u * g;                       // slot s3 at + 16 s3
     const bool lane0 = lane == 0;
-    auto fetch = [&](uint32_t (&r)[32]) {
+    // `init` != nullptr: the job three ahead (same slot) belongs to the same component tile -> leave q - m_t behind
+    auto fetch = [&](uint32_t (&r)[32], const float (*init)[32] = nullptr) {
       bar_spin(my_full + 16u * s3, sph);
       tc_fence_after();
       tc_ld32_issue(my_tmem + 2u * BN * s3, r);
       tc_ld_wait(r);
+      if (init) {
+        tc_st32f(my_tmem + 2u * BN * s3, *init);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
       tc_fence_before();
       __syncwarp();
       if (lane0) bar_arrive(my_empty + 16u * s3);
@@ -410,19 +433,40 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
+          // Job i of this tile (i = 0: common part, i = 1 + m: model m) shares its accumulator slot with job i + 3.
+          // If that one is a model of the same tile, q - m_t is left in the slot and the MMA accumulates on top of
+          // it, so the sum needs no add; the first two models of a tile (their slots were last used by the previous
+          // tile) add q - m_t here instead.
           float qm[32];
           {
             uint32_t r[32];
-            fetch(r);
+            bar_spin(my_full + 16u * s3, sph);
+            tc_fence_after();
+            tc_ld32_issue(my_tmem + 2u * BN * s3, r);
+            tc_ld_wait(r);
 #pragma unroll
             for (int i = 0; i < 32; ++i) qm[i] = __uint_as_float(r[i]) - m_t;
+            if (nm > 2) {
+              tc_st32f(my_tmem + 2u * BN * s3, qm);
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane0) bar_arrive(my_empty + 16u * s3);
+            if (++s3 == 3) { s3 = 0; sph ^= 1u; }
           }
           float* dst = my_part;
 #pragma unroll 1
-          for (int m = 0; m < nm; ++m, dst += UNIT) {
+          for (int m = 0; m < nm && m < 2; ++m, dst += UNIT) {
             uint32_t r[32];
-            fetch(r);
-            *dst += exp_sum32<kPoly, kDeg>(r, qm);
+            fetch(r, m + 3 < nm ? &qm : nullptr);
+            *dst += exp_sum32<kPoly, kDeg, true>(r, qm);
+          }
+#pragma unroll 1
+          for (int m = 2; m < nm; ++m, dst += UNIT) {
+            uint32_t r[32];
+            fetch(r, m + 3 < nm ? &qm : nullptr);
+            *dst += exp_sum32<kPoly, kDeg, false>(r, qm);
           }
         }
         // ---- partial sums of this chunk -> per-frame log-likelihood -> per-utterance score

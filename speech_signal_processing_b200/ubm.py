@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from . import frontend as fe
-from .mixture import GaussianMixture, ModelSet, concat_utterances
+from .mixture import GaussianMixture, ModelSet, SharedModelSet, concat_utterances
 
 
 def map_adapt(ubm: GaussianMixture, speaker_frames, relevance: float = 16.0, adapt=("means",), device=None):
@@ -51,6 +51,20 @@ def map_adapt(ubm: GaussianMixture, speaker_frames, relevance: float = 16.0, ada
     return ow, omu, ovar
 
 
+def map_enrol(ubm: GaussianMixture, speaker_frames, relevance: float = 16.0, device=None) -> SharedModelSet:
+    """Mean-only MAP enrolment straight into the form the shared-variance scoring kernel wants: a
+    :class:`SharedModelSet` of the S adapted mean sets plus the UBM's own means as model S (``ubm_index``), all with the
+    UBM's weights and variances.  ``identify(utts, map_enrol(...))`` then gives the LLR matrix of GMM_UBM.py:191-197
+    with one kernel launch and a per-speaker contraction of D + 2 instead of 2D + 2."""
+    torch = _lib.require_cuda()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    _, mu, _ = map_adapt(ubm, speaker_frames, relevance=relevance, adapt=("means",), device=dev)
+    uw, umu, uvar = ubm._model_set()._params
+    sms = SharedModelSet(uw[0], uvar[0], torch.cat([mu, umu]), ref_model=-1, device=dev)
+    sms.ubm_index = sms.n_models - 1
+    return sms
+
+
 def identify(utts, speakers, ubm=None, precision="tf32", device=None):
     """LLR matrix and decisions for all (utterance, speaker) pairs (GMM_UBM.py:191-197).
 
@@ -62,7 +76,14 @@ def identify(utts, speakers, ubm=None, precision="tf32", device=None):
     torch = _lib.require_cuda()
     dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     feats, offs = concat_utterances(utts, dev)
-    if isinstance(speakers, ModelSet):
+    if isinstance(speakers, SharedModelSet) and getattr(speakers, "ubm_index", None) is not None and ubm is None:
+        # the UBM rides along as one of the mean sets (map_enrol): one launch scores everything
+        scores, _ = speakers.score(feats, offs)
+        k = speakers.ubm_index
+        keep = [i for i in range(speakers.n_models) if i != k]
+        pred = (scores[:, keep] - scores[:, k : k + 1]).cpu().numpy()
+        return pred, pred.argmax(axis=1)
+    if isinstance(speakers, (ModelSet, SharedModelSet)):
         ms = speakers
     else:
         ms = ModelSet(np.stack([np.asarray(m.weights_) for m in speakers]), np.stack([np.asarray(m.means_) for m in speakers]),

@@ -292,6 +292,13 @@ def test_full_size_identify_properties():
             ref = ogmm.score(x, w, host_mu[m], var)
             assert abs(float(s32[r, m]) - ref) <= 2e-6 * abs(ref)
             assert abs(float(scores[i, m]) - ref) <= 1e-4 * abs(ref)
+    # the shared-variance kernel (the bench's scorer) on the same full-size job: same scores, same decisions
+    sms = ssp.SharedModelSet(w, t_var, torch.cat([t_mu, torch.as_tensor(mu, device=dev)[None]]), ref_model=s)
+    sv, _ = sms.score(feats, offs)
+    assert bool(torch.isfinite(sv).all())
+    assert float(((sv - scores).abs() / scores.abs()).max()) < 2e-5
+    assert bool(((sv[:, :s] - sv[:, s:]).argmax(dim=1) == truth).all())
+    assert float(((sv[sub] - s32).abs() / s32.abs()).max()) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------
@@ -361,3 +368,26 @@ def test_shared_variance_many_units_and_models():
     assert (a[:, :n_spk].argmax(axis=1) == b[:, :n_spk].argmax(axis=1)).all()
     a2 = sms.score(feats, offs)[0].cpu().numpy()  # the workspace is left clean: a second call gives the same answer
     assert np.abs(a - a2).max() <= 1e-9 * np.abs(a).max()
+
+
+def test_map_enrol_identify_equals_general_path():
+    """map_enrol -> identify (one shared-variance launch) == map_adapt -> ModelSet -> identify with a separate UBM."""
+    k, d, n_spk = 128, 39, 12
+    w, mu, var = synth.synth_ubm(k, d, seed=41)
+    spk_mu = synth.synth_speaker_means(mu, n_spk, seed=42, shift=0.4)
+    ubm = ssp.GaussianMixture.from_params(w, mu, var)
+    enrol = [synth.sample_gmm(w, spk_mu[i], var, 900, seed=500 + i) for i in range(n_spk)]
+    tests = [synth.sample_gmm(w, spk_mu[i % n_spk], var, 298, seed=600 + i) for i in range(3 * n_spk)]
+    sms = ssp.map_enrol(ubm, enrol, relevance=16.0)
+    assert sms.n_models == n_spk + 1 and sms.ubm_index == n_spk
+    pred_sv, who_sv = ssp.identify(tests, sms)
+    aw, amu, avar = ssp.map_adapt(ubm, enrol, relevance=16.0)
+    pred, who = ssp.identify(tests, ssp.ModelSet(aw, amu, avar), ubm, precision="fp32")
+    assert pred_sv.shape == pred.shape == (len(tests), n_spk)
+    # single-pass TF32 at this small K: 1e-4 relative on |score| ~ 55 per term of the difference
+    np.testing.assert_allclose(pred_sv, pred, rtol=0, atol=1.2e-2)
+    assert (who_sv == who).all() and (who == np.arange(len(tests)) % n_spk).all()
+    # against the general TENSOR kernel the model-side rounding is identical: the two agree far more closely
+    pred_tc, who_tc = ssp.identify(tests, ssp.ModelSet(aw, amu, avar), ubm, precision="tf32")
+    np.testing.assert_allclose(pred_sv, pred_tc, rtol=0, atol=2e-4)
+    assert (who_sv == who_tc).all()
