@@ -98,6 +98,61 @@ __global__ void __launch_bounds__(512, 1) epi_kernel(const float* __restrict__ i
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// ---- half-precision exponentials: ex2.approx.ftz.f16x2 produces two results per MUFU operation
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t x) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(x));
+  return make_float2(lo, hi);
+}
+// kHalf of the 16 pairs through f16x2 (accumulated in f16x2 four pairs at a time), the rest through MUFU f32;
+// no add of a stabiliser (the accumulator already holds it), like the shared-variance kernel's main loop
+template <int kHalf>
+__global__ void __launch_bounds__(512, 1) epi_half_kernel(const float* __restrict__ in, float* __restrict__ out, int iters,
+                                                          long long* __restrict__ cycles) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 4095];
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acch = acc0;
+  float m = 1.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += m;  // stands in for the fresh accumulator values of the next tile
+#pragma unroll
+    for (int g4 = 0; g4 < kHalf; g4 += 4) {
+      uint32_t h = ex2_f16x2(cvt_f16x2(v[2 * g4], v[2 * g4 + 1]));
+#pragma unroll
+      for (int i = 1; i < 4; ++i) h = hadd2(h, ex2_f16x2(cvt_f16x2(v[2 * (g4 + i)], v[2 * (g4 + i) + 1])));
+      acch = __fadd2_rn(acch, unpack_f16x2(h));
+    }
+#pragma unroll
+    for (int i = kHalf; i < 16; i += 2) {
+      acc0 = __fadd2_rn(acc0, make_float2(ex2(v[2 * i]), ex2(v[2 * i + 1])));
+      acc1 = __fadd2_rn(acc1, make_float2(ex2(v[2 * i + 2]), ex2(v[2 * i + 3])));
+    }
+    m = -m;
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc0.x + acc0.y + acc1.x + acc1.y + acch.x + acch.y;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 // plain instruction streams: what one warp-instruction of each kind costs per SM sub-partition
 template <int kKind>
 __global__ void __launch_bounds__(512, 1) pipe_kernel(const float* __restrict__ in, float* __restrict__ out, int iters,
@@ -119,6 +174,10 @@ __global__ void __launch_bounds__(512, 1) pipe_kernel(const float* __restrict__ 
         if (kKind == 3) { a[i].x = ex2(a[i].x); a[i].y = ex2(a[i].y); }                            // 2 x MUFU
         if (kKind == 4) { a[i].x = fmaxf(a[i].x, k.x); a[i].y = fmaxf(a[i].y, k.y); }              // 2 x FMNMX
         if (kKind == 5) { a[i].x += k.x; a[i].y += k.y; }                                          // 2 x FADD
+        if (kKind == 6) { a[i].x = __uint_as_float(cvt_f16x2(a[i].x, a[i].y)); }                   // cvt.rn.f16x2.f32
+        if (kKind == 7) { a[i].x = __uint_as_float(ex2_f16x2(__float_as_uint(a[i].x))); }          // ex2.f16x2
+        if (kKind == 8) { a[i] = unpack_f16x2(__float_as_uint(a[i].x)); }                          // 2 x cvt.f32.f16
+        if (kKind == 9) { a[i].x = __uint_as_float(hadd2(__float_as_uint(a[i].x), __float_as_uint(k.x))); }  // add.f16x2
       }
     }
   }
@@ -188,6 +247,13 @@ int main() {
   EPI(8, 3, false, true, false);
   EPI(16, 3, false, true, true);
   EPI(16, 3, false, false, true);
+#define EPIH(H) \
+  run("epi-half f16x2 pairs=" #H " (no stabiliser add)", [&](int it, long long* c) { epi_half_kernel<H><<<148, 512>>>(in, out, it, c); }, iters, 32.0)
+  EPIH(0);
+  EPIH(4);
+  EPIH(8);
+  EPIH(12);
+  EPIH(16);
 #define PIPE(K, NAME) \
   run(NAME, [&](int it, long long* c) { pipe_kernel<K><<<148, 512>>>(in, out, it, c); }, iters, 64.0)
   PIPE(0, "pipe: 32 x FFMA2 per iter");
@@ -196,5 +262,9 @@ int main() {
   PIPE(3, "pipe: 64 x MUFU.EX2 per iter");
   PIPE(4, "pipe: 64 x FMNMX per iter");
   PIPE(5, "pipe: 64 x FADD per iter");
+  PIPE(6, "pipe: 32 x cvt.rn.f16x2.f32 per iter");
+  PIPE(7, "pipe: 32 x ex2.approx.ftz.f16x2 per iter");
+  PIPE(8, "pipe: 32 x (2 x cvt.f32.f16) per iter");
+  PIPE(9, "pipe: 32 x add.rn.f16x2 per iter");
   return 0;
 }
