@@ -93,6 +93,30 @@ def fit_ubm_sharded(comm: Comm, local_frames, n_components: int, **kw):
     return gm.fit(local_frames)
 
 
+def map_enrol_sharded(comm: Comm, ubm, speaker_frames, relevance: float = 16.0):
+    """Mean-only MAP enrolment with SPEAKERS sharded across ranks (each speaker's frames stay on one rank); the adapted
+    means (S x K x D float64, 160 MB at S = 1000, K = 1024, D = 39) are all-gathered so that every rank ends up with
+    the same replicated :class:`SharedModelSet` (UBM means appended as model S).  No collective on the frame data."""
+    import torch
+
+    from .mixture import SharedModelSet
+    from .ubm import map_adapt
+
+    n_spk = len(speaker_frames)
+    lo, hi = shard_range(n_spk, comm.rank, comm.world_size)
+    uw, umu, uvar = ubm._model_set()._params
+    k, d = umu.shape[1], umu.shape[2]
+    if hi > lo:
+        _, mu, _ = map_adapt(ubm, speaker_frames[lo:hi], relevance=relevance, adapt=("means",))
+    else:
+        mu = torch.empty((0, k, d), dtype=torch.float64, device=umu.device)
+    counts = [shard_range(n_spk, r, comm.world_size) for r in range(comm.world_size)]
+    means = comm.gather_rows(mu, [b - a for a, b in counts])
+    sms = SharedModelSet(uw[0], uvar[0], torch.cat([means, umu]), ref_model=-1, device=umu.device)
+    sms.ubm_index = n_spk
+    return sms
+
+
 def identify_sharded(comm: Comm, utts, speakers, ubm=None, precision="tf32"):
     """Each rank scores its contiguous block of utterances against ALL (replicated) speaker models;
     every rank returns the full (N, S) LLR matrix and decisions."""

@@ -17,7 +17,7 @@ import numpy as np, torch
 sys.path.insert(0, {root!r})
 import speech_signal_processing_b200 as ssp
 from speech_signal_processing_b200 import synth
-from speech_signal_processing_b200.dist import Comm, shard_range, fit_ubm_sharded, identify_sharded
+from speech_signal_processing_b200.dist import Comm, shard_range, fit_ubm_sharded, identify_sharded, map_enrol_sharded
 comm = Comm("nccl")
 k, d = 32, 13
 w, mu, var = synth.synth_ubm(k, d, seed=3)
@@ -49,6 +49,16 @@ full, who = identify_sharded(comm, utts, models, ubm)
 ref, who_ref = ssp.identify(utts, models, ubm)
 np.testing.assert_allclose(full, ref, atol=2e-5)  # fp32 partial-sum order differs with the frame alignment
 assert (who == who_ref).all() and (who == np.arange(11) % 5).all()
+# speaker-sharded MAP enrolment (adapted means all-gathered) + utterance-sharded identify with the shared-variance kernel
+enrol = [synth.sample_gmm(w, spk[i], var, 400 + 13 * i, seed=40 + i) for i in range(5)]
+sms = map_enrol_sharded(comm, ubm, enrol, relevance=16.0)
+sms_ref = ssp.map_enrol(ubm, enrol, relevance=16.0)
+assert sms.n_models == 6 and sms.ubm_index == 5
+np.testing.assert_allclose(sms._params[2].cpu().numpy(), sms_ref._params[2].cpu().numpy(), rtol=0, atol=5e-6)  # TMEM fp32 accumulation order differs with the chunking
+full2, who2 = identify_sharded(comm, utts, sms)
+ref2, who_ref2 = ssp.identify(utts, sms_ref)
+np.testing.assert_allclose(full2, ref2, atol=2e-5)
+assert (who2 == who_ref2).all() and (who2 == np.arange(11) % 5).all()
 comm.barrier()
 torch.distributed.destroy_process_group()
 print("rank", comm.rank, "ok")
