@@ -100,6 +100,39 @@ int ssp_cmvn(const float* feat, const int64_t* frame_offsets, int64_t n_utts, in
              float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Voice-activity pre-filter (reference VAD.py; SURVEY 8(f).4 -- the report runs it in front of GMM-UBM).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ssp_vad_cfg {
+  int32_t frame_len;       /* 256 (VAD.py:22; also the FFT length)                                   */
+  int32_t frame_shift;     /* 128 = frame_len - overlap (VAD.py:23); == frame_len for pre-framed input */
+  int32_t n_blocks;        /* sub-bands of the spectral entropy, 10 (VAD.py:79)                      */
+  int32_t normalize_peak;  /* 1: divide each utterance by max|x| first (VAD.py:133)                  */
+  int32_t pcm_dtype;       /* 0 int16, 1 float32                                                      */
+  float eps;               /* 1e-8 (VAD.py:79)                                                        */
+} ssp_vad_cfg;
+
+/* ceil(n_samples / frame_shift) frames, zero-padded tail (VAD.py:36). */
+int64_t ssp_vad_num_frames(const ssp_vad_cfg* cfg, int64_t n_samples);
+/*
+ * Per-frame features of VAD.py:52-108 for a batch of utterances in one launch:
+ * out_zcr[f]     number of strictly negative products of neighbouring samples (ZCR, :52-63; the caller applies
+ *                the `* (power > 0.1)` gate of feature(), :115)
+ * out_power[f]   sum of squares in double (energy, :66-76)
+ * out_entropy[f] spectral entropy of |FFT|[:128] over n_blocks sub-bands (:79-108)
+ * pcm / sample_offsets / frame_offsets as in ssp_frontend_batch (frame_offsets = prefix sum of ssp_vad_num_frames).
+ */
+int ssp_vad_features(const void* pcm, const int64_t* sample_offsets, int64_t n_utts, const ssp_vad_cfg* cfg,
+                     const int64_t* frame_offsets, float* out_zcr, double* out_power, float* out_entropy,
+                     void* stream);
+/*
+ * VAD_detection (VAD.py:137-182): the double-threshold state machine, one utterance per thread.
+ * zcr must already carry the power gate.  out_speech[f] = 1 for speech frames.  Where the reference's backward
+ * search would run past index -n (IndexError) the search stops there.
+ */
+int ssp_vad_detect(const float* zcr, const double* power, const int64_t* frame_offsets, int64_t n_utts,
+                   float zcr_gate, double ampl, double amph, int32_t min_len, uint8_t* out_speech, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * GMM: packed models, scoring, EM/MAP sufficient statistics.
  * Replaces sklearn.mixture.GaussianMixture(covariance_type='diag').score / .fit internals as
  * called at GMM_UBM.py:158-160,169-170,185,194 (sklearn/mixture/_gaussian_mixture.py:536-553,

@@ -19,6 +19,9 @@ What is restated, and how each piece is pinned
 * ``oracle.gmm`` restates sklearn.mixture.GaussianMixture (diag) E-step, M-step,
   score and the EM loop as called at /root/reference/GMM_UBM.py:158-170,185,194.
   PINNED against sklearn 1.9.0 (golden fixtures + live comparison in the tests).
+* ``oracle.vad`` restates /root/reference/VAD.py (framing, zero-crossing count, energy, spectral entropy, the
+  double-threshold detector and the entropy gate).  PINNED: the unmodified file is imported (shims for
+  ``bayes_opt`` / ``seaborn``) and run on synthetic signals -> ``tests/golden/vad.npz``.
 * ``oracle.frontend.sidekit_mfcc`` restates SIDEKIT 1.3.x ``frontend/features.py``
   ``mfcc`` (the function /root/reference/GMM_UBM.py:20,89 binds).  SIDEKIT is an
   un-vendored, un-pinned dependency (requirements.txt:5) that is absent from

@@ -29,6 +29,11 @@ class FrontendCfg(C.Structure):
     ]
 
 
+class VadCfg(C.Structure):
+    _fields_ = [("frame_len", C.c_int32), ("frame_shift", C.c_int32), ("n_blocks", C.c_int32), ("normalize_peak", C.c_int32),
+                ("pcm_dtype", C.c_int32), ("eps", C.c_float)]
+
+
 class GmmDims(C.Structure):
     _fields_ = [("n_models", C.c_int32), ("n_comp", C.c_int32), ("n_feat", C.c_int32)]
 
@@ -48,6 +53,9 @@ PROTOTYPES = {
     "ssp_frontend_batch": (C.c_int, [_P, _P, _I64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "ssp_delta": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "ssp_cmvn": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "ssp_vad_num_frames": (_I64, [C.POINTER(VadCfg), _I64]),
+    "ssp_vad_features": (C.c_int, [_P, _P, _I64, C.POINTER(VadCfg), _P, _P, _P, _P, _P]),
+    "ssp_vad_detect": (C.c_int, [_P, _P, _P, _I64, C.c_float, C.c_double, C.c_double, _I32, _P, _P]),
     "ssp_gmm_pack_bytes": (_I64, [C.POINTER(GmmDims)]),
     "ssp_gmm_pack_models": (C.c_int, [_P, _P, _P, C.POINTER(GmmDims), _P, _P]),
     "ssp_gmm_score": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(GmmDims), _I32, _P, _P, _P]),

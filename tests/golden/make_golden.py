@@ -14,6 +14,8 @@ processing_mfcc.npz   utils/processing.py::MFCC / enframe / mfccInitFilterBanks 
 delta.npz             GMM_UBM.py::delta outputs
 sklearn_gmm.npz       sklearn GaussianMixture(diag) score_samples / predict_proba / fit
                       trajectory from fixed initial parameters, preprocessing.scale
+vad.npz               VAD.py::enframe / ZCR / energy / spectrum_entropy / feature / VAD_detection / VAD_frequency
+                      on synthetic bursts-in-noise signals
 pipeline.npz          GMM_UBM.py::extract_feature + GMM() end to end on synthetic audio with
                       the sidekit restatement plugged in as ``mfcc`` and a seeded
                       GaussianMixture (random_state only; everything else stock)
@@ -167,12 +169,60 @@ def gen_pipeline():
     print("reference GMM() printed:", line)
 
 
+def vad_signal(seed: int, n: int, bursts):
+    """int16 test signal for the VAD: noise floor + voiced bursts (harmonics) + one unvoiced (noisy) burst."""
+    rs = np.random.RandomState(seed)
+    t = np.arange(n) / 8000.0
+    x = 40.0 * rs.standard_normal(n)
+    for lo, hi, f0, amp in bursts:
+        seg = slice(lo, hi)
+        if f0 > 0:
+            x[seg] += amp * (np.sin(2 * np.pi * f0 * t[seg]) + 0.5 * np.sin(2 * np.pi * 2 * f0 * t[seg] + 0.3))
+        else:
+            x[seg] += amp * rs.standard_normal(hi - lo)
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+VAD_CASES = [
+    (1, 24000, [(3000, 9000, 140.0, 9000.0), (9000, 10500, 0.0, 1500.0), (15000, 21000, 210.0, 6000.0)]),
+    (2, 16000, [(200, 7000, 110.0, 12000.0), (7600, 8200, 180.0, 8000.0), (12000, 15990, 160.0, 10000.0)]),  # run reaches the end
+    (3, 9000, [(0, 4000, 250.0, 7000.0)]),                                                                     # speech from frame 0
+    (4, 5000, [(2000, 2050, 500.0, 20000.0)]),                                                                 # noise + a click: no speech
+    (5, 20011, [(2500, 5200, 95.0, 11000.0), (5300, 9000, 0.0, 4000.0), (11000, 11900, 300.0, 9000.0), (13000, 19000, 130.0, 3000.0)]),
+]
+
+
+def gen_vad():
+    """VAD.py on synthetic signals: framing, per-frame features, both detectors."""
+    ref_shims._stub("bayes_opt", BayesianOptimization=object)
+    ref_shims._stub("seaborn")
+    vad = ref_shims.load("VAD")
+    out = {"n_cases": np.array(len(VAD_CASES))}
+    for i, (seed, n, bursts) in enumerate(VAD_CASES):
+        sig = vad_signal(seed, n, bursts)
+        wave = sig / (max(abs(sig.astype(np.int64))))          # VAD.py:133 (abs in int64: no int16 wrap at -32768)
+        frames = vad.enframe(wave)
+        with contextlib.redirect_stdout(io.StringIO()):
+            z, p, e = vad.feature(frames)
+        out[f"sig{i}"] = sig
+        if frames.shape[1] <= 80:
+            out[f"frames{i}"] = frames   # the larger ones are re-derived in the tests (enframe is pinned by the small ones)
+        out[f"zcr_raw{i}"] = vad.ZCR(frames)
+        out[f"zcr{i}"], out[f"power{i}"], out[f"entropy{i}"] = z, p, e
+        out[f"det{i}"] = vad.VAD_detection(z, p)
+        out[f"det_b{i}"] = vad.VAD_detection(z, p, zcr_gate=25, ampl=1.0, amph=8)
+        out[f"freq{i}"] = vad.VAD_frequency(e)
+    np.savez_compressed(os.path.join(HERE, "vad.npz"), **out)
+    print("vad.npz: speech frames per case", [int(out[f"det{i}"].sum()) for i in range(len(VAD_CASES))])
+
+
 if __name__ == "__main__":
     if not ref_shims.available():
         sys.exit("reference tree not found; fixtures can only be generated in the build container")
     gen_processing()
     gen_sklearn()
     gen_pipeline()
+    gen_vad()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -142,3 +142,22 @@ def test_map_adapt_limits():
     np.testing.assert_allclose(m_0, f / n[:, None], atol=1e-6)  # r -> 0 is the ML mean
     w2, m2, v2 = ogmm.map_adapt(n, f, s, w, mu, var, 500, adapt=("means", "weights", "variances"))
     assert np.isclose(w2.sum(), 1.0) and (v2 > 0).all()
+
+
+def test_vad_matches_reference(golden):
+    """oracle.vad against the unmodified VAD.py (framing, ZCR, energy, spectral entropy, both detectors)."""
+    from oracle import vad as ov
+
+    g = golden("vad.npz")
+    for i in range(int(g["n_cases"])):
+        frames = ov.enframe(ov.wav_normalise(g[f"sig{i}"]))
+        if f"frames{i}" in g:
+            assert np.array_equal(frames, g[f"frames{i}"])
+        z, p, e = ov.feature(frames)
+        assert np.array_equal(ov.zcr(frames), g[f"zcr_raw{i}"])
+        assert np.array_equal(z, g[f"zcr{i}"])
+        np.testing.assert_allclose(p, g[f"power{i}"], rtol=1e-12)
+        np.testing.assert_allclose(e, g[f"entropy{i}"], rtol=1e-9, atol=1e-12)
+        assert np.array_equal(ov.detect(z, p), g[f"det{i}"])
+        assert np.array_equal(ov.detect(z, p, zcr_gate=25, ampl=1.0, amph=8), g[f"det_b{i}"])
+        assert np.array_equal(ov.frequency(e), g[f"freq{i}"])
