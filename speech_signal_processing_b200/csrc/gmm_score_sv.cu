@@ -87,6 +87,24 @@ __device__ __forceinline__ void bar_spin(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > (1ll << 31)) __trap();
   }
 }
+// the control warps' version: a failed poll parks the warp in hardware for up to ~1 us instead of re-issuing the wait
+// loop, which would steal issue slots from the four epilogue warps that share the sub-partition
+__device__ __forceinline__ void bar_spin_relaxed(uint32_t bar, uint32_t parity) {
+  if (bar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000u)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > (1ll << 31)) __trap();
+  }
+}
 __device__ __forceinline__ void bar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     const uint32_t sB_u32 = smem_u32(sB);
     uint32_t stage = 0, ph = 0;
     auto load = [&](const float* src) {
-      bar_spin(b_empty + 8u * stage, ph ^ 1u);
+      bar_spin_relaxed(b_empty + 8u * stage, ph ^ 1u);
       if (elect_one()) {
         bar_arrive_expect_tx(b_full + 8u * stage, tile_bytes);
         bulk_g2s_u32(sB_u32 + stage * tile_bytes, src, tile_bytes, b_full + 8u * stage);
@@ -271,9 +289,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     auto next_slot = [&]() { if (++s3 == 3) { s3 = 0; sph ^= 1u; } };
     // one accumulator job of this row block: r part only (frame operand in TMEM)
     auto job_r = [&](uint32_t preinit) {
-      bar_spin(b_full + 8u * stage, bph);
+      bar_spin_relaxed(b_full + 8u * stage, bph);
       const uint32_t slot = (uint32_t)g + 2u * s3;
-      bar_spin(t_empty + 8u * slot, sph ^ 1u);
+      bar_spin_relaxed(t_empty + 8u * slot, sph ^ 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
@@ -289,12 +307,12 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     };
     // q part (both operands in shared memory), optionally followed by the reference model's r part
     auto job_q = [&](bool with_r) {
-      bar_spin(b_full + 8u * stage, bph);
+      bar_spin_relaxed(b_full + 8u * stage, bph);
       const uint32_t stage_q = stage;
       next_stage();
-      if (with_r) bar_spin(b_full + 8u * stage, bph);
+      if (with_r) bar_spin_relaxed(b_full + 8u * stage, bph);
       const uint32_t slot = (uint32_t)g + 2u * s3;
-      bar_spin(t_empty + 8u * slot, sph ^ 1u);
+      bar_spin_relaxed(t_empty + 8u * slot, sph ^ 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
@@ -315,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       next_slot();
     };
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
-      bar_spin(a_full, unit_idx & 1u);
+      bar_spin_relaxed(a_full, unit_idx & 1u);
       tc_fence_after();
       for (int j = 0; j < NT; ++j) job_q(true);   // pre-pass: full logits of the reference model
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
