@@ -376,6 +376,16 @@ def run_b200(a):
                       "note": "achieved = algorithmic 4*D*K FLOP per (frame, model); the shared-variance kernel executes "
                               "2*(D+2 padded to 48)*K on the tensor pipe and is bound by the 3.05e12 exponentials of the "
                               "log-sum-exp (MUFU ex2 + an FMA-pipe polynomial share), see profiles/"}
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, from a committed ncu --set full capture
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(kernel)
+        if t and (t["utts"], t["speakers"], t["components"]) == (N, S, K):
+            traffic = {"bytes": t["dram_bytes"], "unit": "B per launch", "algorithmic_bytes": t.get("algorithmic_bytes"),
+                       "source": t["source"]}
+    except Exception:
+        traffic = None
     line = {
         "metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -387,7 +397,7 @@ def run_b200(a):
                 "d2h_bytes_per_step": int(host_dec.numel() * 8), "ms_per_step": e2e_ms / a.steps},
         "gpu_launches": launches,
         "roofline": {"bound": bound, "kernel": kernel, **roof_extra,
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (dev_ms / a.steps), "peak_source": peak_note,
                      "frac_of_bf16_peak": achieved / peaks["bf16_tflops_sustained"]},
         "clocks": clocks,

@@ -8,8 +8,10 @@
 //     last radix-4 across lane quadruples with warp shuffles -- 2 shared-memory round trips instead of 4
 //     Stockham passes;
 //   * the real-FFT split handles bins k and 256-k together;
-//   * the triangular filterbank is cut into segments of bounded width so that the 32 lanes share the
-//     ~2 x 257 weights evenly (a lane per filter is bound by the widest triangle), deterministic order;
+//   * the triangular filterbank is cut into 8-bin segments that start on a multiple of 4 bins (weights zero-padded),
+//     spread over the 32 lanes: a segment is two 16-byte loads of weights, two of the spectrum and 8 FMAs, and a
+//     lane per filter is no longer bound by the widest triangle; per-filter sums in a fixed order (deterministic);
+//   * int16 PCM is staged with 16-byte loads (8 samples) when the utterance starts on a 16-byte boundary;
 //   * delta and delta-delta are materialised once in shared memory when the utterance is short enough,
 //     and the CMVN statistics / output passes read them instead of re-deriving 16 taps per element.
 #include <cstdlib>
@@ -23,8 +25,8 @@ constexpr int W = 8;          // warps per CTA == frames per batch
 constexpr int NH = 256;       // complex FFT length
 constexpr int EXS = 36;       // float2 row stride of the transpose buffer (conflict-free for 64-bit accesses)
 constexpr int EXN = 8 * EXS;  // 288 float2 >= 268 needed for the padded spectrum
-constexpr int MAXSEG = 96;
-constexpr int MAXW = 2048;    // filterbank weights cached in shared memory
+constexpr int MAXSEG = 128;   // 8-bin filterbank segments (two-sided 40-filter bank: ~92)
+constexpr int PWN = 272;      // spectrum row: 257 bins + zero padding read by the last aligned segment
 constexpr int MAXF = 64;      // filters
 constexpr int MAXC = 32;      // cepstra
 
@@ -60,11 +62,11 @@ __host__ __device__ inline size_t carve_floats(const ssp_frontend_cfg& c, int ma
                                                 int* stg_out) {
   const int FLp = (c.frame_len + 3) & ~3;
   const int stg = ((W - 1) * c.frame_shift + c.frame_len + 1 + 3) & ~3;
-  const int per_warp = 2 * EXN + 260 + MAXSEG + MAXF;
+  const int per_warp = 2 * EXN + PWN + MAXSEG + MAXF;
   if (per_warp_out) *per_warp_out = per_warp;
   if (stg_out) *stg_out = stg;
-  size_t f = 2 * (NH + 2) + FLp + ((c.n_ceps * (c.n_filt | 1) + 3) & ~3) + MAXW + 3 * MAXSEG + (MAXF + 4) + 4 + 256 + 64 + 64 + stg +
-             (size_t)W * per_warp;
+  size_t f = 2 * (NH + 2) + FLp + ((c.n_ceps * (c.n_filt | 1) + 3) & ~3) + 8 * MAXSEG + 2 * MAXSEG + (MAXF + 4) + 4 + 256 + 64 + 64 +
+             stg + (size_t)W * per_warp;
   f += (size_t)max_frames * c.n_ceps * (mat ? (1 + c.delta_order) : 1);
   return f;
 }
@@ -84,10 +86,9 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   float* win = p; p += (FL + 3) & ~3;
   const int DS = NF | 1;  // odd row stride: lanes reading different rows hit different banks
   float* dct = p; p += (NC * DS + 3) & ~3;
-  float* fbw = p; p += MAXW;
+  float* segw = p; p += 8 * MAXSEG;  // [2 halves][MAXSEG][4]: lane == segment reads 16 bytes at stride 16 (no conflicts)
   int* seg_start = reinterpret_cast<int*>(p); p += MAXSEG;
-  int* seg_len = reinterpret_cast<int*>(p); p += MAXSEG;
-  int* seg_woff = reinterpret_cast<int*>(p); p += MAXSEG;
+  int* seg_filt = reinterpret_cast<int*>(p); p += MAXSEG;
   int* filt_seg0 = reinterpret_cast<int*>(p); p += MAXF + 4;
   int* meta = reinterpret_cast<int*>(p); p += 4;
   float* red = p; p += 256;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   float* ceps = p;
   float2* ex = reinterpret_cast<float2*>(wb);
   float* pw = wb + 2 * EXN;
-  float* segsum = pw + 260;
+  float* segsum = pw + PWN;
   float* mel = segsum + MAXSEG;
 
   const int u = blockIdx.x;
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   }
   for (int i = tid; i < FL; i += 256) win[i] = a.window[i];
   for (int i = tid; i < NC * NF; i += 256) dct[(i / NF) * DS + (i % NF)] = a.dct[i];
-  // filterbank CSR (3 x NF ints) is pulled in cooperatively; thread 0 then cuts the segments out of shared memory
+  // filterbank CSR (3 x NF ints) is pulled in cooperatively; every triangle is cut into 8-bin segments that start
+  // on a multiple of 4 bins
   int* csr = reinterpret_cast<int*>(stage);  // stage is free until the first batch
   for (int i = tid; i < NF; i += 256) {
     csr[i] = a.fb_len[i];
@@ -125,37 +127,32 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   }
   __syncthreads();
   if (tid == 0) {
-    // cut every triangle into segments of at most `width` bins: ~24 segments' worth of work per 32 lanes
-    int total = 0;
-    for (int m = 0; m < NF; ++m) total += csr[m];
-    int width = (total + 23) / 24;
-    if (width < 8) width = 8;
-    int ns = 0;
-    for (;;) {
-      ns = 0;
-      for (int m = 0; m < NF; ++m) ns += max(1, (csr[m] + width - 1) / width);
-      if (ns <= MAXSEG) break;
-      width *= 2;
-    }
     int s = 0;
     for (int m = 0; m < NF; ++m) {
       filt_seg0[m] = s;
-      const int len = csr[m], st = csr[MAXF + m], off = csr[2 * MAXF + m];
-      int done = 0;
-      do {
-        const int l = min(width, len - done);
-        seg_start[s] = st + done;
-        seg_len[s] = l;
-        seg_woff[s] = off + done;
-        done += l;
-        ++s;
-      } while (done < len);
+      const int len = csr[m], st = csr[MAXF + m];
+      if (len > 0) s += (st + len - (st & ~3) + 7) >> 3;
     }
     filt_seg0[NF] = s;
     meta[0] = s;
-    meta[1] = total <= MAXW ? 1 : 0;
-    meta[2] = total;
   }
+  __syncthreads();
+  const int n_seg = meta[0];  // <= MAXSEG is checked on the host side of the launch (frontend_fast_supported + fallback)
+  for (int m = tid; m < NF; m += 256) {
+    const int st = csr[MAXF + m];
+    for (int sg = filt_seg0[m], b = st & ~3; sg < filt_seg0[m + 1] && sg < MAXSEG; ++sg, b += 8) {
+      seg_start[sg] = b;
+      seg_filt[sg] = m;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 8 * min(n_seg, MAXSEG); idx += 256) {
+    const int sg = idx >> 3, j = idx & 7, m = seg_filt[sg];
+    const int rel = seg_start[sg] + j - csr[MAXF + m];
+    const float w = (rel >= 0 && rel < csr[m]) ? a.fb_weights[csr[2 * MAXF + m] + rel] : 0.f;
+    segw[((j >> 2) * MAXSEG + sg) * 4 + (j & 3)] = w;
+  }
+  for (int i = lane; i < PWN; i += 32) pw[i] = 0.f;  // the padding bins stay zero; 0..256 are rewritten every frame
   // per-lane twiddles, constant across frames
   float2 tw1[8], tw2[8];
 #pragma unroll
@@ -167,11 +164,6 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     tw2[k] = make_float2(c, s);
   }
   __syncthreads();
-  const int n_seg = meta[0];
-  const bool w_cached = meta[1] != 0;
-  if (w_cached)
-    for (int i = tid; i < meta[2]; i += 256) fbw[i] = a.fb_weights[i];
-  const float* fw = w_cached ? fbw : a.fb_weights;
 
   const float pre = cfg.preemph;
   const int pmode = cfg.preemph_mode;
@@ -182,8 +174,33 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   // after it, so their global-memory latency hides behind a whole frame of FFT work.
   constexpr int PF = 8;  // samples per thread per batch: (W-1)*shift + frame_len + 1 <= 256 * PF
   float pf[PF];
+  // int16 PCM whose utterance starts on a 16-byte boundary: thread t stages samples [8t, 8t + 8) of the batch with one
+  // 16-byte load (W * shift is a multiple of 8, so every batch stays aligned); the sample before the batch (needed by
+  // the pre-emphasis) goes through thread 255.  Otherwise: one sample per load, 8 loads per thread.
+  const bool vec = sizeof(PcmT) == 2 && ((s_begin & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.pcm) & 15) == 0);
   auto prefetch = [&](int b) {
-    const int64_t g0 = (int64_t)b * W * SH - 1;
+    const int64_t base = (int64_t)b * W * SH;
+    if (vec) {
+      const int64_t j = base + 8 * tid;
+      if (8 * tid < stg - 1 && j + 7 < n_samp) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(a.pcm) + s_begin + j);
+        pf[0] = __uint_as_float(raw.x); pf[1] = __uint_as_float(raw.y); pf[2] = __uint_as_float(raw.z); pf[3] = __uint_as_float(raw.w);
+      } else {
+        // tail of the utterance: per-sample loads, packed the same way so that the unpack below is shared
+        uint32_t wds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t g = j + 2 * e;
+          const int lo = (8 * tid < stg - 1 && g < n_samp) ? (int)reinterpret_cast<const int16_t*>(a.pcm)[s_begin + g] : 0;
+          const int hi = (8 * tid < stg - 1 && g + 1 < n_samp) ? (int)reinterpret_cast<const int16_t*>(a.pcm)[s_begin + g + 1] : 0;
+          wds[e] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+        }
+        pf[0] = __uint_as_float(wds[0]); pf[1] = __uint_as_float(wds[1]); pf[2] = __uint_as_float(wds[2]); pf[3] = __uint_as_float(wds[3]);
+      }
+      pf[4] = (tid == 255 && base > 0 && base - 1 < n_samp) ? load_pcm<PcmT>(a.pcm, s_begin + base - 1) : 0.f;
+      return;
+    }
+    const int64_t g0 = base - 1;
 #pragma unroll
     for (int r = 0; r < PF; ++r) {
       const int i = tid + 256 * r;
@@ -194,10 +211,23 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   prefetch(0);
   for (int b = 0; b < n_batches; ++b) {
     __syncthreads();
+    if (vec) {
+      if (8 * tid < stg - 1) {
 #pragma unroll
-    for (int r = 0; r < PF; ++r) {
-      const int i = tid + 256 * r;
-      if (i < stg) stage[i] = pf[r];
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t wd = __float_as_uint(pf[e]);
+          const int i = 1 + 8 * tid + 2 * e;
+          if (i < stg) stage[i] = (float)(int16_t)(wd & 0xffffu);
+          if (i + 1 < stg) stage[i + 1] = (float)(int16_t)(wd >> 16);
+        }
+      }
+      if (tid == 255) stage[0] = pf[4];
+    } else {
+#pragma unroll
+      for (int r = 0; r < PF; ++r) {
+        const int i = tid + 256 * r;
+        if (i < stg) stage[i] = pf[r];
+      }
     }
     __syncthreads();
     if (b + 1 < n_batches) prefetch(b + 1);
@@ -298,18 +328,30 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     __syncwarp();
 
     // ---- filterbank: bounded-width segments spread over the lanes, then a fixed-order sum per filter
-    for (int sg = lane; sg < n_seg; sg += 32) {
-      const float* w = fw + seg_woff[sg];
-      const float* q = pw + seg_start[sg];
-      const int len = seg_len[sg];
-      float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(w[i], q[i], acc);
+    for (int sg = lane; sg < n_seg && n_seg <= MAXSEG; sg += 32) {
+      const float4* q4 = reinterpret_cast<const float4*>(pw + seg_start[sg]);
+      const float4 w0 = reinterpret_cast<const float4*>(segw)[sg], w1 = reinterpret_cast<const float4*>(segw)[MAXSEG + sg];
+      const float4 q0 = q4[0], q1 = q4[1];
+      float acc = w0.x * q0.x;
+      acc = fmaf(w0.y, q0.y, acc);
+      acc = fmaf(w0.z, q0.z, acc);
+      acc = fmaf(w0.w, q0.w, acc);
+      acc = fmaf(w1.x, q1.x, acc);
+      acc = fmaf(w1.y, q1.y, acc);
+      acc = fmaf(w1.z, q1.z, acc);
+      acc = fmaf(w1.w, q1.w, acc);
       segsum[sg] = acc;
     }
     __syncwarp();
     for (int m = lane; m < NF; m += 32) {
       float acc = 0.f;
-      for (int sg = filt_seg0[m]; sg < filt_seg0[m + 1]; ++sg) acc += segsum[sg];
+      if (n_seg <= MAXSEG) {
+        for (int sg = filt_seg0[m]; sg < filt_seg0[m + 1]; ++sg) acc += segsum[sg];
+      } else {  // a filterbank too wide for the segment table: plain per-filter dot product from global memory
+        const float* w = a.fb_weights + a.fb_offset[m];
+        const float* q = pw + a.fb_start[m];
+        for (int i = 0; i < a.fb_len[m]; ++i) acc = fmaf(w[i], q[i], acc);
+      }
       if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
       acc += cfg.log_add;
       mel[m] = cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc);
