@@ -86,8 +86,21 @@ def identify(utts, speakers, ubm=None, precision="tf32", device=None):
     if isinstance(speakers, (ModelSet, SharedModelSet)):
         ms = speakers
     else:
-        ms = ModelSet(np.stack([np.asarray(m.weights_) for m in speakers]), np.stack([np.asarray(m.means_) for m in speakers]),
-                      np.stack([np.asarray(m.covariances_) for m in speakers]), device=dev)
+        sw = np.stack([np.asarray(m.weights_) for m in speakers])
+        smu = np.stack([np.asarray(m.means_) for m in speakers])
+        svar = np.stack([np.asarray(m.covariances_) for m in speakers])
+        uw, uvar = (np.asarray(ubm.weights_), np.asarray(ubm.covariances_)) if ubm is not None and not isinstance(ubm, ModelSet) else (None, None)
+        if (precision == "tf32" and smu.shape[2] <= 62 and SharedModelSet.shares_base(sw, svar)
+                and (uw is None or (np.array_equal(uw, sw[0]) and np.array_equal(uvar, svar[0])))):
+            # mean-only MAP speakers (e.g. unpickled models adapted from this UBM): shared-variance kernel, UBM included
+            means = smu if uw is None else np.concatenate([smu, np.asarray(ubm.means_)[None]])
+            sms = SharedModelSet(sw[0], svar[0], means, ref_model=-1, device=dev)
+            scores, _ = sms.score(feats, offs)
+            if uw is not None:
+                scores = scores[:, :-1] - scores[:, -1:]
+            pred = scores.cpu().numpy()
+            return pred, pred.argmax(axis=1)
+        ms = ModelSet(sw, smu, svar, device=dev)
     scores, _ = ms.score(feats, offs, precision=precision)
     if ubm is not None:
         ums = ubm if isinstance(ubm, ModelSet) else ModelSet(ubm.weights_, ubm.means_, ubm.covariances_, device=dev)

@@ -391,3 +391,26 @@ def test_map_enrol_identify_equals_general_path():
     pred_tc, who_tc = ssp.identify(tests, ssp.ModelSet(aw, amu, avar), ubm, precision="tf32")
     np.testing.assert_allclose(pred_sv, pred_tc, rtol=0, atol=2e-4)
     assert (who_sv == who_tc).all()
+
+
+def test_identify_routes_shared_base_model_lists_to_the_shared_variance_kernel():
+    """A list of models that all carry the UBM's weights and covariances (mean-only MAP, e.g. unpickled) goes through
+    ssp_gmm_score_shared; the result equals the general path's."""
+    from speech_signal_processing_b200 import _lib
+
+    k, d, n_spk = 64, 26, 6
+    w, mu, var = synth.synth_ubm(k, d, seed=51)
+    spk_mu = synth.synth_speaker_means(mu, n_spk, seed=52, shift=0.4)
+    ubm = ssp.GaussianMixture.from_params(w, mu, var)
+    models = [ssp.GaussianMixture.from_params(w, spk_mu[i], var) for i in range(n_spk)]
+    tests = [synth.sample_gmm(w, spk_mu[i % n_spk], var, 200 + 11 * i, seed=700 + i) for i in range(2 * n_spk)]
+    before = _lib.launch_count()
+    pred, who = ssp.identify(tests, models, ubm)
+    assert _lib.launch_count() - before == 3          # pack + shared-variance kernel + its fix-up pass
+    ref, who_ref = ssp.identify(tests, models, ubm, precision="fp32")
+    np.testing.assert_allclose(pred, ref, rtol=0, atol=1.2e-2)
+    assert (who == who_ref).all() and (who == np.arange(len(tests)) % n_spk).all()
+    # a model with its own variances switches the whole call to the general kernel
+    odd = ssp.GaussianMixture.from_params(w, spk_mu[0], var * 1.1)
+    pred2, _ = ssp.identify(tests, models[:-1] + [odd], ubm)
+    np.testing.assert_allclose(pred2[:, :-1], ref[:, :-1], rtol=0, atol=1.2e-2)
