@@ -262,6 +262,10 @@ class FrontEnd:
         log_e = torch.empty(total, dtype=torch.float32, device=self.device) if want_log_energy else None
         if n_utts == 0 or total == 0:
             return out, frame_offsets, log_e
+        max_fused = int(self.lib.ssp_frontend_max_frames(C.byref(cfg)))
+        if int(nfr.max()) > max_fused:
+            self._extract_mixed(pcm, pcm_dtype, sample_offsets, frame_offsets, nfr, max_fused, out, log_e)
+            return out, frame_offsets, log_e
         d_soff = torch.as_tensor(sample_offsets, device=self.device)
         d_foff = torch.as_tensor(frame_offsets, device=self.device)
         rc = self.lib.ssp_frontend_batch(
@@ -271,6 +275,86 @@ class FrontEnd:
         _lib.check(rc, "ssp_frontend_batch")
         self._keep = (d_soff, d_foff)  # keep the offset tensors alive until the stream has consumed them
         return out, frame_offsets, log_e
+
+
+    # -- utterances too long for the single-pass kernel (its per-utterance cepstra live in shared memory) ------------
+    def _launch(self, pcm, cfg, soff, foff, max_t, out, log_e):
+        torch = _lib.require_cuda()
+        d_soff = torch.as_tensor(np.ascontiguousarray(soff, dtype=np.int64), device=self.device)
+        d_foff = torch.as_tensor(np.ascontiguousarray(foff, dtype=np.int64), device=self.device)
+        rc = self.lib.ssp_frontend_batch(
+            _lib.ptr(pcm), _lib.ptr(d_soff), len(soff) - 1, C.byref(cfg), _lib.ptr(self.t_window), _lib.ptr(self.t_fb_start),
+            _lib.ptr(self.t_fb_len), _lib.ptr(self.t_fb_off), _lib.ptr(self.t_fb_w), _lib.ptr(self.t_dct),
+            _lib.ptr(d_foff), int(max_t), _lib.ptr(out), _lib.ptr(log_e), _lib.stream_ptr())
+        _lib.check(rc, "ssp_frontend_batch")
+        self._keep_long = getattr(self, "_keep_long", []) + [d_soff, d_foff]
+
+    def _extract_mixed(self, pcm, pcm_dtype, soff, foff, nfr, max_fused, out, log_e):
+        """Batch with utterances longer than the fused kernel's shared-memory bound (~35 s at 39-d).  Runs of short
+        utterances go through the fused kernel unchanged.  A long utterance is cut into chunks of whole frames that
+        the kernel turns into raw cepstra (each chunk a "virtual utterance"; frames are self-contained), then
+        ``ssp_delta`` (once or twice) and ``ssp_cmvn`` run over the whole utterance -- three to five launches per
+        long utterance instead of one."""
+        torch = _lib.require_cuda()
+        r = self.recipe
+        self._keep_long = []
+        long_ix = np.nonzero(nfr > max_fused)[0]
+        cfg_full = self._cfg(pcm_dtype)
+        # ---- runs of short utterances between the long ones
+        edges = [-1] + [int(i) for i in long_ix] + [len(nfr)]
+        for a, b in zip(edges[:-1], edges[1:]):
+            lo, hi = a + 1, b
+            if hi > lo and int(nfr[lo:hi].sum()) > 0:
+                self._launch(pcm, cfg_full, soff[lo : hi + 1], foff[lo : hi + 1], int(nfr[lo:hi].max()), out, log_e)
+        # ---- long utterances
+        raw = FrontEnd.__new__(FrontEnd)
+        raw.__dict__.update(self.__dict__)
+        raw.delta_order, raw.cmvn = 0, False
+        nc = self.n_ceps
+        for u in long_ix:
+            t = int(nfr[u])
+            src, mode_cfg = pcm, raw._cfg(pcm_dtype)
+            s0 = int(soff[u])
+            if r.preemph_mode == 2:
+                # whole-signal pre-emphasis crosses chunk borders: apply it up front (y[0] = x[0]) and switch it off
+                x = pcm[s0 : int(soff[u + 1])].to(torch.float32)
+                y = x.clone()
+                y[1:] -= r.preemph * x[:-1]
+                src, s0 = y, 0
+                mode_cfg = raw._cfg(1)
+                mode_cfg.preemph_mode = 0
+            n_samp = int(soff[u + 1] - soff[u])
+            chunk = int(self.lib.ssp_frontend_max_frames(C.byref(mode_cfg)))
+            chunk = max(1, min(chunk, 2048))
+            f_lo = np.arange(0, t, chunk, dtype=np.int64)
+            f_hi = np.minimum(f_lo + chunk, t)
+            c_soff = np.concatenate([s0 + f_lo * r.frame_shift, [0]])
+            # every chunk but the last ends with its last frame; sample_offsets must be non-decreasing pairs, so each
+            # chunk gets its own (start, end) pair through a two-entry offsets array per launch group
+            ceps = torch.empty((t, nc), dtype=torch.float32, device=self.device)
+            le = torch.empty(t, dtype=torch.float32, device=self.device) if log_e is not None else None
+            for k in range(len(f_lo)):
+                start = int(c_soff[k])
+                last = k == len(f_lo) - 1
+                stop = s0 + n_samp if last else start + int(f_hi[k] - f_lo[k] - 1) * r.frame_shift + r.frame_len
+                self._launch(src, mode_cfg, np.array([start, min(stop, s0 + n_samp)]), np.array([0, int(f_hi[k] - f_lo[k])]),
+                             int(f_hi[k] - f_lo[k]), ceps[int(f_lo[k]) :], le[int(f_lo[k]) :] if le is not None else None)
+            cols = [ceps]
+            for _ in range(self.delta_order):
+                d = torch.empty_like(ceps)
+                _lib.check(self.lib.ssp_delta(_lib.ptr(cols[-1]), t, nc, self.delta_n, _lib.ptr(d), _lib.stream_ptr()), "ssp_delta")
+                cols.append(d)
+            feats = torch.cat(cols, dim=1) if len(cols) > 1 else ceps
+            dst = out[int(foff[u]) : int(foff[u + 1])]
+            if self.cmvn:
+                offs = torch.tensor([0, t], dtype=torch.int64, device=self.device)
+                _lib.check(self.lib.ssp_cmvn(_lib.ptr(feats), _lib.ptr(offs), 1, feats.shape[1], _lib.ptr(dst), _lib.stream_ptr()), "ssp_cmvn")
+                self._keep_long.append(offs)
+            else:
+                dst.copy_(feats)
+            if log_e is not None:
+                log_e[int(foff[u]) : int(foff[u + 1])].copy_(le)
+            self._keep_long += [ceps, feats, src]
 
 
 _FRONTENDS: dict = {}

@@ -126,7 +126,24 @@ def test_long_utterance_30s():
     assert_ceps_close(feats.cpu().numpy(), want)
 
 
-def test_utterance_beyond_fused_bound_raises():
-    sig = synth.synth_utterance(2, 6, 16000 * 60)
-    with pytest.raises(NotImplementedError):
-        ssp.mfcc(sig)
+def test_utterances_beyond_the_fused_bound_take_the_chunked_path():
+    """60 s (5998 frames) does not fit the single-pass kernel's shared memory: chunks of whole frames -> raw cepstra,
+    then ssp_delta / ssp_cmvn over the utterance.  Same numbers as the oracle; short neighbours are untouched."""
+    long1 = synth.synth_utterance(2, 6, 16000 * 60)
+    long2 = synth.synth_utterance(4, 1, 16000 * 45 + 123)
+    short = [synth.synth_utterance(1, k, 16000 * 2 + 77 * k) for k in range(3)]
+    out = ssp.mfcc(long1)                                              # the reference's entry point, 13-d
+    want = ofe.sidekit_mfcc(long1)
+    assert out[0].shape == want[0].shape == (5998, 13)
+    assert_ceps_close(out[0], want[0])
+    np.testing.assert_allclose(out[1], want[1], rtol=2e-5)            # frame log-energy
+    batch = [short[0], long1, short[1], short[2], long2]
+    for preset, recipe in (("sidekit", ssp.sidekit_recipe()), ("psf", ssp.psf_recipe())):
+        fe = ssp.FrontEnd(recipe, delta_order=2, cmvn=True)
+        feats, offs, _ = fe.extract(batch)
+        feats = feats.cpu().numpy()
+        for j, sig in enumerate(batch):
+            ref = ofe.features(sig, preset=preset, delta_order=2, cmvn=True)
+            got = feats[offs[j] : offs[j + 1]]
+            assert got.shape == ref.shape
+            np.testing.assert_allclose(got, ref, atol=2e-3 if preset == "psf" else 5e-4)
