@@ -98,6 +98,35 @@ __device__ __forceinline__ void feat_split(const float* xr, int j, int D, bool l
   lo = rna_tf32(v - hi);
 }
 
+// The four elements of K chunk jc of a frame row, split into TF32 hi / lo.  A chunk is almost always all-x or all-x^2
+// (only the chunks that contain column D, 2D or the ones are mixed), and jc is warp-uniform, so the common case is
+// straight-line: load, (square), round, subtract, round.
+__device__ __forceinline__ void chunk_split(const float* xr, int jc, int D, bool live, float (&h)[4], float (&l)[4]) {
+  const int j0 = 4 * jc;
+  if (!live) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { h[e] = 0.f; l[e] = 0.f; }
+  } else if (j0 + 3 < D) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = xr[j0 + e];
+      h[e] = rna_tf32(v);
+      l[e] = rna_tf32(v - h[e]);
+    }
+  } else if (j0 >= D && j0 + 3 < 2 * D) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x = xr[j0 + e - D];
+      const float v = x * x;
+      h[e] = rna_tf32(v);
+      l[e] = rna_tf32(v - h[e]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) feat_split(xr, j0 + e, D, true, h[e], l[e]);
+  }
+}
+
 // Each of the 128 builder threads keeps its share of the NEXT block's features in registers: the global loads are
 // issued right after the current block's operands are handed to the MMA warp and land while the tensor core and
 // the epilogue work, instead of being waited for at the top of every block.
@@ -221,8 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
           float4* dlo = reinterpret_cast<float4*>(sAlo) + brow;
           for (int jc = bpart; jc < KC; jc += 2) {
             float h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) feat_split(xr, 4 * jc + e, D, blive, h[e], l[e]);
+            chunk_split(xr, jc, D, blive, h, l);
             dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
             dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
           }
@@ -460,9 +488,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
           float* xtl = sXlo + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
           for (int jc = part; jc < KC; jc += 4) {
             float h[4], l[4];
+            chunk_split(xr, jc, D, live, h, l);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              feat_split(xr, 4 * jc + e, D, live, h[e], l[e]);
               xth[(4 * jc + e) * 4] = h[e];
               xtl[(4 * jc + e) * 4] = l[e];
             }
