@@ -57,7 +57,7 @@ typedef struct ssp_frontend_cfg {
   float preemph;         /* 0.97                                                             */
   int32_t spec_type;     /* 0 power re^2+im^2; 1 magnitude                                    */
   float spec_scale;      /* spectrum multiplied by this (1/nfft for psf and processing.py)   */
-  int32_t log_type;      /* 0 natural log; 1 log10                                            */
+  int32_t log_type;      /* 0 natural log; 1 log10; 2 none (PLP: raw critical-band energies)  */
   float log_add;         /* added before the log (1e-8 at utils/processing.py:105)           */
   float log_zero_floor;  /* if > 0: exact zeros are replaced by this before the log (psf eps) */
   int32_t energy_mode;   /* 0 none; 1 sidekit ln(sum y^2) of the pre-emphasised, un-windowed
@@ -91,6 +91,22 @@ int ssp_frontend_batch(const void* pcm, const int64_t* sample_offsets, int64_t n
                        const int32_t* fb_len, const int32_t* fb_offset, const float* fb_weights,
                        const float* dct, const int64_t* frame_offsets, int64_t max_frames_per_utt,
                        float* out_feats, float* out_log_energy, void* stream);
+
+/*
+ * Back half of sidekit.frontend.features.plp (bound at GMM_UBM.py:20, called :94-99 for feature_type 'PLP'; a port of
+ * rastamat's rastaplp): critical-band energies (ssp_frontend_batch with a Bark filterbank, log_type 2 and an identity
+ * "DCT") -> RASTA filtering of the log energies along time (optional) -> equal-loudness weighting and cube-root
+ * compression (^0.33), first / last band replicated -> autocorrelation (real inverse DFT of the even extension, given
+ * as the matrix `idft`) -> Levinson-Durbin of order n_ceps - 1 -> LPC cepstra -> lifter.  Double precision inside.
+ * bands         device float[total_frames * n_bands], OVERWRITTEN (RASTA runs in place)
+ * eql           device double[n_bands]           equal-loudness weights
+ * idft          device double[n_ceps * n_bands]  r[k] = sum_i idft[k, i] * post[i]
+ * lift          device double[n_ceps]
+ * out_ceps      device float[total_frames * n_ceps]
+ */
+int ssp_plp_post(float* bands, const int64_t* frame_offsets, int64_t n_utts, int32_t n_bands, int32_t n_ceps,
+                 const double* eql, const double* idft, const double* lift, int32_t rasta, float* out_ceps,
+                 void* stream);
 
 /* GMM_UBM.delta (GMM_UBM.py:53-69) on a (T, F) float32 device matrix. */
 int ssp_delta(const float* feat, int64_t n_frames, int32_t n_feat, int32_t delta_n, float* out,

@@ -28,6 +28,8 @@ What is restated, and how each piece is pinned
   this container: **parity unpinned** except for the reference's own witnesses
   (98x13 cepstra for 1 s @ 16 kHz, report/final.pdf p.5; ``[0]`` is the cepstra,
   UI/GMM_UBM_GUI.py:91).
+* ``oracle.frontend.sidekit_plp`` restates SIDEKIT ``plp`` (GMM_UBM.py:20, :94-99), a port of rastamat's
+  ``rastaplp``; same absent package: **parity unpinned**.
 * ``oracle.frontend.psf_mfcc`` restates python_speech_features 0.6 ``mfcc``
   (imported, never called, at /root/reference/GMM_UBM.py:13; BASELINE config 1
   quotes its 26-filter default).  Absent here: **parity unpinned**.

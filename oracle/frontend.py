@@ -263,3 +263,129 @@ def features(sig, preset="sidekit", delta_order=1, cmvn=True, **kw):
         parts.append(d)
     f = np.hstack(parts)
     return scale(f) if cmvn else f
+
+
+# ----------------------------------------------------------------------------
+# sidekit plp (GMM_UBM.py:20 binds it, :94-99 calls it for feature_type == 'PLP') -- PARITY UNPINNED
+# ----------------------------------------------------------------------------
+# SIDEKIT is absent from the container (see sidekit_mfcc above).  Its ``plp`` is a port of Ellis' rastamat
+# (rastaplp.m: powspec -> audspec -> rasta -> postaud -> dolpc -> lpc2cep -> lifter); the restatement below follows
+# that published algorithm with SIDEKIT's defaults (nwin=0.025, fs=16000, plp_order=13, shift=0.01, prefac=0.97,
+# rasta=True) and the same framing / pre-emphasis / window / FFT front half as ``sidekit_mfcc``.
+
+
+def hz2bark(f):
+    return 6.0 * np.arcsinh(np.asarray(f, dtype=np.float64) / 600.0)
+
+
+def bark2hz(z):
+    return 600.0 * np.sinh(np.asarray(z, dtype=np.float64) / 6.0)
+
+
+def fft2barkmx(nfft, fs, nfilts=0, width=1.0, minfreq=0.0, maxfreq=None):
+    """rastamat fft2barkmx: Bark-spaced trapezoid-in-log filters, 10^min(0, min(hif, -2.5 lof)/width)."""
+    maxfreq = fs / 2.0 if maxfreq is None else maxfreq
+    min_bark = hz2bark(minfreq)
+    nyqbark = hz2bark(maxfreq) - min_bark
+    if nfilts == 0:
+        nfilts = int(math.ceil(nyqbark)) + 1
+    step = nyqbark / (nfilts - 1)
+    binbarks = hz2bark(np.arange(nfft // 2 + 1) * fs / nfft)
+    wts = np.zeros((nfilts, nfft // 2 + 1))
+    for i in range(nfilts):
+        mid = min_bark + i * step
+        lof = binbarks - mid - 0.5
+        hif = binbarks - mid + 0.5
+        wts[i] = 10.0 ** (np.minimum(0.0, np.minimum(hif, -2.5 * lof) / width))
+    return wts
+
+
+def rasta_filter_coefficients():
+    numer = np.arange(-2, 3, dtype=np.float64)
+    numer = -numer / np.sum(numer * numer)     # [0.2, 0.1, 0, -0.1, -0.2]
+    return numer, np.array([1.0, -0.94])
+
+
+def rasta_filt(x):
+    """rastamat rastafilt on (T, nbands) log spectra, filtering along time: the FIR part alone runs over the first
+    four frames to set the state (their outputs are zeroed), the full IIR filter continues from that state."""
+    from scipy.signal import lfilter
+
+    numer, denom = rasta_filter_coefficients()
+    x = np.asarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    n0 = min(4, x.shape[0])
+    _, z = lfilter(numer, [1.0], x[:n0], axis=0, zi=np.zeros((4, x.shape[1])))
+    if x.shape[0] > 4:
+        y[4:], _ = lfilter(numer, denom, x[4:], axis=0, zi=z)
+    return y
+
+
+def postaud_weights(nbands, fmax):
+    """rastamat postaud (Bark): equal-loudness weights at the band centres."""
+    cf = bark2hz(np.linspace(0.0, hz2bark(fmax), nbands))
+    fsq = cf ** 2
+    ftmp = fsq + 1.6e5
+    return (fsq / ftmp) ** 2 * ((fsq + 1.44e6) / (fsq + 9.61e6))
+
+
+def levinson(r, order):
+    """Levinson-Durbin per row of r (T, >= order + 1): returns a (T, order + 1) with a[:, 0] = 1 and the error e (T,)."""
+    r = np.asarray(r, dtype=np.float64)
+    t = r.shape[0]
+    a = np.zeros((t, order + 1))
+    a[:, 0] = 1.0
+    e = r[:, 0].copy()
+    for i in range(1, order + 1):
+        acc = r[:, i].copy()
+        for j in range(1, i):
+            acc += a[:, j] * r[:, i - j]
+        k = -acc / e
+        prev = a.copy()
+        for j in range(1, i):
+            a[:, j] = prev[:, j] + k * prev[:, i - j]
+        a[:, i] = k
+        e = e * (1.0 - k * k)
+    return a, e
+
+
+def sidekit_plp(sig, nwin=0.025, fs=16000, plp_order=13, shift=0.01, get_spec=False, get_mspec=False, prefac=0.97,
+                rasta=True):
+    """Restatement of SIDEKIT ``plp`` (rastamat ``rastaplp``).  Returns ``[ceps (T, plp_order), log_energy (T,), None, None]``."""
+    order = plp_order - 1
+    win = int(round(nwin * fs))
+    hop = int(shift * fs)
+    nfft = 2 ** int(math.ceil(math.log2(win)))
+    framed = sidekit_frames(sig, win, hop)
+    prev = np.concatenate([framed[:, :1], framed[:, :-1]], axis=1)
+    framed = framed - prefac * prev
+    log_energy = np.log((framed ** 2).sum(axis=1))
+    k = np.arange(win)
+    window = 0.5 - 0.5 * np.cos(2.0 * np.pi * k / (win - 1))
+    mag = np.fft.rfft(framed * window, nfft, axis=-1)
+    powspec = mag.real ** 2 + mag.imag ** 2                              # (T, 257)
+    wts = fft2barkmx(nfft, fs, 0, 1.0, 0.0, fs / 2.0)                    # (21, 257) at 16 kHz
+    asp = powspec @ wts.T                                                # (T, nbands)
+    nbands = asp.shape[1]
+    if rasta:
+        asp = np.exp(rasta_filt(np.log(asp)))
+    post = (postaud_weights(nbands, fs / 2.0)[None, :] * asp) ** 0.33
+    post[:, 0] = post[:, 1]
+    post[:, -1] = post[:, -2]
+    # dolpc: autocorrelation = real IDFT of the even-symmetric extension, then Levinson-Durbin
+    ext = np.concatenate([post, post[:, nbands - 2 : 0 : -1]], axis=1)   # (T, 2 (nbands - 1))
+    r = np.real(np.fft.ifft(ext, axis=1))[:, : order + 1]
+    a, e = levinson(r, order)
+    lpc = a / e[:, None]
+    # lpc2cep
+    ncep = order + 1
+    cep = np.zeros((lpc.shape[0], ncep))
+    cep[:, 0] = -np.log(lpc[:, 0])
+    norm = lpc / lpc[:, :1]
+    for n in range(1, ncep):
+        s = np.zeros(lpc.shape[0])
+        for m in range(1, n):
+            s += (n - m) * norm[:, m] * cep[:, n - m]
+        cep[:, n] = -(norm[:, n] + s / n)
+    lift = np.concatenate([[1.0], np.arange(1, ncep, dtype=np.float64) ** 0.6])
+    return [cep * lift[None, :], log_energy, None, None]

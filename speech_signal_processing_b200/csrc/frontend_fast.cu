@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
       }
       if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
       acc += cfg.log_add;
-      mel[m] = cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc);
+      mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
     }
     __syncwarp();
     // ---- DCT

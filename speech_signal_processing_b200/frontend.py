@@ -148,6 +148,45 @@ def psf_recipe(samplerate=16000, winlen=0.025, winstep=0.01, numcep=13, nfilt=26
                   log_zero_floor=float(np.finfo(float).eps), energy_mode=2 if appendEnergy else 0)
 
 
+def _hz2bark(f):
+    return 6.0 * np.arcsinh(np.asarray(f, dtype=np.float64) / 600.0)
+
+
+def bark_filterbank(fs, nfft, nfilts=0, width=1.0, minfreq=0.0, maxfreq=None):
+    """rastamat ``fft2barkmx`` (what SIDEKIT's ``plp`` -> ``audspec`` uses): (nfilts, nfft/2+1)."""
+    maxfreq = fs / 2.0 if maxfreq is None else maxfreq
+    min_bark = float(_hz2bark(minfreq))
+    nyqbark = float(_hz2bark(maxfreq)) - min_bark
+    if nfilts == 0:
+        nfilts = int(math.ceil(nyqbark)) + 1
+    step = nyqbark / (nfilts - 1)
+    binbarks = _hz2bark(np.arange(nfft // 2 + 1) * fs / nfft)
+    mid = min_bark + step * np.arange(nfilts)[:, None]
+    lof, hif = binbarks[None, :] - mid - 0.5, binbarks[None, :] - mid + 0.5
+    return 10.0 ** (np.minimum(0.0, np.minimum(hif, -2.5 * lof) / width))
+
+
+def plp_recipe(nwin=0.025, fs=16000, plp_order=13, shift=0.01, prefac=0.97, rasta=True) -> Recipe:
+    """SIDEKIT ``plp`` defaults (GMM_UBM.py:94-99; a port of rastamat ``rastaplp``; parity unpinned like ``mfcc``).
+    The front-end kernel produces the critical-band energies (Bark filterbank, no log, identity "DCT"); the tables of
+    the back half (``ssp_plp_post``) ride in ``extra``."""
+    flen, hop = int(round(nwin * fs)), int(shift * fs)
+    nfft = _pow2_at_least(flen)
+    fb = bark_filterbank(fs, nfft)
+    nb, nc = fb.shape[0], int(plp_order)
+    cf = 600.0 * np.sinh(np.linspace(0.0, float(_hz2bark(fs / 2.0)), nb) / 6.0)
+    fsq = cf ** 2
+    eql = (fsq / (fsq + 1.6e5)) ** 2 * ((fsq + 1.44e6) / (fsq + 9.61e6))
+    n = 2 * (nb - 1)
+    k, i = np.arange(nc)[:, None], np.arange(nb)[None, :]
+    idft = 2.0 * np.cos(2.0 * np.pi * k * i / n) / n
+    idft[:, 0] = 1.0 / n
+    idft[:, nb - 1] = ((-1.0) ** np.arange(nc)) / n
+    lift = np.concatenate([[1.0], np.arange(1, nc, dtype=np.float64) ** 0.6])
+    return Recipe("plp", flen, hop, nfft, np.hanning(flen), fb, np.eye(nb), framing=0, preemph_mode=1, preemph=prefac,
+                  log_type=2, energy_mode=1, extra={"eql": eql, "idft": idft, "lift": lift, "rasta": bool(rasta), "n_ceps": nc})
+
+
 def processing_recipe(fs=8000, frameSize=512, step=256) -> Recipe:
     """utils/processing.py:110-144 ``MFCC``: Hamming, no pre-emphasis (line 34 is commented out),
     magnitude/n spectrum, 40 talkbox triangles, log10(. + 1e-8), 13 cepstra incl. c0."""
@@ -383,6 +422,64 @@ def mfcc(input_sig, lowfreq=100, maxfreq=8000, nlinfilt=0, nlogfilt=24, nwin=0.0
     return [feats.cpu().numpy(), log_e.cpu().numpy(), None, None]
 
 
+class PlpFrontEnd:
+    """PLP cepstra for a batch of utterances: the fused kernel up to the critical-band energies, ``ssp_plp_post`` for
+    RASTA / equal loudness / LPC / cepstra, then (optionally) ``ssp_delta`` per utterance and ``ssp_cmvn``."""
+
+    def __init__(self, recipe: Recipe | None = None, delta_order: int = 0, delta_n: int = 2, cmvn: bool = False, device=None):
+        torch = _lib.require_cuda()
+        self.recipe = recipe or plp_recipe()
+        self.bands = FrontEnd(self.recipe, delta_order=0, cmvn=False, device=device)
+        self.device, self.lib = self.bands.device, self.bands.lib
+        ex = self.recipe.extra
+        self.n_ceps = int(ex["n_ceps"])
+        self.delta_order, self.delta_n, self.cmvn = int(delta_order), int(delta_n), bool(cmvn)
+        self.out_dim = self.n_ceps * (1 + self.delta_order)
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)  # noqa: E731
+        self.t_eql, self.t_idft, self.t_lift = up(ex["eql"]), up(ex["idft"]), up(ex["lift"])
+
+    def extract(self, signals, want_log_energy: bool = False):
+        """Returns (feats (sum T, out_dim) cuda float32, frame_offsets np.int64, log_energy | None)."""
+        torch = _lib.require_cuda()
+        bands, offs, log_e = self.bands.extract(signals, want_log_energy)
+        total, nb = int(offs[-1]), bands.shape[1]
+        ceps = torch.empty((total, self.n_ceps), dtype=torch.float32, device=self.device)
+        d_off = torch.as_tensor(offs, device=self.device)
+        if total:
+            _lib.check(self.lib.ssp_plp_post(_lib.ptr(bands), _lib.ptr(d_off), len(offs) - 1, nb, self.n_ceps, _lib.ptr(self.t_eql),
+                                             _lib.ptr(self.t_idft), _lib.ptr(self.t_lift), int(self.recipe.extra["rasta"]),
+                                             _lib.ptr(ceps), _lib.stream_ptr()), "ssp_plp_post")
+        feats = ceps
+        if self.delta_order and total:
+            cols = [ceps]
+            for _ in range(self.delta_order):
+                d = torch.empty_like(ceps)
+                for u in range(len(offs) - 1):  # GMM_UBM.delta pads at the utterance edges: one launch per utterance
+                    lo, hi = int(offs[u]), int(offs[u + 1])
+                    if hi > lo:
+                        _lib.check(self.lib.ssp_delta(_lib.ptr(cols[-1][lo:]), hi - lo, self.n_ceps, self.delta_n, _lib.ptr(d[lo:]),
+                                                      _lib.stream_ptr()), "ssp_delta")
+                cols.append(d)
+            feats = torch.cat(cols, dim=1)
+        if self.cmvn and total:
+            out = torch.empty_like(feats)
+            _lib.check(self.lib.ssp_cmvn(_lib.ptr(feats), _lib.ptr(d_off), len(offs) - 1, feats.shape[1], _lib.ptr(out),
+                                         _lib.stream_ptr()), "ssp_cmvn")
+            feats = out
+        self._keep = (d_off, bands, ceps)
+        return feats, offs, log_e
+
+
+def plp(input_sig, nwin=0.025, fs=16000, plp_order=13, shift=0.01, get_spec=False, get_mspec=False, prefac=0.97, rasta=True):
+    """``sidekit.frontend.features.plp`` (GMM_UBM.py:20,94): ``[ceps (T, plp_order), log_energy (T,), None, None]``."""
+    if get_spec or get_mspec:
+        raise NotImplementedError("get_spec / get_mspec are not produced by the fused kernel")
+    key = ("plp", nwin, fs, plp_order, shift, prefac, rasta)
+    fe = _cached(key, lambda: PlpFrontEnd(plp_recipe(nwin, fs, plp_order, shift, prefac, rasta)))
+    feats, _, log_e = fe.extract([np.asarray(input_sig)], want_log_energy=True)
+    return [feats.cpu().numpy(), log_e.cpu().numpy(), None, None]
+
+
 def MFCC(raw_signal, fs=8000, frameSize=512, step=256):
     """``utils.processing.MFCC`` (utils/processing.py:110-144): (ceil(N/step), 13) float64."""
     fe = _cached(("processing", fs, frameSize, step), lambda: FrontEnd(processing_recipe(fs, frameSize, step)))
@@ -432,11 +529,15 @@ def extract_feature(x, y, is_train=False, feature_type="MFCC", delta_order=1, re
     ``train_data[label]`` their per-speaker vertical stack.  ``delta_order=2`` gives the 39-d
     north-star features.
     """
-    if feature_type != "MFCC":
-        raise NameError(feature_type)  # GMM_UBM.py:100-101; PLP is a "next" row (SURVEY 8(f))
-    rec = recipe or sidekit_recipe()
-    fe = _cached(("xf", rec.name, id(recipe) if recipe else 0, delta_order),
-                 lambda: FrontEnd(rec, delta_order=delta_order, delta_n=2, cmvn=True))
+    if feature_type == "PLP":      # GMM_UBM.py:94-99
+        fe = _cached(("xf-plp", id(recipe) if recipe else 0, delta_order),
+                     lambda: PlpFrontEnd(recipe, delta_order=delta_order, delta_n=2, cmvn=True))
+    elif feature_type == "MFCC":
+        rec = recipe or sidekit_recipe()
+        fe = _cached(("xf", rec.name, id(recipe) if recipe else 0, delta_order),
+                     lambda: FrontEnd(rec, delta_order=delta_order, delta_n=2, cmvn=True))
+    else:
+        raise NameError(feature_type)  # GMM_UBM.py:100-101
     feats, offs, _ = fe.extract(list(x))
     host = feats.cpu().numpy()
     feature = [host[offs[i] : offs[i + 1]] for i in range(len(x))]

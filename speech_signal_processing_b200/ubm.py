@@ -212,7 +212,11 @@ def install(gmm_ubm_module, delta_order: int = 1):
     def mfcc_cepstra(sig, **kw):
         return fe.mfcc(sig, **kw)[0]
 
+    def plp_cepstra(sig, **kw):
+        return fe.plp(sig, **kw)[0]
+
     gmm_ubm_module.mfcc = mfcc_cepstra
+    gmm_ubm_module.plp = plp_cepstra
     gmm_ubm_module.delta = fe.delta
     gmm_ubm_module.preprocessing = fe.preprocessing
     gmm_ubm_module.GaussianMixture = GaussianMixture

@@ -147,3 +147,35 @@ def test_utterances_beyond_the_fused_bound_take_the_chunked_path():
             got = feats[offs[j] : offs[j + 1]]
             assert got.shape == ref.shape
             np.testing.assert_allclose(got, ref, atol=2e-3 if preset == "psf" else 5e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# PLP (sidekit.frontend.features.plp, GMM_UBM.py:94-99): front-end kernel with a Bark filterbank + ssp_plp_post
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rasta", [True, False])
+def test_plp_matches_oracle(rasta):
+    """Against the float64 restatement of sidekit / rastamat PLP (parity unpinned like sidekit's mfcc: the package is
+    absent).  Stated tolerance: 2e-3 absolute on liftered cepstra of magnitude 0.1 .. 10 (float32 power spectrum,
+    everything after the critical-band energies in double)."""
+    for n in (16000, 48000, 4000):
+        sig = synth.synth_utterance(7, n % 89, n)
+        got = ssp.plp(sig, rasta=rasta)
+        want = ofe.sidekit_plp(sig, rasta=rasta)
+        assert got[0].shape == want[0].shape and got[0].shape[1] == 13
+        np.testing.assert_allclose(got[0], want[0], rtol=0, atol=2e-3)
+        np.testing.assert_allclose(got[1], want[1], rtol=2e-5)
+        assert got[2] is None and got[3] is None
+
+
+def test_extract_feature_plp_batched():
+    """GMM_UBM.extract_feature(feature_type='PLP'): plp -> delta -> hstack -> scale, for the whole list at once."""
+    x, y = synth.synth_corpus(3, 3, 16000)
+    train, feats, labels = ssp.extract_feature(x, y, is_train=True, feature_type="PLP")
+    assert labels is y and len(feats) == len(x) and set(train) == set(y)
+    for sig, f in zip(x, feats):
+        c = ofe.sidekit_plp(sig)[0]
+        ref = ofe.scale(np.hstack([c, ofe.delta(c)]))
+        assert f.shape == ref.shape == (98, 26)
+        np.testing.assert_allclose(f, ref, rtol=0, atol=2e-2)   # CMVN divides by per-column std (~0.02 .. 0.5)
+    with pytest.raises(NameError):
+        ssp.extract_feature(x, y, feature_type="LPCC")
