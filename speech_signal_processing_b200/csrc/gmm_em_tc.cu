@@ -33,7 +33,8 @@ using namespace tc;
 constexpr int BN = 128;   // components per CTA
 constexpr int BM1 = 128;  // frames per block, pass LSE
 constexpr int BM2 = 64;   // frames per block, pass STATS
-constexpr int EPI = 256;  // 8 builder / epilogue warps: two per TMEM lane quadrant, each owning half of the columns
+constexpr int EPI = 512;  // 16 builder / epilogue warps, four per TMEM lane quadrant: the thread work around the MMAs (operand
+                          // split, exponentials) is latency-bound, more warps hide more of it (8 warps: 7 % slower)
 constexpr int THREADS = 64 + EPI;
 constexpr int MAX_KD = 80;
 constexpr uint32_t TMEM_COLS = 256;  // [0,128): logits, [128, 128+N2): statistics accumulator
@@ -223,8 +224,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
     const int row = ((warp & 3) << 5) | lane;  // TMEM lane == frame row
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const int et = tid - 64;                   // 0..255
-    const int chalf = (warp - 2) >> 2;         // which 64 of the tile's 128 component columns this warp reduces
-    const int brow = et & (BM - 1), bpart = et >> 7;  // row built by this thread, and which half of its K chunks
+    const int chalf = (warp - 2) >> 2;         // epilogue (first 8 warps): which 64 of the tile's 128 component columns
+    const bool epi_warp = chalf < 2;
+    const int brow = et & (BM - 1), bpart = et >> 7;  // row built by this thread, and which quarter of its K chunks
     const int D = a.D;
     Walk<BM> w;
     if (w.start(a.seg, a.n_segs, begin, end)) {
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
           const float* xr = sX + brow * D;
           float4* dhi = reinterpret_cast<float4*>(sAhi) + brow;
           float4* dlo = reinterpret_cast<float4*>(sAlo) + brow;
-          for (int jc = bpart; jc < KC; jc += 2) {
+          for (int jc = bpart; jc < KC; jc += 4) {
             float h[4], l[4];
             chunk_split(xr, jc, D, blive, h, l);
             dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
@@ -259,8 +261,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         mbar_arrive(a_full);
-        mbar_wait(l_full, i & 1u);
+        mbar_wait(l_full, i & 1u);  // every builder waits: the MMAs of this block are done with the operands
         tc_fence_after();
+        if (epi_warp) {
         const uint32_t taddr = tmem_base + lane_addr + chalf * 64;
         float m_run = -3.0e38f, s_run = 0.f;
 #pragma unroll 1
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
         }
         if (row < nt) a.partial[(size_t)(2 * tile + chalf) * a.total_frames + t0 + row] = make_float2(m_run, s_run);
         tc_fence_before();
+        }
         bool flush;
         more = w.next(nt, flush);
         ++i;
@@ -422,9 +426,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
     const int row = ((warp & 3) << 5) | lane;  // TMEM lane == component row within the tile
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const int et = tid - 64;                   // 0..255
-    const int chalf = (warp - 2) >> 2;         // which 32 of the block's 64 frame columns this warp turns into gamma
-    const int fr = et & (BM - 1), part = et >> 6;  // frame row this thread builds, and which quarter of its K chunks
-    const bool norm_thread = part == 3;        // these 64 threads also own the per-frame normaliser
+    const int cq = (warp - 2) >> 2;            // which 16 of the block's 64 frame columns this warp turns into gamma
+    const int fr = et & (BM - 1), part = et >> 6;  // frame row this thread builds, and which eighth of its K chunks
+    const bool norm_thread = part == 7;        // these 64 threads also own the per-frame normaliser
     const float LN2 = 0.69314718055994530942f;
     const int n_part = 2 * a.n_tiles;
     Walk<BM> w;
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
           float4* dlo = reinterpret_cast<float4*>(sFlo) + fr;
           float* xth = sXhi + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
           float* xtl = sXlo + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
-          for (int jc = part; jc < KC; jc += 4) {
+          for (int jc = part; jc < KC; jc += 8) {
             float h[4], l[4];
             chunk_split(xr, jc, D, live, h, l);
 #pragma unroll
@@ -517,18 +521,23 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         mbar_wait(l_full, i & 1u);
         tc_fence_after();
         {
-          uint32_t r[32];
-          tc_ld32_issue(tmem_base + lane_addr + chalf * 32, r);
-          tc_ld_wait(r);
+          uint32_t r[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(tmem_base + lane_addr + cq * 16)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float4* g4 = reinterpret_cast<float4*>(sG) + row;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 ls = *reinterpret_cast<const float4*>(sLse + 32 * chalf + 4 * q);
+          for (int q = 0; q < 4; ++q) {
+            const float4 ls = *reinterpret_cast<const float4*>(sLse + 16 * cq + 4 * q);
             const float g0 = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
             const float g1 = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
             const float g2 = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
             const float g3 = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
-            g4[(8 * chalf + q) * BN] = make_float4(g0, g1, g2, g3);
+            g4[(4 * cq + q) * BN] = make_float4(g0, g1, g2, g3);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
           const int comp = tile * BN + row;
           const uint32_t saddr = tmem_base + lane_addr + STAT_COL;
 #pragma unroll 1
-          for (int c0 = 16 * chalf; c0 < KD; c0 += 32) {
+          for (int c0 = 16 * cq; c0 < KD; c0 += 64) {
             uint32_t r[16];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
