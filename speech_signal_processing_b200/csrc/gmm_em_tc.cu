@@ -590,6 +590,373 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
+
+// ================================================================================================ pass STATS, pipelined
+// Same arithmetic as gmm_em_stats_kernel with two frame blocks in flight, so that the tensor core works on one block
+// while the 16 builder / epilogue warps work on its neighbours:
+//   * the CTA's model tile (TF32 hi + lo) is copied ONCE into tensor memory (160 columns) and is the TMEM-side (A)
+//     operand of the logit GEMM (component == TMEM lane): 80 KB of shared memory become operand buffers;
+//   * gamma is written by tcgen05.st IN PLACE over the logits it came from and is the TMEM-side operand of the
+//     statistics GEMM: it never touches shared memory;
+//   * two F buffers (frames as rows, GEMM 1), three Xt buffers (frames contiguous, GEMM 2) and two 64-column logit
+//     buffers; thread program per block k: build F / Xt of block k, then turn the logits of block k - 1 into gamma;
+//     MMA program: GEMM1(k), GEMM2(k - 1).  The builders never wait for a GEMM that was issued less than a block
+//     ago, so in steady state the period is max(thread work, 1600 tensor cycles) per 64 frames.
+namespace p3 {
+constexpr int NF = 2, NX = 3;
+constexpr uint32_t COL_BHI = 0, COL_BLO = 80;   // model tile, hi and lo (MAX_KD columns each)
+constexpr uint32_t COL_LOGIT = 160;             // + 64 * (k & 1)
+constexpr uint32_t COL_STAT = 288;              // statistics accumulator, n2 <= 80 columns
+struct Carve {
+  int n2, xrows;
+  size_t f_bytes, x_bytes, o_x, o_stage, o_lse, o_bar, bytes;  // F buffers at 0 (hi | lo each), Xt buffers at o_x
+};
+__host__ __device__ inline Carve carve(int KD) {
+  Carve c;
+  c.n2 = (KD + 15) & ~15;
+  c.xrows = c.n2 + 1;
+  c.f_bytes = (size_t)BM2 * KD * 4;
+  c.x_bytes = (size_t)(BM2 / 4) * c.xrows * 16;
+  c.o_x = NF * 2 * c.f_bytes;
+  c.o_stage = c.o_x + NX * 2 * c.x_bytes;
+  c.o_lse = c.o_stage + (size_t)BM2 * (MAX_KD / 2) * 4;
+  c.o_bar = c.o_lse + NX * BM2 * 4;
+  c.bytes = c.o_bar + 128;
+  return c;
+}
+}  // namespace p3
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats3_kernel(const Args a) {
+  using namespace p3;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int BM = BM2;
+  const int KD = a.KD, KC = KD >> 2, D = a.D;
+  const Carve cv = carve(KD);
+  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
+  float* sStage = reinterpret_cast<float*>(smem + cv.o_stage);
+  float* sLse = reinterpret_cast<float*>(smem + cv.o_lse);  // [3][BM]: written while building block k, read by its epilogue one block later
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.o_bar);
+  uint64_t* b_loaded = bars;       // model tile images landed in shared memory (start-up only)
+  uint64_t* a_full = bars + 1;     // [2] F / Xt of block k are built               (k & 1)
+  uint64_t* l_full = bars + 3;     // [2] logits of block k are in TMEM, F[k & 1] is free again
+  uint64_t* g_full = bars + 5;     // [2] gamma of block k is in TMEM
+  uint64_t* x_free = bars + 7;     // [3] GEMM 2 of block k has completed: Xt[k % 3] free, statistics include block k
+  uint64_t* drained = bars + 10;   // the statistics accumulator has been read out after a segment end
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.y;
+  if (tid == 0) {
+    mbar_init(b_loaded, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(a_full + g, EPI);
+      mbar_init(l_full + g, 1);
+      mbar_init(g_full + g, EPI);
+    }
+    for (int g = 0; g < NX; ++g) mbar_init(x_free + g, 1);
+    mbar_init(drained, EPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
+  const int64_t end = min(begin + a.chunk, a.total_frames);
+  if (begin >= end) {  // (uniform) nothing to do for this CTA
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    return;
+  }
+
+  // ---- start-up: model tile hi / lo -> shared memory (the F buffers as scratch) -> tensor memory
+  float* scratch = reinterpret_cast<float*>(smem);  // 2 x tile_bytes == NF x 2 x f_bytes
+  if (warp == 0 && elect_one()) {
+    mbar_arrive_expect_tx(b_loaded, 2u * tile_bytes);
+    bulk_g2s(scratch, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_loaded);
+    bulk_g2s(scratch + BN * KD, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_loaded);
+  }
+  if (warp >= 2 && warp < 10) {
+    const int which = (warp - 2) >> 2;           // warps 2..5 copy hi, 6..9 copy lo
+    const int row = ((warp & 3) << 5) | lane;    // component row == TMEM lane
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    mbar_wait(b_loaded, 0);
+    const float4* img = reinterpret_cast<const float4*>(scratch + (size_t)which * BN * KD) + row;
+    for (int k = 0; k < (KD >> 3); ++k) {
+      const float4 c0 = img[(2 * k) * BN], c1 = img[(2 * k + 1) * BN];
+      const float v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      tc_st8(tmem_base + lane_addr + (which ? COL_BLO : COL_BHI) + 8u * k, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+  }
+  __syncthreads();  // scratch is free again; the tile is visible to the MMA warp
+  tc_fence_after();
+
+  if (warp == 1) {
+    // ===================== MMA issuer =====================
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr uint32_t lbo_f = BM * 16u, sbo = 128u;
+      constexpr uint32_t ks_f = (2u * lbo_f) >> 4;
+      const uint32_t lbo_x = (uint32_t)cv.xrows * 16u, ks_x = (2u * lbo_x) >> 4;
+      const uint32_t base = smem_u32(smem);
+      const int ksteps = KD >> 3;
+      const uint32_t idesc1 = make_idesc_tf32(BN, BM, 0, 0);
+      const uint32_t idesc2 = make_idesc_tf32(BN, cv.n2, 0, 0);
+      const uint32_t t_bhi = tmem_base + COL_BHI, t_blo = tmem_base + COL_BLO, t_stat = tmem_base + COL_STAT;
+      uint32_t k = 0, n_drains = 0;
+      bool prev_first = true, prev_flush = false, pending_drain = false, first_in_seg = true, more = true;
+      // GEMM 2 of block p: statistics += gamma (TMEM, in the logit columns of p) . Xt[p % 3] (shared memory)
+      auto gemm2 = [&](uint32_t p, bool first, bool flush) {
+        mbar_wait(g_full + (p & 1u), (p >> 1) & 1u);
+        if (pending_drain) {
+          mbar_wait(drained, n_drains & 1u);
+          ++n_drains;
+          pending_drain = false;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t xb = base + (uint32_t)(cv.o_x + (size_t)(p % NX) * 2 * cv.x_bytes);
+          const uint64_t xhi = make_desc(xb, lbo_x, sbo), xlo = make_desc(xb + (uint32_t)cv.x_bytes, lbo_x, sbo);
+          const uint32_t t_gam = tmem_base + COL_LOGIT + 64u * (p & 1u);
+          for (int q = 0; q < BM / 8; ++q) tc_mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
+          for (int q = 0; q < BM / 8; ++q) tc_mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
+          tc_commit(x_free + (p % NX));
+        }
+        __syncwarp();
+        if (flush) pending_drain = true;
+      };
+      while (more) {
+        const int nt = w.nt();
+        mbar_wait(a_full + (k & 1u), (k >> 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t fb = base + (uint32_t)((size_t)(k & 1u) * 2 * cv.f_bytes);
+          const uint64_t fhi = make_desc(fb, lbo_f, sbo), flo = make_desc(fb + (uint32_t)cv.f_bytes, lbo_f, sbo);
+          const uint32_t t_log = tmem_base + COL_LOGIT + 64u * (k & 1u);
+          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_log, t_bhi + 8u * q, fhi + (uint64_t)(q * ks_f), idesc1, q > 0 ? 1u : 0u);
+          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_log, t_bhi + 8u * q, flo + (uint64_t)(q * ks_f), idesc1, 1u);
+          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_log, t_blo + 8u * q, fhi + (uint64_t)(q * ks_f), idesc1, 1u);
+          tc_commit(l_full + (k & 1u));
+        }
+        __syncwarp();
+        if (k > 0) gemm2(k - 1, prev_first, prev_flush);
+        bool flush;
+        more = w.next(nt, flush);
+        prev_first = first_in_seg;
+        prev_flush = flush;
+        first_in_seg = flush;
+        ++k;
+      }
+      gemm2(k - 1, prev_first, prev_flush);
+    }
+  } else if (warp >= 2) {
+    // ===================== operand builders (thread == frame) and epilogue (thread == component) =====================
+    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == component row within the tile
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int et = tid - 64;                   // 0..511
+    const int cq = (warp - 2) >> 2;            // which 16 of a block's 64 frame columns this warp turns into gamma
+    const int fr = et & (BM - 1), part = et >> 6;  // frame row this thread builds, and which eighth of its K chunks
+    const bool norm_thread = part == 7;        // these 64 threads also own the per-frame normaliser
+    const float LN2 = 0.69314718055994530942f;
+    const int n_part = 2 * a.n_tiles;
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
+      constexpr int PT = 8;
+      float pf[R];
+      float2 pp[PT];
+      auto prefetch = [&](const Walk<BM>& wb) {
+        prefetch_block<R>(a.feats + wb.t0 * D, wb.nt() * D, et, pf);
+        if (norm_thread && fr < wb.nt()) {
+#pragma unroll
+          for (int y = 0; y < PT; ++y)
+            if (y < n_part) pp[y] = a.partial[(size_t)y * a.total_frames + wb.t0 + fr];
+        }
+      };
+      prefetch(w);
+      uint32_t k = 0, n_drained = 0;
+      bool more = true, prev_flush = false;
+      int prev_seg = -1, ll_seg = -1;
+      float ll_acc = 0.f;
+      auto flush_ll = [&]() {
+        if (tile == 0 && ll_seg >= 0) {
+          const float tot = warp_sum(ll_acc);
+          if (lane == 0 && tot != 0.f) atomicAdd(a.out_loglik + ll_seg, (double)tot);
+        }
+        ll_acc = 0.f;
+      };
+      // logits of block p -> gamma in place; at a segment end also read out the statistics
+      auto epilogue = [&](uint32_t p, int seg_id, bool flush) {
+        mbar_wait(l_full + (p & 1u), (p >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_log = tmem_base + lane_addr + COL_LOGIT + 64u * (p & 1u) + 16u * cq;
+        const float* lse = sLse + (p % NX) * BM + 16 * cq;
+        uint32_t r[16];
+        tc_ld16(t_log, r);
+        float gam[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ls = *reinterpret_cast<const float4*>(lse + 4 * q);
+          gam[4 * q + 0] = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
+          gam[4 * q + 1] = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
+          gam[4 * q + 2] = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
+          gam[4 * q + 3] = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
+        }
+        tc_st16(t_log, gam);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(g_full + (p & 1u));
+        if (flush) {
+          mbar_wait(x_free + (p % NX), (p / NX) & 1u);  // GEMM 2 of block p (and of everything before it) is complete
+          tc_fence_after();
+          const int comp = tile * BN + row;
+          const uint32_t saddr = tmem_base + lane_addr + COL_STAT;
+#pragma unroll 1
+          for (int c0 = 16 * cq; c0 < KD; c0 += 64) {
+            uint32_t s16[16];
+            tc_ld16(saddr + c0, s16);
+            if (comp < a.K) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int jj = c0 + e;
+                const double v = (double)__uint_as_float(s16[e]);
+                if (jj < D) atomicAdd(a.out_f + ((int64_t)seg_id * a.K + comp) * D + jj, v);
+                else if (jj < 2 * D) atomicAdd(a.out_s + ((int64_t)seg_id * a.K + comp) * D + (jj - D), v);
+                else if (jj == 2 * D) atomicAdd(a.out_n + (int64_t)seg_id * a.K + comp, v);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(drained);
+          ++n_drained;
+        }
+      };
+      while (more) {
+        const int nt = w.nt();
+        const int64_t t0 = w.t0;
+        const int seg_id = w.cur;
+        if (seg_id != ll_seg) {
+          flush_ll();
+          ll_seg = seg_id;
+        }
+        // ---- build block k: F[k & 1] was released by GEMM1(k - 2) (waited for in the epilogue of k - 2), Xt[k % 3] by
+        // GEMM2(k - 3)
+        mbar_wait(x_free + (k % NX), ((k / NX) & 1u) ^ 1u);
+        store_block<R>(sStage, nt * D, et, pf);
+        if (norm_thread) {
+          float lse2 = 3.0e38f;  // dead frames: gamma = 2^(x - huge) = 0
+          if (fr < nt) {
+            float m = -3.0e38f;
+#pragma unroll
+            for (int y = 0; y < PT; ++y)
+              if (y < n_part) m = fmaxf(m, pp[y].x);
+            for (int y = PT; y < n_part; ++y) m = fmaxf(m, a.partial[(size_t)y * a.total_frames + t0 + fr].x);
+            float ssum = 0.f;
+#pragma unroll
+            for (int y = 0; y < PT; ++y)
+              if (y < n_part) ssum += pp[y].y * ex2(pp[y].x - m);
+            for (int y = PT; y < n_part; ++y) {
+              const float2 p = a.partial[(size_t)y * a.total_frames + t0 + fr];
+              ssum += p.y * ex2(p.x - m);
+            }
+            lse2 = m + lg2(ssum);
+            if (tile == 0) {
+              const float lse = lse2 * LN2;
+              a.frame_lse[t0 + fr] = lse;
+              ll_acc += lse;
+            }
+          }
+          sLse[(k % NX) * BM + fr] = lse2;
+        }
+        named_bar_sync(1, EPI);
+        {
+          const bool live = fr < nt;
+          const float* xr = sStage + fr * D;
+          unsigned char* fb = smem + (size_t)(k & 1u) * 2 * cv.f_bytes;
+          unsigned char* xb = smem + cv.o_x + (size_t)(k % NX) * 2 * cv.x_bytes;
+          float4* dhi = reinterpret_cast<float4*>(fb) + fr;
+          float4* dlo = reinterpret_cast<float4*>(fb + cv.f_bytes) + fr;
+          float* xth = reinterpret_cast<float*>(xb) + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
+          float* xtl = reinterpret_cast<float*>(xb + cv.x_bytes) + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
+          for (int jc = part; jc < KC; jc += 8) {
+            float h[4], l[4];
+            chunk_split(xr, jc, D, live, h, l);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              xth[(4 * jc + e) * 4] = h[e];
+              xtl[(4 * jc + e) * 4] = l[e];
+            }
+            dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
+            dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
+          }
+          if (part == 0)
+            for (int jx = KD; jx < cv.n2; ++jx) { xth[jx * 4] = 0.f; xtl[jx * 4] = 0.f; }
+        }
+        named_bar_sync(1, EPI);  // staging consumed before the next block's store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(a_full + (k & 1u));
+        {
+          Walk<BM> wn = w;
+          bool fl;
+          if (wn.next(nt, fl)) prefetch(wn);
+        }
+        // ---- gamma of the previous block while the tensor core works on this one
+        if (k > 0) epilogue(k - 1, prev_seg, prev_flush);
+        bool flush;
+        more = w.next(nt, flush);
+        prev_seg = seg_id;
+        prev_flush = flush;
+        ++k;
+      }
+      epilogue(k - 1, prev_seg, prev_flush);
+      flush_ll();
+      (void)n_drained;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 }  // namespace em
 
 bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_lo != 0 && L.n_models == 1; }
@@ -640,6 +1007,18 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   gmm_em_lse_kernel<<<grid, THREADS, smem1, st>>>(a);
   SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
+  static int version = -1;  // SSP_EM_STATS=1 selects the single-buffered kernel (A/B reference)
+  if (version < 0) {
+    const char* e = getenv("SSP_EM_STATS");
+    version = (e && atoi(e) == 1) ? 1 : 3;
+  }
+  if (version == 3) {
+    const size_t smem3 = p3::carve(L.KD).bytes;
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    gmm_em_stats3_kernel<<<grid, THREADS, smem3, st>>>(a);
+    SSP_LAUNCH_CHECK("gmm_em_stats3_kernel");
+    return SSP_OK;
+  }
   gmm_em_stats_kernel<<<grid, THREADS, smem2, st>>>(a);
   SSP_LAUNCH_CHECK("gmm_em_stats_kernel");
   return SSP_OK;
