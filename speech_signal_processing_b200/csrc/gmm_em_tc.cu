@@ -957,6 +957,185 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats3_kernel(const Args a)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+
+// ================================================================================================ pass LSE, pipelined
+// Same arithmetic as gmm_em_lse_kernel.  The frame operand [x, x^2, 1, 1] (TF32 hi + lo) is written straight into
+// tensor memory (tcgen05.st, thread == frame row == TMEM lane) and double-buffered there (2 x 160 columns), the model
+// tile stays in shared memory as the N-side operand, one 128-column accumulator.  Thread program per block k: build
+// A[k & 1] (needs GEMM(k - 2) done), then the epilogue of block k - 1 (tcgen05.ld, release the accumulator at once,
+// max / exp / sum from registers); MMA program: GEMM(k) once A[k & 1] is built and the accumulator has been read.
+// The split of block k + 1 overlaps GEMM(k); in steady state the period is ~1920 tensor cycles + one TMEM read.
+namespace l2 {
+constexpr uint32_t COL_A = 0;      // + 160 * (k & 1): hi at +0, lo at +80
+constexpr uint32_t COL_ACC = 320;  // 128 columns
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse2_kernel(const Args a) {
+  using namespace l2;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int BM = BM1;
+  const int KD = a.KD, D = a.D;
+  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
+  float* sBhi = reinterpret_cast<float*>(smem);
+  float* sBlo = sBhi + BN * KD;
+  float* sX = sBlo + BN * KD;  // feature staging: BM x D floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + BM * MAX_KD / 2);
+  uint64_t* b_full = bars;
+  uint64_t* a_full = bars + 1;    // [2] A[k & 1] is built
+  uint64_t* l_full = bars + 3;    // [2] GEMM(k) complete: accumulator holds block k, A[k & 1] is free
+  uint64_t* acc_free = bars + 5;  // the epilogue warps hold the accumulator's contents in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.y;
+  if (tid == 0) {
+    mbar_init(b_full, 1);
+    mbar_init(a_full, EPI);
+    mbar_init(a_full + 1, EPI);
+    mbar_init(l_full, 1);
+    mbar_init(l_full + 1, 1);
+    mbar_init(acc_free, EPI / 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
+  const int64_t end = min(begin + a.chunk, a.total_frames);
+
+  if (warp == 0) {
+    if (begin < end && elect_one()) {
+      mbar_arrive_expect_tx(b_full, 2u * tile_bytes);
+      bulk_g2s(sBhi, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_full);
+      bulk_g2s(sBlo, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_full);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr uint32_t lbo = BN * 16u, sbo = 128u;
+      constexpr uint32_t kstep = (2u * lbo) >> 4;
+      const uint64_t bhi = make_desc(smem_u32(sBhi), lbo, sbo), blo = make_desc(smem_u32(sBlo), lbo, sbo);
+      const int ksteps = KD >> 3;
+      const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+      const uint32_t t_acc = tmem_base + COL_ACC;
+      mbar_wait(b_full, 0);
+      uint32_t k = 0;
+      bool more = true;
+      while (more) {
+        const int nt = w.nt();
+        mbar_wait(a_full + (k & 1u), (k >> 1) & 1u);
+        if (k > 0) mbar_wait(acc_free, (k - 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t ahi = tmem_base + COL_A + 160u * (k & 1u), alo = ahi + 80u;
+          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_acc, ahi + 8u * q, bhi + (uint64_t)(q * kstep), idesc, q > 0 ? 1u : 0u);
+          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_acc, alo + 8u * q, bhi + (uint64_t)(q * kstep), idesc, 1u);
+          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_acc, ahi + 8u * q, blo + (uint64_t)(q * kstep), idesc, 1u);
+          tc_commit(l_full + (k & 1u));
+        }
+        __syncwarp();
+        bool flush;
+        more = w.next(nt, flush);
+        ++k;
+      }
+    }
+  } else {
+    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == frame row (built AND reduced by this thread's warp quadrant)
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int et = tid - 64;                   // 0..511
+    const int part = (warp - 2) >> 2;          // 0..3: which K columns this thread builds; epilogue: parts 0, 1 take 64 columns each
+    const bool epi_warp = part < 2;
+    Walk<BM> w;
+    if (w.start(a.seg, a.n_segs, begin, end)) {
+      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
+      float pf[R];
+      prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
+      uint32_t k = 0;
+      bool more = true;
+      int prev_nt = 0;
+      int64_t prev_t0 = 0;
+      // block p: accumulator -> registers -> (max, sum 2^(x - max)) over this thread's 64 columns
+      auto epilogue = [&](uint32_t p, int nt_p, int64_t t0_p) {
+        mbar_wait(l_full + (p & 1u), (p >> 1) & 1u);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        const uint32_t taddr = tmem_base + lane_addr + COL_ACC + part * 64;
+        tc_ld32_issue(taddr, ra);
+        tc_ld32_issue(taddr + 32, rb);
+        tc_ld_wait2(ra, rb);
+        tc_fence_before();
+        mbar_arrive(acc_free);
+        float cm = max3(__uint_as_float(ra[0]), __uint_as_float(ra[1]), __uint_as_float(rb[0]));
+#pragma unroll
+        for (int e = 2; e < 32; e += 2) cm = max3(cm, __uint_as_float(ra[e]), __uint_as_float(ra[e + 1]));
+#pragma unroll
+        for (int e = 1; e < 31; e += 2) cm = max3(cm, __uint_as_float(rb[e]), __uint_as_float(rb[e + 1]));
+        cm = fmaxf(cm, __uint_as_float(rb[31]));
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          acc0 += ex2(__uint_as_float(ra[e]) - cm);
+          acc1 += ex2(__uint_as_float(ra[e + 1]) - cm);
+          acc2 += ex2(__uint_as_float(rb[e]) - cm);
+          acc3 += ex2(__uint_as_float(rb[e + 1]) - cm);
+        }
+        if (row < nt_p) a.partial[(size_t)(2 * tile + part) * a.total_frames + t0_p + row] = make_float2(cm, (acc0 + acc1) + (acc2 + acc3));
+      };
+      while (more) {
+        const int nt = w.nt();
+        const int64_t t0 = w.t0;
+        // ---- build A[k & 1]: GEMM(k - 2), its last reader, must be complete
+        if (k >= 2) {
+          mbar_wait(l_full + (k & 1u), ((k - 2) >> 1) & 1u);
+          tc_fence_after();
+        }
+        store_block<R>(sX, nt * D, et, pf);
+        named_bar_sync(1, EPI);
+        {
+          Walk<BM> wn = w;
+          bool fl;
+          if (wn.next(nt, fl)) prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
+        }
+        {
+          const bool live = row < nt;
+          const float* xr = sX + row * D;
+          const uint32_t t_hi = tmem_base + lane_addr + COL_A + 160u * (k & 1u), t_lo = t_hi + 80u;
+          for (int c = part; c < (KD >> 3); c += 4) {  // 8 contraction columns at a time
+            float h0[4], l0[4], h1[4], l1[4];
+            chunk_split(xr, 2 * c, D, live, h0, l0);
+            chunk_split(xr, 2 * c + 1, D, live, h1, l1);
+            const float hv[8] = {h0[0], h0[1], h0[2], h0[3], h1[0], h1[1], h1[2], h1[3]};
+            const float lv[8] = {l0[0], l0[1], l0[2], l0[3], l1[0], l1[1], l1[2], l1[3]};
+            tc_st8(t_hi + 8u * c, hv);
+            tc_st8(t_lo + 8u * c, lv);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        named_bar_sync(1, EPI);  // staged rows consumed before the next block overwrites them
+        tc_fence_before();
+        mbar_arrive(a_full + (k & 1u));
+        // ---- epilogue of the previous block while the tensor core works on this one
+        if (k > 0 && epi_warp) epilogue(k - 1, prev_nt, prev_t0);
+        prev_nt = nt;
+        prev_t0 = t0;
+        bool flush;
+        more = w.next(nt, flush);
+        ++k;
+      }
+      if (epi_warp) epilogue(k - 1, prev_nt, prev_t0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 }  // namespace em
 
 bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_lo != 0 && L.n_models == 1; }
@@ -1005,8 +1184,20 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   dim3 grid((unsigned)gx, (unsigned)a.n_tiles);
   SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  gmm_em_lse_kernel<<<grid, THREADS, smem1, st>>>(a);
-  SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
+  static int lse_version = -1;  // SSP_EM_LSE=1 selects the single-buffered kernel (A/B reference)
+  if (lse_version < 0) {
+    const char* e = getenv("SSP_EM_LSE");
+    lse_version = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  if (lse_version == 2) {
+    const size_t smem1b = (size_t)(2 * BN * L.KD + BM1 * MAX_KD / 2) * sizeof(float) + 128;
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1b));
+    gmm_em_lse2_kernel<<<grid, THREADS, smem1b, st>>>(a);
+    SSP_LAUNCH_CHECK("gmm_em_lse2_kernel");
+  } else {
+    gmm_em_lse_kernel<<<grid, THREADS, smem1, st>>>(a);
+    SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
+  }
   static int version = -1;  // SSP_EM_STATS=1 selects the single-buffered kernel (A/B reference)
   if (version < 0) {
     const char* e = getenv("SSP_EM_STATS");
