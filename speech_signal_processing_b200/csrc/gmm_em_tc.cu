@@ -7,18 +7,20 @@
 // descriptor silently yields zeros on sm_100a), so every operand is laid out with its contraction index
 // contiguous.
 //
-//   grid = (frame chunks, component tiles of 128); the CTA's model tile (hi + lo) stays resident in shared memory
-//   and frame blocks stream through.  Two passes (the per-frame normaliser needs ALL component tiles):
+//   grid = (frame chunks, component tiles of 128); frame blocks stream through each CTA.  Two passes (the per-frame
+//   normaliser needs ALL component tiles):
 //
-//   pass LSE   (gmm_em_lse_kernel, 128-frame blocks): logits[frame, comp] -> thread == frame row ->
-//              per-tile (max, sum 2^x) partials to the workspace.
-//   pass STATS (gmm_em_stats_kernel, 64-frame blocks): TRANSPOSED logits[comp, frame] = B . F^T, so that
-//              thread == component row: gamma = 2^(L2 - lse2[frame]) (lse2 from the partials, broadcast from
-//              shared memory) is written 16 bytes at a time, conflict-free, straight into the K-major
-//              [component][frame] operand of GEMM 2:  stats[comp, :] += gamma . [x, x^2, 1, 1] over the frames,
-//              accumulated in TMEM across all blocks of a segment (lane == component), hi + lo passes of the
-//              frame-contiguous feature operand Xt.  At a segment end the 128 x (2D+2) accumulator is added
-//              to the double-precision N / F / S outputs.
+//   pass LSE   (gmm_em_lse_kernel, 128-frame blocks): logits[frame, comp]; the frame operand lives double-buffered in
+//              TENSOR MEMORY (tcgen05.st, thread == frame row), the model tile (hi + lo) in shared memory; thread ==
+//              frame row -> per-tile (max, sum 2^x) partials to the workspace.
+//   pass STATS (gmm_em_stats_kernel, 64-frame blocks): TRANSPOSED logits[comp, frame] = B . F^T with the model tile
+//              (hi + lo) resident in TENSOR MEMORY, so that thread == component row: gamma = 2^(L2 - lse2[frame]) (lse2
+//              from the partials) is written by tcgen05.st IN PLACE over the logits and is the TMEM-side operand of
+//              GEMM 2:  stats[comp, :] += gamma . [x, x^2, 1, 1] over the frames, accumulated in TMEM across all blocks
+//              of a segment, hi + lo passes of the frame-contiguous feature operand Xt.  At a segment end the
+//              128 x (2D+2) accumulator is added to the double-precision N / F / S outputs.
+//   Both passes keep two blocks in flight (double / triple-buffered operands): the 16 builder / epilogue warps split
+//   block k and post-process block k - 1 while the tensor core multiplies.
 // Blocks never straddle a segment, so one kernel pair serves UBM EM (one segment) and batched MAP enrolment
 // (one segment per speaker).
 #include <cstdlib>
@@ -148,452 +150,9 @@ __device__ __forceinline__ void store_block(float* dst, int n, int et, const flo
   }
 }
 
-// ================================================================================================ pass LSE
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int BM = BM1;
-  const int KD = a.KD, KC = KD >> 2;
-  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
-  float* sBhi = reinterpret_cast<float*>(smem);
-  float* sBlo = sBhi + BN * KD;
-  float* sAhi = sBlo + BN * KD;
-  float* sAlo = sAhi + BM * KD;
-  float* sX = sAlo + BM * KD;  // feature staging: BM x D floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + BM * MAX_KD / 2);
-  uint64_t* b_full = bars;
-  uint64_t* a_full = bars + 1;
-  uint64_t* l_full = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.y;
-  if (tid == 0) {
-    mbar_init(b_full, 1);
-    mbar_init(a_full, EPI);
-    mbar_init(l_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
-  const int64_t end = min(begin + a.chunk, a.total_frames);
-
-  if (warp == 0) {
-    if (begin < end && elect_one()) {
-      mbar_arrive_expect_tx(b_full, 2u * tile_bytes);
-      bulk_g2s(sBhi, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_full);
-      bulk_g2s(sBlo, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_full);
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr uint32_t lbo = BM * 16u, sbo = 128u;
-      constexpr uint32_t kstep = (2u * lbo) >> 4;
-      const uint64_t ahi = make_desc(smem_u32(sAhi), lbo, sbo), alo = make_desc(smem_u32(sAlo), lbo, sbo);
-      const uint64_t bhi = make_desc(smem_u32(sBhi), lbo, sbo), blo = make_desc(smem_u32(sBlo), lbo, sbo);
-      const int ksteps = KD >> 3;
-      const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
-      mbar_wait(b_full, 0);
-      uint32_t i = 0;
-      bool more = true;
-      while (more) {
-        const int nt = w.nt();
-        mbar_wait(a_full, i & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, ahi + (uint64_t)(k * kstep), bhi + (uint64_t)(k * kstep), idesc, k > 0);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, alo + (uint64_t)(k * kstep), bhi + (uint64_t)(k * kstep), idesc, 1u);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, ahi + (uint64_t)(k * kstep), blo + (uint64_t)(k * kstep), idesc, 1u);
-          tc_commit(l_full);
-        }
-        __syncwarp();
-        bool flush;
-        more = w.next(nt, flush);
-        ++i;
-      }
-    }
-  } else {
-    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == frame row
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int et = tid - 64;                   // 0..255
-    const int chalf = (warp - 2) >> 2;         // epilogue (first 8 warps): which 64 of the tile's 128 component columns
-    const bool epi_warp = chalf < 2;
-    const int brow = et & (BM - 1), bpart = et >> 7;  // row built by this thread, and which quarter of its K chunks
-    const int D = a.D;
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
-      float pf[R];
-      prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
-      uint32_t i = 0;
-      bool more = true;
-      while (more) {
-        const int nt = w.nt();
-        const int64_t t0 = w.t0;
-        store_block<R>(sX, nt * D, et, pf);
-        named_bar_sync(1, EPI);
-        {
-          Walk<BM> wn = w;
-          bool fl;
-          if (wn.next(nt, fl)) prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
-        }
-        {
-          const bool blive = brow < nt;
-          const float* xr = sX + brow * D;
-          float4* dhi = reinterpret_cast<float4*>(sAhi) + brow;
-          float4* dlo = reinterpret_cast<float4*>(sAlo) + brow;
-          for (int jc = bpart; jc < KC; jc += 4) {
-            float h[4], l[4];
-            chunk_split(xr, jc, D, blive, h, l);
-            dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
-            dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
-          }
-        }
-        named_bar_sync(1, EPI);  // staged rows consumed before the next block overwrites them
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(a_full);
-        mbar_wait(l_full, i & 1u);  // every builder waits: the MMAs of this block are done with the operands
-        tc_fence_after();
-        if (epi_warp) {
-        const uint32_t taddr = tmem_base + lane_addr + chalf * 64;
-        float m_run = -3.0e38f, s_run = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tc_ld32_issue(taddr + c * 32, r);
-          tc_ld_wait(r);
-          float cmax = __uint_as_float(r[0]);
-#pragma unroll
-          for (int e = 1; e < 32; ++e) cmax = fmaxf(cmax, __uint_as_float(r[e]));
-          const float m_new = fmaxf(m_run, cmax);
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            acc0 += ex2(__uint_as_float(r[e]) - m_new);
-            acc1 += ex2(__uint_as_float(r[e + 1]) - m_new);
-          }
-          s_run = fmaf(s_run, ex2(m_run - m_new), acc0 + acc1);
-          m_run = m_new;
-        }
-        if (row < nt) a.partial[(size_t)(2 * tile + chalf) * a.total_frames + t0 + row] = make_float2(m_run, s_run);
-        tc_fence_before();
-        }
-        bool flush;
-        more = w.next(nt, flush);
-        ++i;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
-}
-
 // ================================================================================================ pass STATS
-struct StatsCarve {
-  int kd, n2, xrows;
-  size_t o_bhi, o_blo, o_fhi, o_flo, o_xhi, o_xlo, o_g, o_lse, o_bar, bytes;
-};
-__host__ __device__ inline StatsCarve stats_carve(int KD) {
-  StatsCarve c;
-  c.kd = KD;
-  c.n2 = (KD + 15) & ~15;
-  c.xrows = c.n2 + 1;  // odd row count: the 16 K-chunks of the frame-contiguous operand start in different banks
-  size_t o = 0;
-  c.o_bhi = o; o += (size_t)BN * KD * 4;
-  c.o_blo = o; o += (size_t)BN * KD * 4;
-  c.o_fhi = o; o += (size_t)BM2 * KD * 4;
-  c.o_flo = o; o += (size_t)BM2 * KD * 4;
-  c.o_xhi = o; o += (size_t)(BM2 / 4) * c.xrows * 16;
-  c.o_xlo = o; o += (size_t)(BM2 / 4) * c.xrows * 16;
-  c.o_g = o; o += (size_t)BN * BM2 * 4;  // gamma [BM2/4][BN][4]; doubles as the feature staging buffer
-  c.o_lse = o; o += BM2 * 4;
-  c.o_bar = o; o += 64;
-  c.bytes = o;
-  return c;
-}
-
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int BM = BM2;
-  const int KD = a.KD, KC = KD >> 2, D = a.D;
-  const StatsCarve cv = stats_carve(KD);
-  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
-  float* sBhi = reinterpret_cast<float*>(smem + cv.o_bhi);
-  float* sBlo = reinterpret_cast<float*>(smem + cv.o_blo);
-  float* sFhi = reinterpret_cast<float*>(smem + cv.o_fhi);  // [KC][BM][4]: frames as rows (N operand of GEMM 1)
-  float* sFlo = reinterpret_cast<float*>(smem + cv.o_flo);
-  float* sXhi = reinterpret_cast<float*>(smem + cv.o_xhi);  // [BM/4][xrows][4]: features as rows, frames contiguous
-  float* sXlo = reinterpret_cast<float*>(smem + cv.o_xlo);
-  float* sG = reinterpret_cast<float*>(smem + cv.o_g);
-  float* sLse = reinterpret_cast<float*>(smem + cv.o_lse);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.o_bar);
-  uint64_t* b_full = bars;
-  uint64_t* a_full = bars + 1;
-  uint64_t* l_full = bars + 2;
-  uint64_t* g_full = bars + 3;
-  uint64_t* a_free = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.y;
-  if (tid == 0) {
-    mbar_init(b_full, 1);
-    mbar_init(a_full, EPI);
-    mbar_init(l_full, 1);
-    mbar_init(g_full, EPI);
-    mbar_init(a_free, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
-  const int64_t end = min(begin + a.chunk, a.total_frames);
-
-  if (warp == 0) {
-    if (begin < end && elect_one()) {
-      mbar_arrive_expect_tx(b_full, 2u * tile_bytes);
-      bulk_g2s(sBhi, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_full);
-      bulk_g2s(sBlo, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_full);
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      // GEMM 1 (transposed logits): A = model tile (M = 128 components), B = frame block (N = 64 frames), K = features
-      constexpr uint32_t lbo_b = BN * 16u, lbo_f = BM * 16u, sbo = 128u;
-      constexpr uint32_t ks_b = (2u * lbo_b) >> 4, ks_f = (2u * lbo_f) >> 4;
-      const uint64_t bhi = make_desc(smem_u32(sBhi), lbo_b, sbo), blo = make_desc(smem_u32(sBlo), lbo_b, sbo);
-      const uint64_t fhi = make_desc(smem_u32(sFhi), lbo_f, sbo), flo = make_desc(smem_u32(sFlo), lbo_f, sbo);
-      // GEMM 2: A = gamma (M = 128 components, K = frames), B = Xt (N = n2 feature rows, K = frames)
-      const uint32_t lbo_x = (uint32_t)cv.xrows * 16u;
-      const uint32_t ks_g = (2u * lbo_b) >> 4, ks_x = (2u * lbo_x) >> 4;
-      const uint64_t gd = make_desc(smem_u32(sG), lbo_b, sbo);
-      const uint64_t xhi = make_desc(smem_u32(sXhi), lbo_x, sbo), xlo = make_desc(smem_u32(sXlo), lbo_x, sbo);
-      const int ksteps = KD >> 3;
-      const uint32_t idesc1 = make_idesc_tf32(BN, BM, 0, 0);
-      const uint32_t idesc2 = make_idesc_tf32(BN, cv.n2, 0, 0);
-      mbar_wait(b_full, 0);
-      uint32_t i = 0;
-      bool first_in_seg = true, more = true;
-      while (more) {
-        const int nt = w.nt();
-        mbar_wait(a_full, i & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, bhi + (uint64_t)(k * ks_b), fhi + (uint64_t)(k * ks_f), idesc1, k > 0);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, bhi + (uint64_t)(k * ks_b), flo + (uint64_t)(k * ks_f), idesc1, 1u);
-          for (int k = 0; k < ksteps; ++k) tc_mma_tf32(tmem_base, blo + (uint64_t)(k * ks_b), fhi + (uint64_t)(k * ks_f), idesc1, 1u);
-          tc_commit(l_full);
-        }
-        __syncwarp();
-        mbar_wait(g_full, i & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          for (int k = 0; k < BM / 8; ++k)
-            tc_mma_tf32(tmem_base + STAT_COL, gd + (uint64_t)(k * ks_g), xhi + (uint64_t)(k * ks_x), idesc2,
-                        (first_in_seg && k == 0) ? 0u : 1u);
-          for (int k = 0; k < BM / 8; ++k)
-            tc_mma_tf32(tmem_base + STAT_COL, gd + (uint64_t)(k * ks_g), xlo + (uint64_t)(k * ks_x), idesc2, 1u);
-          tc_commit(a_free);
-        }
-        __syncwarp();
-        bool flush;
-        more = w.next(nt, flush);
-        first_in_seg = flush;
-        ++i;
-      }
-    }
-  } else {
-    // ===================== operand builder (thread == frame) and epilogue (thread == component) =====================
-    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == component row within the tile
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int et = tid - 64;                   // 0..255
-    const int cq = (warp - 2) >> 2;            // which 16 of the block's 64 frame columns this warp turns into gamma
-    const int fr = et & (BM - 1), part = et >> 6;  // frame row this thread builds, and which eighth of its K chunks
-    const bool norm_thread = part == 7;        // these 64 threads also own the per-frame normaliser
-    const float LN2 = 0.69314718055994530942f;
-    const int n_part = 2 * a.n_tiles;
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
-      constexpr int PT = 8;                                        // half-tile partials kept in registers
-      float pf[R];
-      float2 pp[PT];
-      auto prefetch_partials = [&](int64_t t0n, int ntn) {
-        if (norm_thread && fr < ntn) {
-#pragma unroll
-          for (int y = 0; y < PT; ++y)
-            if (y < n_part) pp[y] = a.partial[(size_t)y * a.total_frames + t0n + fr];
-        }
-      };
-      prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
-      prefetch_partials(w.t0, w.nt());
-      uint32_t i = 0;
-      bool more = true;
-      float ll_acc = 0.f;
-      while (more) {
-        const int nt = w.nt();
-        const int64_t t0 = w.t0;
-        const int seg_id = w.cur;
-        mbar_wait(a_free, (i & 1u) ^ 1u);  // GEMM 2 of the previous block is done with gamma / Xt / F
-        store_block<R>(sG, nt * D, et, pf);
-        // per-frame normaliser from the half-tile partials of pass LSE (log2 domain), from the prefetched registers
-        if (norm_thread) {
-          float lse2 = 3.0e38f;  // dead frames: gamma = 2^(x - huge) = 0
-          if (fr < nt) {
-            float m = -3.0e38f;
-#pragma unroll
-            for (int y = 0; y < PT; ++y)
-              if (y < n_part) m = fmaxf(m, pp[y].x);
-            for (int y = PT; y < n_part; ++y) m = fmaxf(m, a.partial[(size_t)y * a.total_frames + t0 + fr].x);
-            float ssum = 0.f;
-#pragma unroll
-            for (int y = 0; y < PT; ++y)
-              if (y < n_part) ssum += pp[y].y * ex2(pp[y].x - m);
-            for (int y = PT; y < n_part; ++y) {
-              const float2 p = a.partial[(size_t)y * a.total_frames + t0 + fr];
-              ssum += p.y * ex2(p.x - m);
-            }
-            lse2 = m + lg2(ssum);
-            if (tile == 0) {
-              const float lse = lse2 * LN2;
-              a.frame_lse[t0 + fr] = lse;
-              ll_acc += lse;
-            }
-          }
-          sLse[fr] = lse2;
-        }
-        named_bar_sync(1, EPI);
-        {
-          // frame-row operand F (K-major, frames as rows) and frame-contiguous operand Xt (features as rows)
-          const bool live = fr < nt;
-          const float* xr = sG + fr * D;
-          float4* dhi = reinterpret_cast<float4*>(sFhi) + fr;
-          float4* dlo = reinterpret_cast<float4*>(sFlo) + fr;
-          float* xth = sXhi + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
-          float* xtl = sXlo + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
-          for (int jc = part; jc < KC; jc += 8) {
-            float h[4], l[4];
-            chunk_split(xr, jc, D, live, h, l);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              xth[(4 * jc + e) * 4] = h[e];
-              xtl[(4 * jc + e) * 4] = l[e];
-            }
-            dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
-            dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
-          }
-          // rows KD..n2-1 of Xt feed accumulator columns nobody reads, but must be finite
-          if (part == 0)
-            for (int j = KD; j < cv.n2; ++j) { xth[j * 4] = 0.f; xtl[j * 4] = 0.f; }
-        }
-        named_bar_sync(1, EPI);  // staging consumed, sLse visible
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(a_full);
-        {
-          Walk<BM> wn = w;
-          bool fl;
-          if (wn.next(nt, fl)) {
-            prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
-            prefetch_partials(wn.t0, wn.nt());
-          }
-        }
-        // ---- transposed logits: lane == component, columns == frames (this warp: 32 of them)
-        mbar_wait(l_full, i & 1u);
-        tc_fence_after();
-        {
-          uint32_t r[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-              : "r"(tmem_base + lane_addr + cq * 16)
-              : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float4* g4 = reinterpret_cast<float4*>(sG) + row;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 ls = *reinterpret_cast<const float4*>(sLse + 16 * cq + 4 * q);
-            const float g0 = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
-            const float g1 = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
-            const float g2 = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
-            const float g3 = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
-            g4[(4 * cq + q) * BN] = make_float4(g0, g1, g2, g3);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(g_full);
-        bool flush;
-        more = w.next(nt, flush);
-        if (flush) {
-          // ---- segment (or chunk) end: drain the statistics accumulator; lane == component, the two warps of a
-          // lane quadrant take alternate 16-column groups
-          mbar_wait(a_free, i & 1u);  // GEMM 2 of this block has completed
-          tc_fence_after();
-          const int comp = tile * BN + row;
-          const uint32_t saddr = tmem_base + lane_addr + STAT_COL;
-#pragma unroll 1
-          for (int c0 = 16 * cq; c0 < KD; c0 += 64) {
-            uint32_t r[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(saddr + c0)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (comp < a.K) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int j = c0 + e;
-                const double v = (double)__uint_as_float(r[e]);
-                if (j < D) atomicAdd(a.out_f + ((int64_t)seg_id * a.K + comp) * D + j, v);
-                else if (j < 2 * D) atomicAdd(a.out_s + ((int64_t)seg_id * a.K + comp) * D + (j - D), v);
-                else if (j == 2 * D) atomicAdd(a.out_n + (int64_t)seg_id * a.K + comp, v);
-              }
-            }
-          }
-          if (tile == 0) {
-            // ll_acc lives in the norm_thread warps; the others contribute zero
-            const float tot = warp_sum(ll_acc);
-            if (lane == 0 && tot != 0.f) atomicAdd(a.out_loglik + seg_id, (double)tot);
-            ll_acc = 0.f;
-          }
-          tc_fence_before();
-        }
-        ++i;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-}
-
-
-// ================================================================================================ pass STATS, pipelined
-// Same arithmetic as gmm_em_stats_kernel with two frame blocks in flight, so that the tensor core works on one block
-// while the 16 builder / epilogue warps work on its neighbours:
+// Two frame blocks in flight, so that the tensor core works on one block while the 16 builder / epilogue warps work
+// on its neighbours:
 //   * the CTA's model tile (TF32 hi + lo) is copied ONCE into tensor memory (160 columns) and is the TMEM-side (A)
 //     operand of the logit GEMM (component == TMEM lane): 80 KB of shared memory become operand buffers;
 //   * gamma is written by tcgen05.st IN PLACE over the logits it came from and is the TMEM-side operand of the
@@ -658,7 +217,7 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats3_kernel(const Args a) {
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) {
   using namespace p3;
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int BM = BM2;
@@ -958,8 +517,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats3_kernel(const Args a)
 }
 
 
-// ================================================================================================ pass LSE, pipelined
-// Same arithmetic as gmm_em_lse_kernel.  The frame operand [x, x^2, 1, 1] (TF32 hi + lo) is written straight into
+// ================================================================================================ pass LSE
+// The frame operand [x, x^2, 1, 1] (TF32 hi + lo) is written straight into
 // tensor memory (tcgen05.st, thread == frame row == TMEM lane) and double-buffered there (2 x 160 columns), the model
 // tile stays in shared memory as the N-side operand, one 128-column accumulator.  Thread program per block k: build
 // A[k & 1] (needs GEMM(k - 2) done), then the epilogue of block k - 1 (tcgen05.ld, release the accumulator at once,
@@ -970,7 +529,7 @@ constexpr uint32_t COL_A = 0;      // + 160 * (k & 1): hi at +0, lo at +80
 constexpr uint32_t COL_ACC = 320;  // 128 columns
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse2_kernel(const Args a) {
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   using namespace l2;
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int BM = BM1;
@@ -1179,38 +738,14 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   a.out_f = out_f;
   a.out_s = out_s;
   a.out_loglik = out_loglik;
-  const size_t smem1 = (size_t)(2 * BN * L.KD + 2 * BM1 * L.KD + BM1 * MAX_KD / 2) * sizeof(float) + 64;
-  const size_t smem2 = stats_carve(L.KD).bytes;
+  const size_t smem_lse = (size_t)(2 * BN * L.KD + BM1 * MAX_KD / 2) * sizeof(float) + 128;
+  const size_t smem_stats = p3::carve(L.KD).bytes;
   dim3 grid((unsigned)gx, (unsigned)a.n_tiles);
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  static int lse_version = -1;  // SSP_EM_LSE=1 selects the single-buffered kernel (A/B reference)
-  if (lse_version < 0) {
-    const char* e = getenv("SSP_EM_LSE");
-    lse_version = (e && atoi(e) == 1) ? 1 : 2;
-  }
-  if (lse_version == 2) {
-    const size_t smem1b = (size_t)(2 * BN * L.KD + BM1 * MAX_KD / 2) * sizeof(float) + 128;
-    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1b));
-    gmm_em_lse2_kernel<<<grid, THREADS, smem1b, st>>>(a);
-    SSP_LAUNCH_CHECK("gmm_em_lse2_kernel");
-  } else {
-    gmm_em_lse_kernel<<<grid, THREADS, smem1, st>>>(a);
-    SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
-  }
-  static int version = -1;  // SSP_EM_STATS=1 selects the single-buffered kernel (A/B reference)
-  if (version < 0) {
-    const char* e = getenv("SSP_EM_STATS");
-    version = (e && atoi(e) == 1) ? 1 : 3;
-  }
-  if (version == 3) {
-    const size_t smem3 = p3::carve(L.KD).bytes;
-    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    gmm_em_stats3_kernel<<<grid, THREADS, smem3, st>>>(a);
-    SSP_LAUNCH_CHECK("gmm_em_stats3_kernel");
-    return SSP_OK;
-  }
-  gmm_em_stats_kernel<<<grid, THREADS, smem2, st>>>(a);
+  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lse));
+  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats));
+  gmm_em_lse_kernel<<<grid, THREADS, smem_lse, st>>>(a);
+  SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
+  gmm_em_stats_kernel<<<grid, THREADS, smem_stats, st>>>(a);
   SSP_LAUNCH_CHECK("gmm_em_stats_kernel");
   return SSP_OK;
 }
