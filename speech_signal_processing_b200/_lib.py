@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libssp_b200.so")
+LIB_PATH = os.environ.get("SSP_B200_LIB") or os.path.join(PKG, "libssp_b200.so")  # override: A/B a second build
 
 PREC_FP32 = 0
 PREC_TF32 = 1
