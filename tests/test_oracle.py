@@ -161,3 +161,50 @@ def test_vad_matches_reference(golden):
         assert np.array_equal(ov.detect(z, p), g[f"det{i}"])
         assert np.array_equal(ov.detect(z, p, zcr_gate=25, ampl=1.0, amph=8), g[f"det_b{i}"])
         assert np.array_equal(ov.frequency(e), g[f"freq{i}"])
+
+
+def test_plp_building_blocks_known_answers():
+    """sidekit's plp is unpinned (package absent); its building blocks are checked against independent computations:
+    Levinson-Durbin vs a Toeplitz solve, the LPC -> cepstrum recursion vs the FFT cepstrum of the all-pole spectrum,
+    the RASTA filter vs scipy.signal.lfilter from rest, the Bark filterbank's shape facts, and the output shape the
+    reference's report quotes for 1 s of audio (98 frames)."""
+    from scipy.linalg import solve_toeplitz
+    from scipy.signal import lfilter
+
+    from speech_signal_processing_b200 import synth
+
+    rs = np.random.RandomState(0)
+    # Levinson: a[1:] solves R a = -r[1:], error = r0 + sum a_k r_k
+    x = rs.standard_normal((5, 400))
+    r = np.array([[np.dot(row[: 400 - k], row[k:]) for k in range(13)] for row in x])
+    a, e = ofe.levinson(r, 12)
+    for i in range(5):
+        sol = solve_toeplitz(r[i, :12], -r[i, 1:13])
+        np.testing.assert_allclose(a[i, 1:], sol, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(e[i], r[i, 0] + np.dot(a[i, 1:], r[i, 1:13]), rtol=1e-10)
+    # LPC -> cepstrum: c_n of log(1 / A(z)) from the recursion == inverse FFT of the log all-pole spectrum
+    poles = 0.6 * np.exp(1j * np.array([0.4, 1.3, 2.2]))
+    poly = np.real(np.poly(np.concatenate([poles, poles.conj()])))          # A(z) = 1 + a1 z^-1 + ...
+    n_fft = 4096
+    log_h = -np.log(np.fft.fft(poly, n_fft))
+    cep_fft = np.real(np.fft.ifft(log_h))[:7]
+    cep = np.zeros(7)
+    for n in range(1, 7):
+        s = sum((n - m) * poly[m] * cep[n - m] for m in range(1, n))
+        cep[n] = -(poly[n] + s / n)
+    np.testing.assert_allclose(cep[1:], cep_fft[1:], atol=1e-9)
+    # RASTA: after the four warm-up frames the output is the IIR filter continued from the FIR state
+    z = rs.standard_normal((50, 3))
+    y = ofe.rasta_filt(z)
+    assert np.all(y[:4] == 0.0)
+    numer, denom = ofe.rasta_filter_coefficients()
+    np.testing.assert_allclose(numer, [0.2, 0.1, 0.0, -0.1, -0.2])
+    full_fir = lfilter(numer, [1.0], z, axis=0)
+    np.testing.assert_allclose(y[4], full_fir[4] , atol=1e-12)               # first IIR output has no feedback term yet
+    np.testing.assert_allclose(y[5], full_fir[5] + 0.94 * y[4], atol=1e-12)
+    # Bark filterbank at 16 kHz / 512: 21 bands, unit peaks, centre frequencies increasing
+    w = ofe.fft2barkmx(512, 16000)
+    assert w.shape == (21, 257) and np.isclose(w.max(axis=1)[1:-1], 1.0, atol=0.2).all()
+    assert (np.diff(w.argmax(axis=1)) > 0).all()
+    out = ofe.sidekit_plp(synth.synth_utterance(1, 2, 16000))
+    assert out[0].shape == (98, 13) and out[1].shape == (98,) and np.isfinite(out[0]).all()
