@@ -46,7 +46,8 @@ void ssp_reset_launch_count(void);
 typedef struct ssp_frontend_cfg {
   int32_t frame_len;     /* samples per frame (400)                                          */
   int32_t frame_shift;   /* hop (160)                                                        */
-  int32_t nfft;          /* power of two in [64, 4096], >= frame_len                          */
+  int32_t nfft;          /* [64, 4096], >= frame_len; a power of two runs an FFT, any other
+                            length (utils/processing.py:129: nfft = frame length) a direct DFT */
   int32_t n_filt;        /* mel filters (24 sidekit, 26 psf, 40 processing.py)               */
   int32_t n_ceps;        /* cepstra kept (13)                                                */
   int32_t framing;       /* 0: floor((N-len)/shift)+1, no padding (sidekit)

@@ -41,15 +41,26 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
   const int T = (int)(a.frame_offsets[u + 1] - f_begin);
   if (T <= 0) return;
 
-  for (int q = threadIdx.x; q < NH; q += blockDim.x) {
-    float s, c;
-    sincospif(-2.0f * (float)q / (float)NH, &s, &c);
-    tw_fft[q] = make_float2(c, s);
-  }
-  for (int k = threadIdx.x; k <= NH; k += blockDim.x) {
-    float s, c;
-    sincospif(-2.0f * (float)k / (float)nfft, &s, &c);
-    tw_real[k] = make_float2(c, s);
+  // FFT lengths that are not a power of two (utils/processing.py:129 uses the frame length, e.g. 400) take a direct
+  // DFT against one table e^{-2 pi i q / nfft}, q < nfft, laid over the two FFT tables (2 nfft <= 4 NH + 4 floats).
+  const bool pow2 = (nfft & (nfft - 1)) == 0;
+  if (pow2) {
+    for (int q = threadIdx.x; q < NH; q += blockDim.x) {
+      float s, c;
+      sincospif(-2.0f * (float)q / (float)NH, &s, &c);
+      tw_fft[q] = make_float2(c, s);
+    }
+    for (int k = threadIdx.x; k <= NH; k += blockDim.x) {
+      float s, c;
+      sincospif(-2.0f * (float)k / (float)nfft, &s, &c);
+      tw_real[k] = make_float2(c, s);
+    }
+  } else {
+    for (int q = threadIdx.x; q < nfft; q += blockDim.x) {
+      double s, c;
+      sincospi(-2.0 * (double)q / (double)nfft, &s, &c);
+      tw_fft[q] = make_float2((float)c, (float)s);
+    }
   }
   for (int i = threadIdx.x; i < FL; i += blockDim.x) win[i] = a.window[i];
   __syncthreads();
@@ -90,7 +101,7 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
     // ---- Stockham autosort FFT of NH complex points (radix 4, one radix-2 stage if log2(NH) is odd)
     float2* src = bufA;
     float2* dst = bufB;
-    for (int Ns = 1; Ns < NH;) {
+    for (int Ns = 1; pow2 && Ns < NH;) {
       const int rem = NH / Ns;
       if ((rem & 3) == 0) {
         const int q4 = NH >> 2;
@@ -133,12 +144,42 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
     // src now holds Z = FFT_NH(z).  Real-input split: X[k] = Xe[k] + e^{-2 pi i k/nfft} Xo[k].
     float etot = 0.f;
     for (int k = lane; k <= NH; k += 32) {
-      const float2 zk = src[k & (NH - 1)];
-      const float2 zm = src[(NH - k) & (NH - 1)];
-      const float2 xe = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-      const float2 xo = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-      const float2 x = cmul(tw_real[k], xo);
-      const float re = xe.x + x.x, im = xe.y + x.y;
+      float re, im;
+      if (pow2) {
+        const float2 zk = src[k & (NH - 1)];
+        const float2 zm = src[(NH - k) & (NH - 1)];
+        const float2 xe = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 xo = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        const float2 x = cmul(tw_real[k], xo);
+        re = xe.x + x.x;
+        im = xe.y + x.y;
+      } else {
+        // X[k] = sum_n z[n] e^{-2 pi i k n / nfft}; the table index k n mod nfft is carried exactly in integers and
+        // two partial sums per component keep the FP32 accumulation error at the FFT path's level.
+        float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
+        int idx = 0;
+        int n = 0;
+        for (; n + 1 < FL; n += 2) {
+          const float2 w0 = tw_fft[idx];
+          idx += k;
+          if (idx >= nfft) idx -= nfft;
+          const float2 w1 = tw_fft[idx];
+          idx += k;
+          if (idx >= nfft) idx -= nfft;
+          const float v0 = zr[n], v1 = zr[n + 1];
+          re0 = fmaf(v0, w0.x, re0);
+          im0 = fmaf(v0, w0.y, im0);
+          re1 = fmaf(v1, w1.x, re1);
+          im1 = fmaf(v1, w1.y, im1);
+        }
+        if (n < FL) {
+          const float2 w0 = tw_fft[idx];
+          re0 = fmaf(zr[n], w0.x, re0);
+          im0 = fmaf(zr[n], w0.y, im0);
+        }
+        re = re0 + re1;
+        im = im0 + im1;
+      }
       float p = fmaf(re, re, im * im);
       if (cfg.spec_type == 1) p = sqrtf(p);
       p *= cfg.spec_scale;
@@ -235,7 +276,7 @@ static size_t frontend_smem(const ssp_frontend_cfg& c, int max_frames) {
 
 static bool frontend_cfg_ok(const ssp_frontend_cfg* c) {
   if (!c) return false;
-  if (c->nfft < 64 || c->nfft > 4096 || (c->nfft & (c->nfft - 1))) return false;
+  if (c->nfft < 64 || c->nfft > 4096) return false;  // powers of two: FFT; anything else: direct DFT
   if (c->frame_len < 1 || c->frame_len > c->nfft || c->frame_shift < 1) return false;
   if (c->n_filt < 1 || c->n_filt > 256 || c->n_ceps < 1 || c->n_ceps > c->n_filt) return false;
   if (c->delta_order < 0 || c->delta_order > 2 || (c->delta_order > 0 && c->delta_n < 1)) return false;

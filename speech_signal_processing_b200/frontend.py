@@ -73,7 +73,8 @@ def processing_filterbank(fs, nfft):
     two_sided = _area_triangles(edges, nfft, fs, nfft, drop_last_falling=False)
     half = nfft // 2
     fb = two_sided[:, : half + 1].copy()
-    fb[:, 1:half] += two_sided[:, :half:-1]  # bin nfft-k folds onto k
+    mirror = two_sided[:, :half:-1]  # bins nfft-1 ... half+1 fold onto 1 ... (half-1 for even nfft, half for odd)
+    fb[:, 1 : 1 + mirror.shape[1]] += mirror
     return fb
 
 
@@ -191,8 +192,8 @@ def processing_recipe(fs=8000, frameSize=512, step=256) -> Recipe:
     """utils/processing.py:110-144 ``MFCC``: Hamming, no pre-emphasis (line 34 is commented out),
     magnitude/n spectrum, 40 talkbox triangles, log10(. + 1e-8), 13 cepstra incl. c0."""
     n = int(frameSize)
-    if n & (n - 1) or not 64 <= n <= 4096:
-        raise NotImplementedError("frameSize (= FFT length at utils/processing.py:129) must be a power of two in [64, 4096]")
+    if not 64 <= n <= 4096:
+        raise NotImplementedError("frameSize (= FFT length at utils/processing.py:129) must lie in [64, 4096]")
     k = np.arange(n)
     ham = 0.54 - 0.46 * np.cos(2.0 * np.pi * k / (n - 1))
     return Recipe("processing", n, int(step), n, ham, processing_filterbank(fs, n), dct_rows(13, 40), framing=2,

@@ -18,14 +18,21 @@ def assert_ceps_close(got, want, tol=1e-4):
 def test_processing_MFCC_matches_reference_outputs(golden):
     """utils.processing.MFCC run unmodified (fixtures) vs the kernel with the 'processing' tables."""
     g = golden("processing_mfcc.npz")
-    for tag in "abd":
+    for tag in "abcd":  # c: frameSize 400 = FFT length 400 (utils/processing.py:129) -> the direct-DFT path
         fs, fsz, step = (int(v) for v in g[f"{tag}_cfg"])
         got = ssp.MFCC(g[f"{tag}_sig"], fs, fsz, step)
         assert got.dtype == np.float64
         assert_ceps_close(got, g[f"{tag}_mfcc"])
-    fs, fsz, step = (int(v) for v in g["c_cfg"])
-    with pytest.raises(NotImplementedError):
-        ssp.MFCC(g["c_sig"], fs, fsz, step)  # frameSize 400: FFT length must be a power of two
+
+
+@pytest.mark.parametrize("fs,frame_size,step", [(8000, 200, 80), (16000, 400, 160), (8000, 255, 100), (16000, 1000, 400)])
+def test_processing_MFCC_any_frame_size_matches_oracle(fs, frame_size, step):
+    """Frame sizes that are not a power of two, odd ones included, against the oracle restatement (itself pinned by
+    the reference outputs of cases a-d)."""
+    sig = synth.synth_utterance(4, frame_size % 89, 2 * fs + 123, fs)
+    got = ssp.MFCC(sig, fs, frame_size, step)
+    want = ofe.processing_mfcc(sig, fs, frame_size, step)
+    assert_ceps_close(got, want)
 
 
 @pytest.mark.parametrize("n_samples", [16000, 48000, 400, 12345])

@@ -35,7 +35,30 @@ def test_recipe_tables_match_oracle(golden):
         x = np.abs(np.fft.fft(np.random.RandomState(0).standard_normal(512)))
         np.testing.assert_allclose(folded @ x[:257], two_sided @ x, rtol=1e-12)
     with pytest.raises(NotImplementedError):
-        ssp.processing_recipe(16000, 400, 160)
+        ssp.processing_recipe(16000, 5000, 160)
+
+
+@pytest.mark.parametrize("fs,frame_size,step,tag", [(16000, 400, 160, "c"), (8000, 512, 256, "a"), (8000, 255, 100, None)])
+def test_processing_tables_reproduce_reference_for_any_frame_size(golden, fs, frame_size, step, tag):
+    """What the kernel computes from the 'processing' tables (window -> one-sided magnitude / nfft -> folded
+    filterbank -> log10(. + 1e-8) -> DCT rows), emulated in numpy, against the unmodified utils/processing.py
+    output; frame sizes that are not a power of two (nfft = frame length, utils/processing.py:129) and odd ones
+    (bin nfft/2 has a mirror image then) included."""
+    r = ssp.processing_recipe(fs, frame_size, step)
+    assert r.nfft == frame_size and r.fbank.shape == (40, frame_size // 2 + 1)
+    if tag is None:
+        sig = synth.synth_utterance(2, 5, 3000, fs)
+        want = ofe.processing_mfcc(sig, fs, frame_size, step)
+    else:
+        g = golden("processing_mfcc.npz")
+        sig, want = g[f"{tag}_sig"], g[f"{tag}_mfcc"]
+    n_frames = -(-len(sig) // step)
+    padded = np.zeros((n_frames - 1) * step + frame_size)
+    padded[: len(sig)] = sig
+    frames = np.stack([padded[t * step : t * step + frame_size] for t in range(n_frames)]) * r.window
+    spec = np.abs(np.fft.rfft(frames, r.nfft, axis=1)) * r.spec_scale
+    got = np.log10(spec @ r.fbank.T + r.log_add) @ r.dct.T
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
 
 
 def test_dct_rows_and_lifter():
