@@ -54,8 +54,13 @@ def test_host_only_entry_points(lib):
     assert lib.ssp_frontend_num_frames(C.byref(c2), 48000) == 300
     assert lib.ssp_frontend_num_frames(C.byref(c2), 0) == 0
     assert lib.ssp_frontend_max_frames(C.byref(c0)) > 2998  # a 30 s utterance fits the fused kernel
+    dft = cfg(0)
+    dft.nfft = 400  # not a power of two: accepted, direct-DFT path
+    assert lib.ssp_frontend_num_frames(C.byref(dft), 48000) == 298
     bad = cfg(0)
-    bad.nfft = 400
+    bad.nfft = 320  # shorter than the frame
+    assert lib.ssp_frontend_num_frames(C.byref(bad), 48000) == 0
+    bad.nfft = 8192
     assert lib.ssp_frontend_num_frames(C.byref(bad), 48000) == 0
     d = _lib.GmmDims(1001, 1024, 39)
     nbytes = lib.ssp_gmm_pack_bytes(C.byref(d))
