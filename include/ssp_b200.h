@@ -49,16 +49,21 @@ typedef struct ssp_frontend_cfg {
   int32_t nfft;          /* [64, 4096], >= frame_len; a power of two runs an FFT, any other
                             length (utils/processing.py:129: nfft = frame length) a direct DFT */
   int32_t n_filt;        /* mel filters (24 sidekit, 26 psf, 40 processing.py)               */
-  int32_t n_ceps;        /* cepstra kept (13)                                                */
+  int32_t n_ceps;        /* cepstra kept (13); n_ceps*(1+delta_order) <= 64, or up to n_filt
+                            (<= 256) with delta_order 0 and cmvn 0                            */
   int32_t framing;       /* 0: floor((N-len)/shift)+1, no padding (sidekit)
                             1: 1+ceil((N-len)/shift), zero-padded tail (psf)
-                            2: ceil(N/shift), zero-padded tail (utils/processing.py:27)       */
+                            2: ceil(N/shift), zero-padded tail (utils/processing.py:27)
+                            3: 1+floor(N/shift), frame f centred on sample f*shift, edges
+                               mirrored (librosa center=True, pad_mode='reflect'); preemph_mode 0
+                            4: as 3 with zero padding (pad_mode='constant')                    */
   int32_t preemph_mode;  /* 0 none; 1 per frame, y[0]=x[0]-p*x[0] (sidekit);
                             2 whole signal, y[0]=x[0] (psf)                                    */
   float preemph;         /* 0.97                                                             */
   int32_t spec_type;     /* 0 power re^2+im^2; 1 magnitude                                    */
   float spec_scale;      /* spectrum multiplied by this (1/nfft for psf and processing.py)   */
-  int32_t log_type;      /* 0 natural log; 1 log10; 2 none (PLP: raw critical-band energies)  */
+  int32_t log_type;      /* 0 natural log; 1 log10; 2 none (PLP: raw critical-band energies);
+                            3 dB: 10 log10(max(x, log_zero_floor)) (librosa power_to_db, amin)  */
   float log_add;         /* added before the log (1e-8 at utils/processing.py:105)           */
   float log_zero_floor;  /* if > 0: exact zeros are replaced by this before the log (psf eps) */
   int32_t energy_mode;   /* 0 none; 1 sidekit ln(sum y^2) of the pre-emphasised, un-windowed
@@ -108,6 +113,18 @@ int ssp_frontend_batch(const void* pcm, const int64_t* sample_offsets, int64_t n
 int ssp_plp_post(float* bands, const int64_t* frame_offsets, int64_t n_utts, int32_t n_bands, int32_t n_ceps,
                  const double* eql, const double* idft, const double* lift, int32_t rasta, float* out_ceps,
                  void* stream);
+
+/*
+ * Back half of librosa.feature.mfcc as MFCC_DTW.py:27-30 calls it (MFCC_lib): log-mel power in dB
+ * (ssp_frontend_batch with framing 3, log_type 3 and an identity "DCT") -> power_to_db's top_db clip against the maximum
+ * of the whole utterance -> DCT-II rows.
+ * mel_db        device float[total_frames * n_mels]
+ * dct           device float[n_ceps * n_mels]
+ * top_db        clip to (utterance max - top_db); negative: no clip (librosa top_db=None)
+ * out_ceps      device float[total_frames * n_ceps]
+ */
+int ssp_mel_db_post(const float* mel_db, const int64_t* frame_offsets, int64_t n_utts, int32_t n_mels, int32_t n_ceps,
+                    const float* dct, float top_db, float* out_ceps, void* stream);
 
 /* GMM_UBM.delta (GMM_UBM.py:53-69) on a (T, F) float32 device matrix. */
 int ssp_delta(const float* feat, int64_t n_frames, int32_t n_feat, int32_t delta_n, float* out,

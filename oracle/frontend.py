@@ -389,3 +389,70 @@ def sidekit_plp(sig, nwin=0.025, fs=16000, plp_order=13, shift=0.01, get_spec=Fa
         cep[:, n] = -(norm[:, n] + s / n)
     lift = np.concatenate([[1.0], np.arange(1, ncep, dtype=np.float64) ** 0.6])
     return [cep * lift[None, :], log_energy, None, None]
+
+
+# ----------------------------------------------------------------------------
+# librosa.feature.mfcc (MFCC_DTW.py:27-30 ``MFCC_lib``) -- PARITY UNPINNED
+# ----------------------------------------------------------------------------
+# librosa is absent from the container and un-pinned (requirements.txt).  Restated from its published algorithm with
+# the defaults the reference call relies on: ``librosa.feature.mfcc(y, sr=8000, n_mfcc=13)`` -> melspectrogram
+# (n_fft=2048, hop_length=512, periodic Hann, center=True with reflect padding, power 2, 128 Slaney mel bands with
+# area normalisation, fmin 0, fmax sr/2) -> power_to_db (ref 1, amin 1e-10, top_db 80 against the maximum of the
+# whole utterance) -> DCT-II ortho, first n_mfcc rows.  torchaudio's MFCC transform (same conventions, an independent
+# implementation) is the cross-check in tests/test_oracle.py.
+
+
+def slaney_hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3.0
+    min_log_hz, logstep = 1000.0, math.log(6.4) / 27.0
+    lin = f / f_sp
+    return np.where(f >= min_log_hz, min_log_hz / f_sp + np.log(np.maximum(f, min_log_hz) / min_log_hz) / logstep, lin)
+
+
+def slaney_mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3.0
+    min_log_hz, logstep = 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def librosa_mel_filters(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    """``librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney')`` -> (n_mels, n_fft//2+1)."""
+    fmax = sr / 2.0 if fmax is None else fmax
+    fftfreqs = np.arange(n_fft // 2 + 1) * (sr / float(n_fft))
+    mel_f = slaney_mel_to_hz(np.linspace(slaney_hz_to_mel(fmin), slaney_hz_to_mel(fmax), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, n_fft // 2 + 1))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.maximum(0.0, np.minimum(lower, upper))
+    w *= (2.0 / (mel_f[2 : n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return w
+
+
+def librosa_mfcc(y, sr=8000, n_mfcc=13, n_fft=2048, hop_length=512, n_mels=128, fmin=0.0, fmax=None, top_db=80.0,
+                 center=True, pad_mode="reflect", amin=1e-10):
+    """``librosa.feature.mfcc`` -> (n_mfcc, T) like librosa (MFCC_DTW.py:28 then takes ``.T.flatten()``)."""
+    y = np.asarray(y, dtype=np.float64)
+    if center:
+        y = np.pad(y, n_fft // 2, mode=pad_mode)
+    if len(y) < n_fft:
+        return np.zeros((n_mfcc, 0))
+    T = 1 + (len(y) - n_fft) // hop_length
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n_fft) / n_fft)  # scipy get_window('hann', fftbins=True)
+    frames = np.stack([y[t * hop_length : t * hop_length + n_fft] for t in range(T)]) * win
+    power = np.abs(np.fft.rfft(frames, n_fft, axis=1)) ** 2
+    mel = power @ librosa_mel_filters(sr, n_fft, n_mels, fmin, fmax).T
+    db = 10.0 * np.log10(np.maximum(amin, mel))  # ref = 1.0 -> the reference term is 10 log10(max(amin, 1)) = 0
+    if top_db is not None:
+        db = np.maximum(db, db.max() - top_db)
+    return (db @ dct2_ortho_matrix(n_mfcc, n_mels).T).T
+
+
+def mfcc_lib(raw_signal, n_mfcc=13):
+    """MFCC_DTW.py:27-30 ``MFCC_lib``: float32 cast, sr=8000, flattened frame-major."""
+    return librosa_mfcc(np.asarray(raw_signal).astype("float32"), sr=8000, n_mfcc=n_mfcc).T.flatten()

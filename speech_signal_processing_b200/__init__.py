@@ -7,11 +7,13 @@ first call that needs it and a missing library or device raises.
 """
 from . import synth  # noqa: F401  (host-side synthetic inputs)
 from . import vad  # noqa: F401  (reference VAD.py entry points)
-from .frontend import (FrontEnd, MFCC, PlpFrontEnd, Recipe, delta, extract_feature, mfcc, plp, plp_recipe,  # noqa: F401
-                       preprocessing, processing_recipe, psf_recipe, scale, sidekit_recipe)
+from .frontend import (FrontEnd, MFCC, MFCC_lib, MelDbFrontEnd, PlpFrontEnd, Recipe, delta, extract_feature,  # noqa: F401
+                       librosa_mfcc, librosa_recipe, mfcc, plp, plp_recipe, preprocessing, processing_recipe, psf_recipe,
+                       scale, sidekit_recipe)
 from .mixture import GaussianMixture, ModelSet, SharedModelSet, score_matrix  # noqa: F401
 from .ubm import GMM, identify, install, load_data, load_extract, main, map_adapt, map_enrol  # noqa: F401
 
-__all__ = ["FrontEnd", "Recipe", "sidekit_recipe", "psf_recipe", "processing_recipe", "mfcc", "plp", "plp_recipe", "PlpFrontEnd", "MFCC", "delta", "scale",
+__all__ = ["FrontEnd", "Recipe", "sidekit_recipe", "psf_recipe", "processing_recipe", "mfcc", "plp", "plp_recipe", "PlpFrontEnd", "MFCC", "MFCC_lib",
+           "librosa_mfcc", "librosa_recipe", "MelDbFrontEnd", "delta", "scale",
            "preprocessing", "extract_feature", "GaussianMixture", "ModelSet", "SharedModelSet", "score_matrix", "GMM", "identify",
            "map_adapt", "map_enrol", "install", "load_data", "load_extract", "main", "synth", "vad"]

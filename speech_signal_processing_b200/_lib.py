@@ -52,6 +52,7 @@ PROTOTYPES = {
     "ssp_frontend_max_frames": (_I64, [C.POINTER(FrontendCfg)]),
     "ssp_frontend_batch": (C.c_int, [_P, _P, _I64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "ssp_plp_post": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _P]),
+    "ssp_mel_db_post": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, C.c_float, _P, _P]),
     "ssp_delta": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "ssp_cmvn": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "ssp_vad_num_frames": (_I64, [C.POINTER(VadCfg), _I64]),

@@ -69,17 +69,30 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
   const int pmode = cfg.preemph_mode;
   const float LOG10_E = 0.43429448190325176f;
 
+  // framing 3 / 4 (librosa center=True, MFCC_DTW.py:27-30): frame f is centred on sample f * shift; positions outside
+  // the utterance are mirrored about the first / last sample (numpy 'reflect', any number of folds) or read as zero.
+  const bool centred = cfg.framing >= 3;
+  const int64_t refl_period = 2 * (n_samp - 1);
   for (int f = warp; f < T; f += nwarps) {
-    const int64_t s0 = (int64_t)f * cfg.frame_shift;
+    const int64_t s0 = (int64_t)f * cfg.frame_shift - (centred ? (FL >> 1) : 0);
     // ---- load, pre-emphasis, time-domain energy, window; packed as NH complex values
     float energy = 0.f;
     float* zr = reinterpret_cast<float*>(bufA);
     for (int i = lane; i < nfft; i += 32) {
       float v = 0.f;
       if (i < FL) {
-        const int64_t gi = s0 + i;
+        int64_t gi = s0 + i;
+        if (cfg.framing == 3 && (gi < 0 || gi >= n_samp)) {
+          if (refl_period == 0) {
+            gi = 0;
+          } else {
+            gi %= refl_period;
+            if (gi < 0) gi += refl_period;
+            if (gi >= n_samp) gi = refl_period - gi;
+          }
+        }
         float y = 0.f;
-        if (gi < n_samp) {
+        if (gi >= 0 && gi < n_samp) {
           const float cur = load_pcm<PcmT>(a.pcm, s_begin + gi);
           if (pmode == 0) {
             y = cur;
@@ -197,7 +210,11 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
       for (int i = 0; i < len; ++i) acc = fmaf(__ldg(w + i), p[i], acc);
       if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
       acc += cfg.log_add;
-      mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
+      if (cfg.log_type == 3) {  // librosa power_to_db: 10 log10(max(amin, S)), ref = 1
+        mel[m] = 10.f * log10f(fmaxf(acc, cfg.log_zero_floor));
+      } else {
+        mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
+      }
     }
     __syncwarp();
     // ---- DCT (rows chosen by the host: c0 kept or dropped, lifter folded in)
@@ -280,8 +297,12 @@ static bool frontend_cfg_ok(const ssp_frontend_cfg* c) {
   if (c->frame_len < 1 || c->frame_len > c->nfft || c->frame_shift < 1) return false;
   if (c->n_filt < 1 || c->n_filt > 256 || c->n_ceps < 1 || c->n_ceps > c->n_filt) return false;
   if (c->delta_order < 0 || c->delta_order > 2 || (c->delta_order > 0 && c->delta_n < 1)) return false;
-  if (c->n_ceps * (1 + c->delta_order) > 64) return false;
-  if (c->framing < 0 || c->framing > 2 || c->preemph_mode < 0 || c->preemph_mode > 2) return false;
+  // 64 mean / inverse-std slots for the fused CMVN; without CMVN and deltas a frame may keep every filter output
+  // (PLP critical bands, librosa's 128 log-mel bands) for a post kernel
+  if (c->n_ceps * (1 + c->delta_order) > 64 && (c->cmvn || c->delta_order)) return false;
+  if (c->framing < 0 || c->framing > 4 || c->preemph_mode < 0 || c->preemph_mode > 2) return false;
+  if (c->framing >= 3 && c->preemph_mode != 0) return false;
+  if (c->log_type < 0 || c->log_type > 3 || (c->log_type == 3 && !(c->log_zero_floor > 0.f))) return false;
   if (c->pcm_dtype < 0 || c->pcm_dtype > 1) return false;
   return true;
 }
@@ -362,7 +383,8 @@ extern "C" int64_t ssp_frontend_num_frames(const ssp_frontend_cfg* c, int64_t n)
   switch (c->framing) {
     case 0: return n < len ? 0 : (n - len) / hop + 1;
     case 1: return n <= len ? 1 : 1 + (n - len + hop - 1) / hop;
-    default: return (n + hop - 1) / hop;
+    case 2: return (n + hop - 1) / hop;
+    default: return 1 + n / hop;  // centred: the signal is padded by len / 2 on both sides
   }
 }
 

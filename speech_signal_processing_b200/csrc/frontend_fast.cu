@@ -447,7 +447,8 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
 }  // namespace ff
 
 bool frontend_fast_supported(const ssp_frontend_cfg& c) {
-  return c.nfft == 512 && c.n_filt <= ff::MAXF && c.n_ceps <= ff::MAXC && c.frame_len >= 2 && c.frame_shift >= 1 &&
+  return c.nfft == 512 && c.framing <= 2 && c.log_type <= 2 && c.n_filt <= ff::MAXF && c.n_ceps <= ff::MAXC &&
+         c.frame_len >= 2 && c.frame_shift >= 1 &&
          (ff::W - 1) * c.frame_shift + c.frame_len + 1 <= 256 * 8;
 }
 

@@ -188,6 +188,46 @@ def plp_recipe(nwin=0.025, fs=16000, plp_order=13, shift=0.01, prefac=0.97, rast
                   log_type=2, energy_mode=1, extra={"eql": eql, "idft": idft, "lift": lift, "rasta": bool(rasta), "n_ceps": nc})
 
 
+def _slaney_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1000.0) / 1000.0) * (27.0 / math.log(6.4)), f * (3.0 / 200.0))
+
+
+def _slaney_imel(m):
+    m = np.asarray(m, dtype=np.float64)
+    return np.where(m >= 15.0, 1000.0 * np.exp((math.log(6.4) / 27.0) * (m - 15.0)), m * (200.0 / 3.0))
+
+
+def slaney_filterbank(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    """``librosa.filters.mel`` defaults (Slaney mel scale, area-normalised triangles evaluated at the bin centres)."""
+    fmax = sr / 2.0 if fmax is None else float(fmax)
+    hz = np.arange(n_fft // 2 + 1) * (sr / float(n_fft))
+    edges = _slaney_imel(np.linspace(_slaney_mel(fmin), _slaney_mel(fmax), n_mels + 2))
+    fb = np.zeros((n_mels, n_fft // 2 + 1))
+    for i in range(n_mels):
+        lo, ce, hi = edges[i : i + 3]
+        fb[i] = np.maximum(0.0, np.minimum((hz - lo) / (ce - lo), (hi - hz) / (hi - ce))) * (2.0 / (hi - lo))
+    return fb
+
+
+def librosa_recipe(sr=8000, n_mfcc=13, n_fft=2048, hop_length=512, n_mels=128, fmin=0.0, fmax=None, top_db=80.0,
+                   center=True, pad_mode="reflect", amin=1e-10) -> Recipe:
+    """``librosa.feature.mfcc(y, sr=8000, n_mfcc=13)`` as MFCC_DTW.py:27-30 calls it (parity unpinned: librosa is absent
+    and un-pinned).  The fused kernel produces the log-mel power in dB per frame (identity "DCT"); the
+    utterance-wide ``top_db`` clip and the DCT (``ssp_mel_db_post``) ride in ``extra``."""
+    if pad_mode not in ("reflect", "constant"):
+        raise NotImplementedError(f"pad_mode {pad_mode!r} (reflect and constant are built)")
+    n = int(n_fft)
+    if not 64 <= n <= 4096:
+        raise NotImplementedError("n_fft must lie in [64, 4096]")
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)  # periodic Hann (scipy get_window, fftbins=True)
+    framing = (3 if pad_mode == "reflect" else 4) if center else 0
+    return Recipe("librosa", n, int(hop_length), n, win, slaney_filterbank(sr, n, n_mels, fmin, fmax), np.eye(int(n_mels)),
+                  framing=framing, log_type=3, log_zero_floor=float(amin),
+                  extra={"dct": dct_rows(int(n_mfcc), int(n_mels)), "top_db": -1.0 if top_db is None else float(top_db),
+                         "n_ceps": int(n_mfcc)})
+
+
 def processing_recipe(fs=8000, frameSize=512, step=256) -> Recipe:
     """utils/processing.py:110-144 ``MFCC``: Hamming, no pre-emphasis (line 34 is commented out),
     magnitude/n spectrum, 40 talkbox triangles, log10(. + 1e-8), 13 cepstra incl. c0."""
@@ -291,8 +331,10 @@ class FrontEnd:
             nfr = np.where(lens < r.frame_len, 0, (lens - r.frame_len) // r.frame_shift + 1)
         elif r.framing == 1:
             nfr = np.where(lens <= r.frame_len, 1, 1 + -(-(lens - r.frame_len) // r.frame_shift))
-        else:
+        elif r.framing == 2:
             nfr = -(-lens // r.frame_shift)
+        else:
+            nfr = 1 + lens // r.frame_shift
         nfr = np.where(lens <= 0, 0, nfr).astype(np.int64)
         frame_offsets = np.zeros(n_utts + 1, dtype=np.int64)
         np.cumsum(nfr, out=frame_offsets[1:])
@@ -303,6 +345,8 @@ class FrontEnd:
         if n_utts == 0 or total == 0:
             return out, frame_offsets, log_e
         max_fused = int(self.lib.ssp_frontend_max_frames(C.byref(cfg)))
+        if int(nfr.max()) > max_fused and r.framing >= 3:
+            raise NotImplementedError(f"centred framing: utterances beyond {max_fused} frames are not chunked")
         if int(nfr.max()) > max_fused:
             self._extract_mixed(pcm, pcm_dtype, sample_offsets, frame_offsets, nfr, max_fused, out, log_e)
             return out, frame_offsets, log_e
@@ -469,6 +513,48 @@ class PlpFrontEnd:
             feats = out
         self._keep = (d_off, bands, ceps)
         return feats, offs, log_e
+
+
+class MelDbFrontEnd:
+    """librosa-convention MFCC for a batch of utterances: the fused kernel up to the log-mel power in dB,
+    ``ssp_mel_db_post`` for the utterance-wide ``top_db`` clip and the DCT."""
+
+    def __init__(self, recipe: Recipe | None = None, device=None):
+        torch = _lib.require_cuda()
+        self.recipe = recipe or librosa_recipe()
+        self.bands = FrontEnd(self.recipe, delta_order=0, cmvn=False, device=device)
+        self.device, self.lib = self.bands.device, self.bands.lib
+        ex = self.recipe.extra
+        self.n_ceps = self.out_dim = int(ex["n_ceps"])
+        self.top_db = float(ex["top_db"])
+        self.t_dct = torch.as_tensor(np.ascontiguousarray(ex["dct"], dtype=np.float32), device=self.device)
+
+    def extract(self, signals):
+        """Returns (ceps (sum T, n_mfcc) cuda float32, frame_offsets np.int64)."""
+        torch = _lib.require_cuda()
+        mel_db, offs, _ = self.bands.extract(signals)
+        total, nm = int(offs[-1]), mel_db.shape[1]
+        ceps = torch.empty((total, self.n_ceps), dtype=torch.float32, device=self.device)
+        d_off = torch.as_tensor(offs, device=self.device)
+        if total:
+            _lib.check(self.lib.ssp_mel_db_post(_lib.ptr(mel_db), _lib.ptr(d_off), len(offs) - 1, nm, self.n_ceps,
+                                                _lib.ptr(self.t_dct), self.top_db, _lib.ptr(ceps), _lib.stream_ptr()),
+                       "ssp_mel_db_post")
+        self._keep = (d_off, mel_db)
+        return ceps, offs
+
+
+def librosa_mfcc(y, sr=8000, n_mfcc=13, **kwargs):
+    """``librosa.feature.mfcc(y, sr=sr, n_mfcc=n_mfcc, ...)`` (MFCC_DTW.py:28): (n_mfcc, T) float32."""
+    key = ("librosa", sr, n_mfcc, tuple(sorted(kwargs.items())))
+    fe = _cached(key, lambda: MelDbFrontEnd(librosa_recipe(sr=sr, n_mfcc=n_mfcc, **kwargs)))
+    ceps, _ = fe.extract([np.asarray(y, dtype=np.float32)])
+    return np.ascontiguousarray(ceps.cpu().numpy().T)
+
+
+def MFCC_lib(raw_signal, n_mfcc=13):
+    """``MFCC_DTW.MFCC_lib`` (MFCC_DTW.py:27-30): librosa MFCC at sr=8000, frame-major, flattened."""
+    return librosa_mfcc(np.asarray(raw_signal).astype("float32"), sr=8000, n_mfcc=n_mfcc).T.flatten()
 
 
 def plp(input_sig, nwin=0.025, fs=16000, plp_order=13, shift=0.01, get_spec=False, get_mspec=False, prefac=0.97, rasta=True):

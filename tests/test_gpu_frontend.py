@@ -186,3 +186,26 @@ def test_extract_feature_plp_batched():
         np.testing.assert_allclose(f, ref, rtol=0, atol=2e-2)   # CMVN divides by per-column std (~0.02 .. 0.5)
     with pytest.raises(NameError):
         ssp.extract_feature(x, y, feature_type="LPCC")
+
+
+@pytest.mark.parametrize("n_samples", [12000, 24000, 700, 1])
+def test_MFCC_lib_matches_oracle(n_samples):
+    """MFCC_DTW.MFCC_lib (librosa.feature.mfcc at sr=8000; MFCC_DTW.py:27-30): centred, mirror-padded frames of 2048,
+    128 Slaney mel bands, dB with the utterance-wide 80 dB clip, DCT -- fused kernel + ssp_mel_db_post."""
+    sig = synth.synth_utterance(6, n_samples % 11, n_samples, 8000)
+    got = ssp.MFCC_lib(sig)
+    want = ofe.mfcc_lib(sig)
+    assert got.shape == want.shape == (13 * (1 + n_samples // 512),)
+    assert_ceps_close(got, want)
+
+
+def test_librosa_mfcc_options_match_oracle():
+    sig = synth.synth_utterance(8, 2, 9000, 8000)
+    for kw in (dict(pad_mode="constant"), dict(center=False), dict(top_db=None), dict(n_fft=512, hop_length=128, n_mels=40),
+               dict(n_fft=400, hop_length=160, n_mels=40, sr=16000)):
+        full = dict(sr=8000, n_mfcc=13)
+        full.update(kw)
+        got = ssp.librosa_mfcc(sig.astype(np.float32), **full)
+        want = ofe.librosa_mfcc(sig.astype(np.float32), **full)
+        assert got.shape == want.shape and got.shape[0] == 13
+        assert_ceps_close(got, want)

@@ -61,6 +61,28 @@ def test_processing_tables_reproduce_reference_for_any_frame_size(golden, fs, fr
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
 
 
+def test_librosa_recipe_tables_match_oracle():
+    """Host tables of the librosa convention (MFCC_DTW.py:27-30) and the kernel's mirror-index rule, emulated in numpy."""
+    r = ssp.librosa_recipe()
+    assert (r.frame_len, r.frame_shift, r.nfft, r.framing, r.log_type, r.preemph_mode) == (2048, 512, 2048, 3, 3, 0)
+    np.testing.assert_allclose(r.fbank, ofe.librosa_mel_filters(8000, 2048), atol=1e-14)
+    np.testing.assert_allclose(r.extra["dct"], ofe.dct2_ortho_matrix(13, 128), atol=1e-15)
+    assert ssp.librosa_recipe(pad_mode="constant").framing == 4 and ssp.librosa_recipe(center=False).framing == 0
+    for n in (12000, 700, 2):  # 700 and 2: the padding folds more than once
+        sig = synth.synth_utterance(3, n % 7, n, 8000).astype(np.float64)
+        t_frames = 1 + n // 512
+        idx = np.arange(t_frames)[:, None] * 512 + np.arange(2048)[None, :] - 1024
+        per = 2 * (n - 1)
+        m = np.mod(idx, per)
+        m = np.where(m >= n, per - m, m)
+        power = np.abs(np.fft.rfft(sig[m] * r.window, axis=1)) ** 2
+        db = 10 * np.log10(np.maximum(power @ r.fbank.T, r.log_zero_floor))
+        db = np.maximum(db, db.max() - r.extra["top_db"])
+        np.testing.assert_allclose((db @ r.extra["dct"].T).T, ofe.librosa_mfcc(sig), atol=1e-8)
+    with pytest.raises(NotImplementedError):
+        ssp.librosa_recipe(pad_mode="edge")
+
+
 def test_dct_rows_and_lifter():
     np.testing.assert_allclose(pfe.dct_rows(13, 26), ofe.dct2_ortho_matrix(13, 26), atol=1e-15)
     lift = 1 + 11 * np.sin(np.pi * np.arange(13) / 22)

@@ -208,3 +208,46 @@ def test_plp_building_blocks_known_answers():
     assert (np.diff(w.argmax(axis=1)) > 0).all()
     out = ofe.sidekit_plp(synth.synth_utterance(1, 2, 16000))
     assert out[0].shape == (98, 13) and out[1].shape == (98,) and np.isfinite(out[0]).all()
+
+
+def test_librosa_restatement_agrees_with_torchaudio():
+    """librosa is absent (parity unpinned); torchaudio's MFCC transform implements the same conventions independently
+    (Slaney mel / area norm, centred reflect-padded STFT, power_to_db with top_db 80, DCT-II ortho) -- a cross-check of
+    the restatement, not a pin.  MFCC_DTW.py:27-30."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    from speech_signal_processing_b200 import synth
+
+    sig = synth.synth_utterance(3, 1, 12000, 8000).astype(np.float64)
+    tr = torchaudio.transforms.MFCC(sample_rate=8000, n_mfcc=13, dct_type=2, norm="ortho", log_mels=False, melkwargs=dict(
+        n_fft=2048, hop_length=512, n_mels=128, center=True, pad_mode="reflect", power=2.0, norm="slaney", mel_scale="slaney",
+        f_min=0.0, f_max=4000.0)).double()
+    want = tr(torch.from_numpy(sig)).numpy()
+    got = ofe.librosa_mfcc(sig)
+    assert got.shape == want.shape == (13, 1 + 12000 // 512)
+    # torchaudio builds its filterbank in float32: agreement to ~1e-7 relative on values up to ~900
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-3)
+    assert ofe.mfcc_lib(sig.astype(np.int16)).shape == (13 * 24,)
+
+
+def test_librosa_known_answers():
+    # Slaney mel scale: linear below 1 kHz (200/3 Hz per mel), log above; the two branches meet at 1 kHz = 15 mel
+    assert ofe.slaney_hz_to_mel(1000.0) == pytest.approx(15.0)
+    assert ofe.slaney_hz_to_mel(200.0) == pytest.approx(3.0)
+    assert ofe.slaney_mel_to_hz(ofe.slaney_hz_to_mel(3210.0)) == pytest.approx(3210.0)
+    assert ofe.slaney_hz_to_mel(6400.0) == pytest.approx(15.0 + 27.0)  # log step: 27 mel per factor 6.4
+    fb = ofe.librosa_mel_filters(8000, 2048)
+    assert fb.shape == (128, 1025) and (fb >= 0).all() and (fb.sum(axis=1) > 0).all()
+    # area normalisation: every triangle integrates to ~1 over frequency
+    np.testing.assert_allclose(fb.sum(axis=1) * (8000 / 2048), 1.0, atol=0.08)
+    # digital silence: every band sits at amin -> -100 dB everywhere -> only c0 is non-zero
+    c = ofe.librosa_mfcc(np.zeros(4096))
+    np.testing.assert_allclose(c[0], -100.0 * np.sqrt(128), rtol=1e-12)
+    np.testing.assert_allclose(c[1:], 0.0, atol=1e-9)
+    # a tone far above the floor: the top_db clip holds every band within 80 dB of the maximum
+    t = np.arange(8000) / 8000.0
+    tone = 1e4 * np.sin(2 * np.pi * 440.0 * t)
+    c_clip = ofe.librosa_mfcc(tone)
+    c_free = ofe.librosa_mfcc(tone, top_db=None)
+    assert np.abs(c_clip - c_free).max() > 1.0
+    assert c_clip.shape == (13, 1 + 8000 // 512)
