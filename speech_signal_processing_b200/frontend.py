@@ -287,6 +287,20 @@ class FrontEnd:
         cfg = self._cfg(0)
         return int(self.lib.ssp_frontend_num_frames(C.byref(cfg), int(n_samples)))
 
+    def frame_counts(self, lens) -> np.ndarray:
+        """Frames per utterance for an array of sample counts (the rule of ``ssp_frontend_num_frames``, vectorised)."""
+        r = self.recipe
+        lens = np.asarray(lens, dtype=np.int64)
+        if r.framing == 0:
+            nfr = np.where(lens < r.frame_len, 0, (lens - r.frame_len) // r.frame_shift + 1)
+        elif r.framing == 1:
+            nfr = np.where(lens <= r.frame_len, 1, 1 + -(-(lens - r.frame_len) // r.frame_shift))
+        elif r.framing == 2:
+            nfr = -(-lens // r.frame_shift)
+        else:
+            nfr = 1 + lens // r.frame_shift
+        return np.where(lens <= 0, 0, nfr).astype(np.int64)
+
     # -- host entry: list of 1-D numpy signals -----------------------------------------------
     def pack_host(self, signals):
         """Concatenate utterances into one pinned host buffer + offsets (int16 stays int16)."""
@@ -325,17 +339,8 @@ class FrontEnd:
         cfg = self._cfg(pcm_dtype)
         sample_offsets = np.asarray(sample_offsets, dtype=np.int64)
         n_utts = len(sample_offsets) - 1
-        lens = np.diff(sample_offsets)
         r = self.recipe
-        if r.framing == 0:
-            nfr = np.where(lens < r.frame_len, 0, (lens - r.frame_len) // r.frame_shift + 1)
-        elif r.framing == 1:
-            nfr = np.where(lens <= r.frame_len, 1, 1 + -(-(lens - r.frame_len) // r.frame_shift))
-        elif r.framing == 2:
-            nfr = -(-lens // r.frame_shift)
-        else:
-            nfr = 1 + lens // r.frame_shift
-        nfr = np.where(lens <= 0, 0, nfr).astype(np.int64)
+        nfr = self.frame_counts(np.diff(sample_offsets))
         frame_offsets = np.zeros(n_utts + 1, dtype=np.int64)
         np.cumsum(nfr, out=frame_offsets[1:])
         total = int(frame_offsets[-1])

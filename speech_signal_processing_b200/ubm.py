@@ -110,6 +110,97 @@ def identify(utts, speakers, ubm=None, precision="tf32", device=None):
     return pred, pred.argmax(axis=1)
 
 
+# frames one wave of the persistent scoring kernels covers: 148 CTAs x 256-frame units
+_WAVE_FRAMES = 148 * 256
+
+
+def split_for_overlap(frame_counts, head_fraction: float = 0.1, min_frames: int = 4 * _WAVE_FRAMES) -> int:
+    """Utterances in the head part of a two-part pipelined batch: about ``head_fraction`` of the frames, rounded to
+    whole waves of the persistent scoring kernel so that cutting the batch does not add a partly filled wave.  0 means
+    "do not split" (batch too small for the overlap to pay)."""
+    cum = np.cumsum(np.asarray(frame_counts, dtype=np.int64))
+    total = int(cum[-1]) if len(cum) else 0
+    if total < min_frames or len(cum) < 2:
+        return 0
+    waves = max(1, int(round(head_fraction * total / _WAVE_FRAMES)))
+    n = int(np.searchsorted(cum, waves * _WAVE_FRAMES, side="right"))
+    if not 0 < n < len(cum):  # less than a wave or two in total: cut at the plain fraction
+        n = int(np.searchsorted(cum, head_fraction * total, side="right"))
+    return n if 0 < n < len(cum) else 0
+
+
+def identify_pcm(host_pcm, sample_offsets, front_end, speakers, ubm_index=None, precision="tf32", out=None,
+                 head_fraction: float = 0.1, min_split_frames: int = 4 * _WAVE_FRAMES):
+    """Raw PCM on the host -> speaker decisions on the host, for one batch of utterances: the front-end of
+    GMM_UBM.py:129 and the scoring / argmax of :191-197 as one call.
+
+    ``host_pcm``: 1-D int16 / float32 torch tensor (pinned memory makes the copies asynchronous) or numpy array with all
+    utterances back to back; ``sample_offsets``: int64 (N+1,); ``front_end``: :class:`FrontEnd`; ``speakers``:
+    :class:`ModelSet` / :class:`SharedModelSet`; ``ubm_index``: the model whose score is subtracted (and excluded from
+    the argmax), or None.  The host-to-device copy is cut in two at an utterance boundary: the head (about a tenth of
+    the frames, whole scoring waves) is copied on the current stream and goes straight into the front-end and scoring
+    kernels while a side stream copies the rest, so all but the head's transfer is hidden behind compute.
+    Returns ``(decisions (N,) int64 host tensor, total_frames)``; the call returns after the decisions have landed."""
+    torch = _lib.require_cuda()
+    dev = front_end.device
+    if isinstance(host_pcm, np.ndarray):
+        host_pcm = torch.from_numpy(np.ascontiguousarray(host_pcm))
+    sample_offsets = np.asarray(sample_offsets, dtype=np.int64)
+    n_utts = len(sample_offsets) - 1
+    if out is None:
+        out = torch.empty(n_utts, dtype=torch.int64, pin_memory=True)
+    nfr = front_end.frame_counts(np.diff(sample_offsets))
+    n_head = split_for_overlap(nfr, head_fraction, min_split_frames)
+    cur = torch.cuda.current_stream(dev)
+    pcm = torch.empty(int(sample_offsets[-1] - sample_offsets[0]), dtype=host_pcm.dtype, device=dev)
+    base = int(sample_offsets[0])
+    parts = [(0, n_utts)] if n_head == 0 else [(0, n_head), (n_head, n_utts)]
+    ready = []
+    side = None
+    for k, (lo, hi) in enumerate(parts):
+        a, b = int(sample_offsets[lo]) - base, int(sample_offsets[hi]) - base
+        if k == 0:
+            pcm[a:b].copy_(host_pcm[base + a : base + b], non_blocking=True)
+            ready.append(None)
+        else:
+            side = _side_stream(dev)
+            side.wait_stream(cur)  # the buffer was allocated on the current stream
+            with torch.cuda.stream(side):
+                pcm[a:b].copy_(host_pcm[base + a : base + b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ready.append(ev)
+    dec = torch.empty(n_utts, dtype=torch.int64, device=dev)
+    total = 0
+    for (lo, hi), ev in zip(parts, ready):
+        if ev is not None:
+            cur.wait_event(ev)
+        offs = sample_offsets[lo : hi + 1] - base
+        feats, foffs, _ = front_end.extract_device(pcm, offs)
+        total += int(foffs[-1])
+        scores, _ = speakers.score(feats, foffs, precision=precision)
+        if ubm_index is not None:
+            k = int(ubm_index) % scores.shape[1]
+            llr = scores - scores[:, k : k + 1]
+            llr[:, k] = -float("inf")
+            scores = llr
+        torch.argmax(scores, dim=1, out=dec[lo:hi])
+    out.copy_(dec, non_blocking=True)
+    cur.synchronize()
+    return out, total
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev):
+    torch = _lib.require_cuda()
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 label_encoder: dict = {}
 
 

@@ -414,3 +414,31 @@ def test_identify_routes_shared_base_model_lists_to_the_shared_variance_kernel()
     odd = ssp.GaussianMixture.from_params(w, spk_mu[0], var * 1.1)
     pred2, _ = ssp.identify(tests, models[:-1] + [odd], ubm)
     np.testing.assert_allclose(pred2[:, :-1], ref[:, :-1], rtol=0, atol=1.2e-2)
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_identify_pcm_equals_separate_calls(split):
+    """identify_pcm (pinned host PCM -> decisions on the host, H2D of the tail overlapped with the kernels of the head)
+    == front-end + scoring + argmax called one after the other on the whole batch; also with ragged utterance lengths
+    and the UBM in the middle of the model set."""
+    import torch
+
+    k, d, n_spk = 128, 39, 6
+    w, mu, var = synth.synth_ubm(k, d, seed=3, spread=0.8)
+    spk = synth.synth_speaker_means(mu, n_spk, seed=4, shift=0.3)
+    means = np.concatenate([spk[:2], mu[None], spk[2:]])  # UBM is model 2
+    sms = ssp.SharedModelSet(w, var, means, ref_model=2)
+    sigs = [synth.synth_utterance(s % 5, s, 16000 + 800 * (s % 7)) for s in range(40)]
+    fe = ssp.FrontEnd(ssp.sidekit_recipe(), delta_order=2, cmvn=True)
+    host, offs = fe.pack_host(sigs)
+    feats, foffs, _ = fe.extract(sigs)
+    scores, _ = sms.score(feats, foffs)
+    llr = (scores - scores[:, 2:3]).cpu().numpy()
+    llr[:, 2] = -np.inf
+    want = llr.argmax(axis=1)
+    got, total = ssp.identify_pcm(host, offs, fe, sms, ubm_index=2, min_split_frames=0 if split else 1 << 40, head_fraction=0.3)
+    assert total == int(foffs[-1]) and got.dtype == torch.int64 and got.shape == (len(sigs),)
+    assert (got.numpy() == want).all()
+    # numpy PCM (not pinned) and no UBM: plain argmax over the scores
+    got2, _ = ssp.identify_pcm(host.numpy().copy(), offs, fe, sms, min_split_frames=0 if split else 1 << 40)
+    assert (got2.numpy() == scores.cpu().numpy().argmax(axis=1)).all()

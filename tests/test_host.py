@@ -103,6 +103,22 @@ def test_shard_helpers():
     assert (max(loads) - min(loads)) <= lens.max()
 
 
+def test_split_for_overlap_cuts_on_whole_waves():
+    from speech_signal_processing_b200.ubm import _WAVE_FRAMES, split_for_overlap
+
+    nfr = np.full(10000, 298)
+    n = split_for_overlap(nfr)  # config 4: a tenth of 2.98 M frames = 7.9 waves -> 8 waves
+    assert 0 < n < 10000
+    assert n * 298 <= 8 * _WAVE_FRAMES < (n + 1) * 298
+    assert split_for_overlap(np.full(100, 298)) == 0           # too small to pay
+    assert split_for_overlap(np.array([10 * _WAVE_FRAMES])) == 0  # one utterance cannot be cut
+    ragged = np.random.RandomState(0).randint(98, 2998, size=5000)
+    m = split_for_overlap(ragged, 0.25)
+    assert 0 < m < 5000 and ragged[:m].sum() <= round(0.25 * ragged.sum() / _WAVE_FRAMES) * _WAVE_FRAMES
+    assert split_for_overlap(np.array([300, 300, 300]), 0.3, min_frames=0) == 0  # head would be empty: no split
+    assert split_for_overlap(np.full(40, 115), 0.3, min_frames=0) == 12           # below one wave: the plain fraction
+
+
 def test_product_never_imports_the_oracle_or_reference():
     pkg = os.path.join(ROOT, "speech_signal_processing_b200")
     for dirpath, _, files in os.walk(pkg):
