@@ -335,7 +335,20 @@ def run_b200(a):
     barrier()
     e2e_ms = ev[0].elapsed_time(ev[1])
     clocks = sampler.stop() if rank == 0 else None
-    e2e_same = bool((host_dec.to(dev) == dec).all().item())  # host-to-host decisions == HBM-resident decisions
+    # host-to-host decisions vs HBM-resident decisions.  The two paths cut the batch differently, so the FP32 partial
+    # sums inside a warp group other frames of an utterance (the cross-warp accumulation is float64): scores agree to
+    # ~1e-6 absolute and a decision can only differ where the top-2 LLR margin is below that.  Report the count and
+    # the largest margin among differing utterances instead of a bare flag.
+    e2e_dec = host_dec.to(dev)
+    differ = (e2e_dec != dec).nonzero().flatten()
+    e2e_check = {"utts": int(dec.numel()), "differ": int(differ.numel()), "largest_llr_margin_among_differing": 0.0}
+    if differ.numel():
+        feats, foffs, _ = fe.extract_device(pcm, sample_offsets)
+        sc, _ = scorer.score(feats, foffs, precision=a.precision)
+        llr = (sc[:, :S] - sc[:, S:])[differ]
+        e2e_check["largest_llr_margin_among_differing"] = float(
+            (llr.gather(1, dec[differ][:, None]) - llr.gather(1, e2e_dec[differ][:, None])).abs().max().item())
+        del feats, sc, llr
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(frames)], dtype=torch.float64, device=dev)
@@ -403,7 +416,7 @@ def run_b200(a):
                      "frac_of_bf16_peak": achieved / peaks["bf16_tflops_sustained"]},
         "clocks": clocks,
         "check": {"tc_vs_fp32_max_rel": rel, "decisions_equal": bool((dec_tc == dec_fp).all().item()), "utts": sub,
-                  "e2e_decisions_equal_device_path": e2e_same},
+                  "e2e_vs_device_decisions": e2e_check},
     }
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
