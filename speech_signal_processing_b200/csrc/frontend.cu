@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
   float* mean = red + blockDim.x;                                // 64
   float* istd = mean + 64;                                       // 64
   float* warp_base = istd + 64;
-  const int per_warp = 4 * NH + (NH + 4) + ((NF + 3) & ~3);      // bufA, bufB (float2 each), spectrum, mel
+  const int per_warp = (4 * NH + (NH + 4) + ((NF + 3) & ~3) + 3) & ~3;  // bufA, bufB (float2 each), spectrum, mel; 16-byte multiple
   float* wb = warp_base + (size_t)warp * per_warp;
   float2* bufA = reinterpret_cast<float2*>(wb);
   float2* bufB = bufA + NH;
@@ -43,8 +43,18 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
 
   // FFT lengths that are not a power of two (utils/processing.py:129 uses the frame length, e.g. 400) take a direct
   // DFT against one table e^{-2 pi i q / nfft}, q < nfft, laid over the two FFT tables (2 nfft <= 4 NH + 4 floats).
+  // Even lengths whose half is 2^a 3^b 5^c (400 = 2 * 200) run the half-size complex FFT with radix-3 / radix-5 stages
+  // next to the radix-4 / radix-2 ones; everything else (odd lengths, other prime factors) the direct DFT.
   const bool pow2 = (nfft & (nfft - 1)) == 0;
-  if (pow2) {
+  bool smooth = (nfft & 1) == 0;
+  {
+    int m = NH;
+    while ((m & 1) == 0) m >>= 1;
+    while (m % 3 == 0) m /= 3;
+    while (m % 5 == 0) m /= 5;
+    smooth = smooth && m == 1;
+  }
+  if (smooth) {
     for (int q = threadIdx.x; q < NH; q += blockDim.x) {
       float s, c;
       sincospif(-2.0f * (float)q / (float)NH, &s, &c);
@@ -111,16 +121,16 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
     energy = warp_sum(energy);
     __syncwarp();
 
-    // ---- Stockham autosort FFT of NH complex points (radix 4, one radix-2 stage if log2(NH) is odd)
+    // ---- Stockham autosort FFT of NH complex points (radix 4, then radix 2 / 3 / 5 stages for what is left of NH)
     float2* src = bufA;
     float2* dst = bufB;
-    for (int Ns = 1; pow2 && Ns < NH;) {
+    for (int Ns = 1; smooth && Ns < NH;) {
       const int rem = NH / Ns;
       if ((rem & 3) == 0) {
         const int q4 = NH >> 2;
         const int tstep = NH / (Ns * 4);
         for (int j = lane; j < q4; j += 32) {
-          const int k = j & (Ns - 1);
+          const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
           float2 v0 = src[j], v1 = src[j + q4], v2 = src[j + 2 * q4], v3 = src[j + 3 * q4];
           if (Ns > 1) {
             v1 = cmul(v1, tw_fft[k * tstep]);
@@ -138,11 +148,11 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
           dst[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
         }
         Ns <<= 2;
-      } else {
+      } else if ((rem & 1) == 0) {
         const int q2 = NH >> 1;
         const int tstep = NH / (Ns * 2);
         for (int j = lane; j < q2; j += 32) {
-          const int k = j & (Ns - 1);
+          const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
           float2 v0 = src[j], v1 = src[j + q2];
           if (Ns > 1) v1 = cmul(v1, tw_fft[k * tstep]);
           const int j0 = ((j - k) << 1) + k;
@@ -150,6 +160,54 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
           dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
         }
         Ns <<= 1;
+      } else if (rem % 3 == 0) {
+        const int q3 = NH / 3;
+        const int tstep = NH / (Ns * 3);
+        const float S3 = 0.86602540378443865f;  // sin(2 pi / 3)
+        for (int j = lane; j < q3; j += 32) {
+          const int k = j % Ns;
+          float2 v0 = src[j], v1 = src[j + q3], v2 = src[j + 2 * q3];
+          if (Ns > 1) {
+            v1 = cmul(v1, tw_fft[k * tstep]);
+            v2 = cmul(v2, tw_fft[2 * k * tstep]);
+          }
+          const float2 t = make_float2(v1.x + v2.x, v1.y + v2.y);
+          const float2 a = make_float2(fmaf(-0.5f, t.x, v0.x), fmaf(-0.5f, t.y, v0.y));
+          const float2 b = make_float2(S3 * (v1.x - v2.x), S3 * (v1.y - v2.y));
+          const int j0 = (j - k) * 3 + k;
+          dst[j0] = make_float2(v0.x + t.x, v0.y + t.y);
+          dst[j0 + Ns] = make_float2(a.x + b.y, a.y - b.x);      // a - i b
+          dst[j0 + 2 * Ns] = make_float2(a.x - b.y, a.y + b.x);  // a + i b
+        }
+        Ns *= 3;
+      } else {
+        const int q5 = NH / 5;
+        const int tstep = NH / (Ns * 5);
+        const float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f;  // cos(2 pi / 5), cos(4 pi / 5)
+        const float S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;   // sin(2 pi / 5), sin(4 pi / 5)
+        for (int j = lane; j < q5; j += 32) {
+          const int k = j % Ns;
+          float2 v0 = src[j], v1 = src[j + q5], v2 = src[j + 2 * q5], v3 = src[j + 3 * q5], v4 = src[j + 4 * q5];
+          if (Ns > 1) {
+            v1 = cmul(v1, tw_fft[k * tstep]);
+            v2 = cmul(v2, tw_fft[2 * k * tstep]);
+            v3 = cmul(v3, tw_fft[3 * k * tstep]);
+            v4 = cmul(v4, tw_fft[4 * k * tstep]);
+          }
+          const float2 t1 = make_float2(v1.x + v4.x, v1.y + v4.y), t2 = make_float2(v2.x + v3.x, v2.y + v3.y);
+          const float2 t3 = make_float2(v1.x - v4.x, v1.y - v4.y), t4 = make_float2(v2.x - v3.x, v2.y - v3.y);
+          const float2 a1 = make_float2(fmaf(C1, t1.x, fmaf(C2, t2.x, v0.x)), fmaf(C1, t1.y, fmaf(C2, t2.y, v0.y)));
+          const float2 a2 = make_float2(fmaf(C2, t1.x, fmaf(C1, t2.x, v0.x)), fmaf(C2, t1.y, fmaf(C1, t2.y, v0.y)));
+          const float2 b1 = make_float2(fmaf(S1, t3.x, S2 * t4.x), fmaf(S1, t3.y, S2 * t4.y));
+          const float2 b2 = make_float2(fmaf(S2, t3.x, -S1 * t4.x), fmaf(S2, t3.y, -S1 * t4.y));
+          const int j0 = (j - k) * 5 + k;
+          dst[j0] = make_float2(v0.x + t1.x + t2.x, v0.y + t1.y + t2.y);
+          dst[j0 + Ns] = make_float2(a1.x + b1.y, a1.y - b1.x);      // a1 - i b1
+          dst[j0 + 2 * Ns] = make_float2(a2.x + b2.y, a2.y - b2.x);  // a2 - i b2
+          dst[j0 + 3 * Ns] = make_float2(a2.x - b2.y, a2.y + b2.x);  // a2 + i b2
+          dst[j0 + 4 * Ns] = make_float2(a1.x - b1.y, a1.y + b1.x);  // a1 + i b1
+        }
+        Ns *= 5;
       }
       __syncwarp();
       float2* tmp = src; src = dst; dst = tmp;
@@ -158,9 +216,9 @@ __global__ void __launch_bounds__(256) frontend_kernel(const FrontendArgs a) {
     float etot = 0.f;
     for (int k = lane; k <= NH; k += 32) {
       float re, im;
-      if (pow2) {
-        const float2 zk = src[k & (NH - 1)];
-        const float2 zm = src[(NH - k) & (NH - 1)];
+      if (smooth) {
+        const float2 zk = src[k == NH ? 0 : k];
+        const float2 zm = src[k == 0 ? 0 : NH - k];
         const float2 xe = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 xo = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
         const float2 x = cmul(tw_real[k], xo);
@@ -286,14 +344,14 @@ static int frontend_warps(int nfft) { return nfft <= 512 ? 8 : (nfft <= 1024 ? 4
 static size_t frontend_smem(const ssp_frontend_cfg& c, int max_frames) {
   const int NH = c.nfft / 2, nw = frontend_warps(c.nfft);
   size_t floats = 2 * (size_t)NH + 2 * ((size_t)NH + 2) + ((c.frame_len + 3) & ~3) + nw * 32 + 128;
-  floats += (size_t)nw * (4 * NH + (NH + 4) + ((c.n_filt + 3) & ~3));
+  floats += (size_t)nw * ((4 * NH + (NH + 4) + ((c.n_filt + 3) & ~3) + 3) & ~3);
   floats += (size_t)max_frames * c.n_ceps;
   return floats * sizeof(float);
 }
 
 static bool frontend_cfg_ok(const ssp_frontend_cfg* c) {
   if (!c) return false;
-  if (c->nfft < 64 || c->nfft > 4096) return false;  // powers of two: FFT; anything else: direct DFT
+  if (c->nfft < 64 || c->nfft > 4096) return false;  // even with a 2^a 3^b 5^c half: FFT; anything else: direct DFT
   if (c->frame_len < 1 || c->frame_len > c->nfft || c->frame_shift < 1) return false;
   if (c->n_filt < 1 || c->n_filt > 256 || c->n_ceps < 1 || c->n_ceps > c->n_filt) return false;
   if (c->delta_order < 0 || c->delta_order > 2 || (c->delta_order > 0 && c->delta_n < 1)) return false;

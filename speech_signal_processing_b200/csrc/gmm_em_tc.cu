@@ -39,8 +39,6 @@ constexpr int EPI = 512;  // 16 builder / epilogue warps, four per TMEM lane qua
                           // split, exponentials) is latency-bound, more warps hide more of it (8 warps: 7 % slower)
 constexpr int THREADS = 64 + EPI;
 constexpr int MAX_KD = 80;
-constexpr uint32_t TMEM_COLS = 256;  // [0,128): logits, [128, 128+N2): statistics accumulator
-constexpr uint32_t STAT_COL = 128;
 
 struct Args {
   const float* feats;

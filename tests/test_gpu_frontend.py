@@ -25,10 +25,12 @@ def test_processing_MFCC_matches_reference_outputs(golden):
         assert_ceps_close(got, g[f"{tag}_mfcc"])
 
 
-@pytest.mark.parametrize("fs,frame_size,step", [(8000, 200, 80), (16000, 400, 160), (8000, 255, 100), (16000, 1000, 400)])
+@pytest.mark.parametrize("fs,frame_size,step", [(8000, 200, 80), (16000, 400, 160), (8000, 255, 100), (16000, 1000, 400),
+                                                (16000, 480, 160), (8000, 434, 200), (16000, 90, 45), (16000, 162, 80)])
 def test_processing_MFCC_any_frame_size_matches_oracle(fs, frame_size, step):
-    """Frame sizes that are not a power of two, odd ones included, against the oracle restatement (itself pinned by
-    the reference outputs of cases a-d)."""
+    """Frame sizes that are not a power of two against the oracle restatement (itself pinned by the reference outputs
+    of cases a-d): 200 / 400 / 1000 / 480 / 90 / 162 take the mixed-radix FFT (half = 2^a 3^b 5^c), 255 (odd) and 434
+    (2 * 7 * 31) the direct DFT."""
     sig = synth.synth_utterance(4, frame_size % 89, 2 * fs + 123, fs)
     got = ssp.MFCC(sig, fs, frame_size, step)
     want = ofe.processing_mfcc(sig, fs, frame_size, step)
