@@ -36,3 +36,15 @@ def golden():
         return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
     return load
+
+
+@pytest.fixture(scope="session")
+def config1_corpus():
+    """BASELINE configs[0] audio (10 speakers x 30 utterances x 3 s) regenerated from the seeds and split the way
+    GMM_UBM.py:125 does; tests/golden/config1.npz holds the CRC of the test half."""
+    from sklearn.model_selection import train_test_split
+
+    from speech_signal_processing_b200 import synth
+
+    x, y = synth.synth_corpus(10, 30, 48000)
+    return train_test_split(x, y, test_size=0.3, random_state=0)

@@ -3,7 +3,7 @@
 
 Run in the build container only (needs /root/reference and sklearn 1.9.0):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [processing|sklearn|pipeline|vad|config1 ...]
 
 Writes small ``.npz`` files next to this script.  The reference modules are imported
 through ``oracle.ref_shims`` (stub modules for the absent GUI/audio packages).
@@ -16,6 +16,8 @@ sklearn_gmm.npz       sklearn GaussianMixture(diag) score_samples / predict_prob
                       trajectory from fixed initial parameters, preprocessing.scale
 vad.npz               VAD.py::enframe / ZCR / energy / spectrum_entropy / feature / VAD_detection / VAD_frequency
                       on synthetic bursts-in-noise signals
+config1.npz           BASELINE configs[0] at its stated size (10 speakers x 30 utterances x 3 s, 64 components) through the
+                      unmodified GMM_UBM.py::extract_feature + GMM(): reference-trained models, LLR matrix, accuracy line
 pipeline.npz          GMM_UBM.py::extract_feature + GMM() end to end on synthetic audio with
                       the sidekit restatement plugged in as ``mfcc`` and a seeded
                       GaussianMixture (random_state only; everything else stock)
@@ -169,6 +171,85 @@ def gen_pipeline():
     print("reference GMM() printed:", line)
 
 
+CONFIG1 = dict(n_spk=10, n_utt=30, n_samp=48000, k=64)  # BASELINE configs[0] at its stated size
+
+
+def config1_split():
+    """The corpus and the reference's own split (GMM_UBM.py:125) of BASELINE configs[0]; shared with the GPU test, which
+    regenerates the audio from the seeds instead of shipping 29 MB of PCM."""
+    from sklearn.model_selection import train_test_split
+
+    x, y = synth.synth_corpus(CONFIG1["n_spk"], CONFIG1["n_utt"], CONFIG1["n_samp"])
+    return train_test_split(x, y, test_size=0.3, random_state=0)
+
+
+def gen_config1():
+    """BASELINE configs[0] ("GMM_UBM.py default pipeline on CPU: 13-dim MFCC ... + 64-comp diag GMM, 10 speakers,
+    synthetic audio") run through the UNMODIFIED reference extract_feature + GMM() (sidekit restatement plugged in as
+    ``mfcc``, seeded GaussianMixture).  Stored: the reference-trained models, the LLR matrix ``pred`` of the 90 test
+    utterances (GMM_UBM.py:191-194), the printed accuracy line and a fingerprint of audio + features."""
+    import zlib
+
+    from sklearn.mixture import GaussianMixture
+
+    def mfcc_cepstra(sig, **kw):
+        return ofe.sidekit_mfcc(sig, **kw)[0]
+
+    gu = ref_shims.load("GMM_UBM", sidekit_mfcc=mfcc_cepstra)
+    gu.mfcc = mfcc_cepstra
+    x_tr, x_te, y_tr, y_te = config1_split()
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        train, f_tr, y_tr2 = gu.extract_feature(x=x_tr, y=y_tr, is_train=True)
+        f_te, y_te2 = gu.extract_feature(x=x_te, y=y_te)
+    gu.label_encoder.clear()
+    gu.label_encoder.update({f"spk{i}": i for i in range(CONFIG1["n_spk"])})
+    gu.GaussianMixture = functools.partial(GaussianMixture, random_state=0)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+                gu.GMM(train, f_tr, y_tr2, f_te, y_te2, n_components=CONFIG1["k"], model=False)
+            with open("Model/GMM_MFCC_model.pkl", "rb") as f:
+                gmms = pickle.load(f)
+            with open("Model/UBM_MFCC_model.pkl", "rb") as f:
+                ubm = pickle.load(f)
+        finally:
+            os.chdir(cwd)
+    line = [ln for ln in buf.getvalue().splitlines() if "train acc" in ln][-1]
+    pred = np.zeros((len(f_te), len(gmms)))
+    for i in range(len(gmms)):
+        for j in range(len(f_te)):
+            pred[j, i] = gmms[i].score(f_te[j]) - ubm.score(f_te[j])  # GMM_UBM.py:194
+    out = {
+        "y_test": np.array(y_te2), "pred": pred, "printed": np.array(line),
+        "audio_crc": np.array(zlib.crc32(np.concatenate(x_te).tobytes())),
+        "feat_first": np.asarray(f_te[0], dtype=np.float64), "feat_last": np.asarray(f_te[-1], dtype=np.float64),
+        "feat_abs_mean": np.array([np.abs(f).mean() for f in f_te]),
+        "gmm_w": np.stack([g.weights_ for g in gmms]), "gmm_mu": np.stack([g.means_ for g in gmms]).astype(np.float32),
+        "gmm_var": np.stack([g.covariances_ for g in gmms]).astype(np.float32),
+        "ubm_w": ubm.weights_, "ubm_mu": ubm.means_.astype(np.float32), "ubm_var": ubm.covariances_.astype(np.float32),
+    }
+    # the models are stored in float32 (half the bytes); pred is recomputed from the stored parameters so that the
+    # fixture is self-consistent (the float32 rounding of a parameter moves a score by ~1e-6)
+    def sk(wt, m, v):
+        e = GaussianMixture(n_components=len(wt), covariance_type="diag")
+        e.weights_, e.means_, e.covariances_ = wt, m.astype(np.float64), v.astype(np.float64)
+        e.precisions_cholesky_ = 1 / np.sqrt(e.covariances_)
+        return e
+
+    u32 = sk(out["ubm_w"], out["ubm_mu"], out["ubm_var"])
+    g32 = [sk(out["gmm_w"][i], out["gmm_mu"][i], out["gmm_var"][i]) for i in range(len(gmms))]
+    pred32 = np.array([[g.score(f) - u32.score(f) for g in g32] for f in f_te])
+    assert np.abs(pred32 - pred).max() < 1e-4 and (pred32.argmax(1) == pred.argmax(1)).all()
+    out["pred"] = pred32
+    sorted_llr = np.sort(pred32, axis=1)
+    out["min_top2_margin"] = np.array((sorted_llr[:, -1] - sorted_llr[:, -2]).min())
+    np.savez_compressed(os.path.join(HERE, "config1.npz"), **out)
+    print("config 1: reference GMM() printed:", line, "| min top-2 LLR margin", float(out["min_top2_margin"]))
+
+
 def vad_signal(seed: int, n: int, bursts):
     """int16 test signal for the VAD: noise floor + voiced bursts (harmonics) + one unvoiced (noisy) burst."""
     rs = np.random.RandomState(seed)
@@ -219,10 +300,11 @@ def gen_vad():
 if __name__ == "__main__":
     if not ref_shims.available():
         sys.exit("reference tree not found; fixtures can only be generated in the build container")
-    gen_processing()
-    gen_sklearn()
-    gen_pipeline()
-    gen_vad()
+    only = set(sys.argv[1:])
+    for name, fn in (("processing", gen_processing), ("sklearn", gen_sklearn), ("pipeline", gen_pipeline), ("vad", gen_vad),
+                     ("config1", gen_config1)):
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -442,3 +442,42 @@ def test_identify_pcm_equals_separate_calls(split):
     # numpy PCM (not pinned) and no UBM: plain argmax over the scores
     got2, _ = ssp.identify_pcm(host.numpy().copy(), offs, fe, sms, min_split_frames=0 if split else 1 << 40)
     assert (got2.numpy() == scores.cpu().numpy().argmax(axis=1)).all()
+
+
+def test_config1_reference_pipeline_at_full_size(golden, config1_corpus, tmp_path, monkeypatch):
+    """BASELINE configs[0] at its stated size (10 speakers x 30 utterances x 3 s, 26-d, 64 components): audio ->
+    extract_feature on the GPU -> GMM(model=True) with the models the UNMODIFIED reference trained (fixture) -> the LLR
+    matrix of GMM_UBM.py:191-194, every decision and the printed accuracy equal the reference's."""
+    import zlib
+
+    from sklearn.mixture import GaussianMixture as SkGM
+
+    g = golden("config1.npz")
+    _, x_te, _, y_te = config1_corpus
+    assert zlib.crc32(np.concatenate(x_te).tobytes()) == int(g["audio_crc"])
+    feats, labels = ssp.extract_feature(x_te, list(y_te))
+    assert len(feats) == 90 and feats[0].shape == (298, 26)
+    tol = lambda want: 1e-4 * np.maximum(1.0, np.abs(want))  # noqa: E731  (SURVEY 8(c))
+    # CMVN divides by a per-dimension std of ~1e-1..1e1: allow the front-end tolerance after that scaling
+    assert (np.abs(feats[0] - g["feat_first"]) <= 5 * tol(g["feat_first"])).all()
+    assert (np.abs(feats[-1] - g["feat_last"]) <= 5 * tol(g["feat_last"])).all()
+    np.testing.assert_allclose([np.abs(f).mean() for f in feats], g["feat_abs_mean"], rtol=1e-4)
+
+    def sk(wt, m, v):
+        e = SkGM(n_components=len(wt), covariance_type="diag")
+        e.weights_, e.means_, e.covariances_ = wt, m.astype(np.float64), v.astype(np.float64)
+        e.precisions_cholesky_ = 1 / np.sqrt(e.covariances_)
+        return e
+
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "Model").mkdir()
+    with open("Model/GMM_MFCC_model.pkl", "wb") as f:
+        pickle.dump([sk(g["gmm_w"][i], g["gmm_mu"][i], g["gmm_var"][i]) for i in range(10)], f)
+    with open("Model/UBM_MFCC_model.pkl", "wb") as f:
+        pickle.dump(sk(g["ubm_w"], g["ubm_mu"], g["ubm_var"]), f)
+    for precision in ("fp32", "tf32"):
+        acc_tr, acc, pred = ssp.GMM({}, feats, labels, feats, labels, n_components=64, model=True, precision=precision)
+        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=2e-3 if precision == "fp32" else 2e-2)
+        assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
+        assert acc == 1.0 and "test acc 100.00%" in str(g["printed"])
+    assert float(g["min_top2_margin"]) > 100 * 2e-2  # decisions are far from the tolerance

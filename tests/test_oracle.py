@@ -251,3 +251,24 @@ def test_librosa_known_answers():
     c_free = ofe.librosa_mfcc(tone, top_db=None)
     assert np.abs(c_clip - c_free).max() > 1.0
     assert c_clip.shape == (13, 1 + 8000 // 512)
+
+
+def test_config1_reference_run_is_reproduced_by_the_oracle(golden, config1_corpus):
+    """BASELINE configs[0] at its stated size: the models the unmodified GMM_UBM.GMM() trained (fixture), scored by the
+    oracle on oracle features of the regenerated audio, reproduce the reference's LLR matrix and decisions."""
+    import zlib
+
+    g = golden("config1.npz")
+    _, x_te, _, y_te = config1_corpus
+    assert zlib.crc32(np.concatenate(x_te).tobytes()) == int(g["audio_crc"]), "synthetic audio differs from the fixture's"
+    assert list(y_te) == list(g["y_test"])
+    feats = [ofe.features(x, preset="sidekit", delta_order=1, cmvn=True) for x in x_te]
+    np.testing.assert_allclose(feats[0], g["feat_first"], atol=2e-5)   # the reference path is float32 after the spectrum
+    np.testing.assert_allclose(feats[-1], g["feat_last"], atol=2e-5)
+    np.testing.assert_allclose([np.abs(f).mean() for f in feats], g["feat_abs_mean"], rtol=1e-5)
+    mu, var = g["gmm_mu"].astype(np.float64), g["gmm_var"].astype(np.float64)
+    pred = np.array([[ogmm.score(f, g["gmm_w"][i], mu[i], var[i]) for i in range(10)] for f in feats])
+    pred -= np.array([ogmm.score(f, g["ubm_w"], g["ubm_mu"].astype(np.float64), g["ubm_var"].astype(np.float64)) for f in feats])[:, None]
+    np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=5e-4)
+    assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
+    assert (pred.argmax(axis=1) == np.asarray(y_te)).mean() == 1.0 and "test acc 100.00%" in str(g["printed"])
