@@ -52,6 +52,7 @@ def parse_args():
                     help="shared: the shared-variance tensor kernel (mean-only MAP speakers keep the UBM's weights and "
                          "variances); general: the kernel for arbitrary model sets")
     ap.add_argument("--cpu-utts", type=int, default=0, help="reference arm: utterances per step (0 = auto-size)")
+    ap.add_argument("--cpu-budget", type=float, default=100.0, help="reference arm: seconds of CPU work for the whole run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -123,7 +124,7 @@ def run_reference(a):
         f0 = _cpu_frontend_task(sig0)
         list(pool.map(_cpu_score_task, [(f0, i % (n_models - 1), i % (n_models - 1) + 2) for i in range(0, 2 * procs, 2)]))
         per_pair = (time.perf_counter() - t0) / 2.0  # wall seconds per (utt, model) per worker
-        budget = 100.0 / max(1, a.steps + a.warmup)   # whole run within a few minutes
+        budget = a.cpu_budget / max(1, a.steps + a.warmup)   # whole run within a few minutes
         n_utt = a.cpu_utts or int(max(1, min(64, budget / max(1e-6, per_pair * (n_models + 1) / procs))))
         sigs = [synth.synth_utterance(s % 50, s // 50, UTT_SAMPLES) for s in range(n_utt)]
         chunk = max(1, (n_models + procs - 1) // procs)
@@ -212,7 +213,7 @@ def cpu_baseline_subprocess(a):
     """The oracle-port CPU baseline, run in a child BEFORE this process touches CUDA (it forks workers)."""
     try:
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                              "--utts", str(a.utts), "--speakers", str(a.speakers), "--components", str(a.components)],
+                              "--cpu-budget", "30", "--utts", str(a.utts), "--speakers", str(a.speakers), "--components", str(a.components)],
                              capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
         line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
         return json.loads(line)["cpu_baseline"]
