@@ -190,6 +190,54 @@ def identify_pcm(host_pcm, sample_offsets, front_end, speakers, ubm_index=None, 
     return out, total
 
 
+def chunk_features(audio, feature_type="MFCC", fs=16000, seconds=1.0):
+    """The feature side of ``records()`` in the final GUI (UI/tmp.py:301-326): the recording is cut into whole chunks of
+    ``seconds`` (a trailing partial chunk is dropped, :305-307), every chunk goes through ``mfcc(chunk)[0]``,
+    ``plp(chunk)[0]`` or both side by side (``'MFCC_PLP'``, :311-319) -- no deltas -- and ``preprocessing.scale``
+    (:321).  All chunks share ONE upload and one front-end launch per feature type: a chunk is a pair of offsets into
+    the recording.  Returns a list of (T, F) float32 arrays, one per chunk."""
+    torch = _lib.require_cuda()
+    audio = np.asarray(audio)
+    if audio.ndim == 2:
+        audio = audio[:, 0]
+    n = int(round(seconds * fs))
+    n_chunks = len(audio) // n
+    if n_chunks == 0:
+        return []
+    chunks = [audio[i * n : (i + 1) * n] for i in range(n_chunks)]
+    if feature_type == "MFCC":
+        front = fe._cached(("chunk-mfcc", fs), lambda: fe.FrontEnd(fe.sidekit_recipe(fs=fs), delta_order=0, cmvn=True))
+        feats, offs, _ = front.extract(chunks)
+    elif feature_type == "PLP":
+        front = fe._cached(("chunk-plp", fs), lambda: fe.PlpFrontEnd(fe.plp_recipe(fs=fs), delta_order=0, cmvn=True))
+        feats, offs, _ = front.extract(chunks)
+    elif feature_type == "MFCC_PLP":
+        f_m = fe._cached(("chunk-mfcc-raw", fs), lambda: fe.FrontEnd(fe.sidekit_recipe(fs=fs), delta_order=0, cmvn=False))
+        f_p = fe._cached(("chunk-plp-raw", fs), lambda: fe.PlpFrontEnd(fe.plp_recipe(fs=fs), delta_order=0, cmvn=False))
+        a, offs, _ = f_m.extract(chunks)
+        b, offs_p, _ = f_p.extract(chunks)
+        assert np.array_equal(offs, offs_p)
+        both = torch.cat([a, b], dim=1).contiguous()
+        feats = torch.empty_like(both)
+        d_off = torch.as_tensor(offs, device=both.device)
+        if both.numel():
+            _lib.check(_lib.load().ssp_cmvn(_lib.ptr(both), _lib.ptr(d_off), len(offs) - 1, both.shape[1], _lib.ptr(feats),
+                                            _lib.stream_ptr()), "ssp_cmvn")
+    else:
+        raise NameError(feature_type)
+    host = feats.cpu().numpy()
+    return [host[offs[i] : offs[i + 1]] for i in range(n_chunks)]
+
+
+def chunk_identify(features, gmms, ubm, precision="tf32"):
+    """``_GMM_test`` of the final GUI (UI/tmp.py:337-349) and ``test`` of the GMM-UBM GUI (UI/GMM_UBM_GUI.py:102-113)
+    for a list of chunk feature matrices: ``pred[j, i] = GMM[i].score(x_j) - UBM.score(x_j)`` in one launch, the GUI's
+    "probability" ``exp(pred.max(1)) / exp(pred).sum(1)`` and the argmax.  Returns ``(pred, prob, decisions)``."""
+    pred, who = identify(features, gmms, ubm, precision=precision)
+    prob = np.exp(pred.max(axis=1)) / np.exp(pred).sum(axis=1)
+    return pred, prob, who
+
+
 _SIDE_STREAMS: dict = {}
 
 

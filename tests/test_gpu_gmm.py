@@ -481,3 +481,43 @@ def test_config1_reference_pipeline_at_full_size(golden, config1_corpus, tmp_pat
         assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
         assert acc == 1.0 and "test acc 100.00%" in str(g["printed"])
     assert float(g["min_top2_margin"]) > 100 * 2e-2  # decisions are far from the tolerance
+
+
+@pytest.mark.parametrize("feature_type", ["MFCC", "PLP", "MFCC_PLP"])
+def test_chunked_gui_path_matches_oracle(feature_type):
+    """records() + _GMM_test() of the final GUI (UI/tmp.py:301-349): 1-s chunks -> mfcc / plp / both side by side ->
+    scale -> GMM[i].score - UBM.score -> the GUI's probability and argmax, batched."""
+    from oracle import frontend as ofe
+
+    audio = np.concatenate([synth.synth_utterance(s, 7, 16000 + 2200 * s) for s in range(3)])  # 3.4 s -> 3 chunks
+    feats = ssp.chunk_features(audio, feature_type)
+    assert len(feats) == len(audio) // 16000 == 3
+    want = []
+    for i in range(3):
+        ch = audio[i * 16000 : (i + 1) * 16000]
+        parts = []
+        if "MFCC" in feature_type:
+            parts.append(ofe.sidekit_mfcc(ch)[0])
+        if "PLP" in feature_type:
+            parts.append(ofe.sidekit_plp(ch)[0])
+        want.append(ofe.scale(np.hstack(parts)))
+    for f, w_ in zip(feats, want):
+        assert f.shape == w_.shape == (98, 13 * (2 if feature_type == "MFCC_PLP" else 1))
+        # scale divides by per-column std (PLP columns: ~0.02 .. 0.5)
+        np.testing.assert_allclose(f, w_, rtol=0, atol=5e-4 if feature_type == "MFCC" else 2e-2)
+    d = feats[0].shape[1]
+    models = []
+    for i in range(3):
+        wt, mu, var = synth.synth_ubm(8, d, seed=70 + i, spread=0.7)
+        models.append(ssp.GaussianMixture.from_params(wt, mu, var))
+    wt, mu, var = synth.synth_ubm(8, d, seed=80, spread=0.7)
+    ubm = ssp.GaussianMixture.from_params(wt, mu, var)
+    pred, prob, who = ssp.chunk_identify(feats, models, ubm, precision="fp32")
+    ref = np.array([[ogmm.score(f.astype(np.float64), m.weights_, m.means_, m.covariances_)
+                     - ogmm.score(f.astype(np.float64), ubm.weights_, ubm.means_, ubm.covariances_) for m in models] for f in feats])
+    np.testing.assert_allclose(pred, ref, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(prob, np.exp(ref.max(axis=1)) / np.exp(ref).sum(axis=1), rtol=1e-3)
+    assert (who == ref.argmax(axis=1)).all()
+    assert ssp.chunk_features(audio[:15999], feature_type) == []
+    with pytest.raises(NameError):
+        ssp.chunk_features(audio, "LPCC")
