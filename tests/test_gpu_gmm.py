@@ -477,10 +477,13 @@ def test_config1_reference_pipeline_at_full_size(golden, config1_corpus, tmp_pat
         pickle.dump(sk(g["ubm_w"], g["ubm_mu"], g["ubm_var"]), f)
     for precision in ("fp32", "tf32"):
         acc_tr, acc, pred = ssp.GMM({}, feats, labels, feats, labels, n_components=64, model=True, precision=precision)
-        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=2e-3 if precision == "fp32" else 2e-2)
+        # an LLR is the difference of two scores of magnitude 30 .. 100; the single-pass TF32 kernel is good to 5e-4
+        # relative per score at this model size (K = 64; measured here: 4.4e-4 of the LLR at worst), the FP32 kernel
+        # sees only the front-end's float32 differences
+        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=2e-3 if precision == "fp32" else 5e-2)
         assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
         assert acc == 1.0 and "test acc 100.00%" in str(g["printed"])
-    assert float(g["min_top2_margin"]) > 100 * 2e-2  # decisions are far from the tolerance
+    assert float(g["min_top2_margin"]) > 100 * 5e-2  # decisions are far from the tolerance
 
 
 @pytest.mark.parametrize("feature_type", ["MFCC", "PLP", "MFCC_PLP"])
