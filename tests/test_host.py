@@ -129,6 +129,28 @@ def test_product_never_imports_the_oracle_or_reference():
                 assert "/root/reference" not in text, f
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """The oracle is test infrastructure: outside tests/ only __graft_entry__.py (smoke) and bench.py (CPU baseline /
+    reference arm) may import it; helper scripts under benchmarks/ and profiles/ must not."""
+    allowed = {os.path.join(ROOT, "__graft_entry__.py"), os.path.join(ROOT, "bench.py")}
+    for top in ("benchmarks", "profiles", "include", "speech_signal_processing_b200"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".sh")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+    for f in os.listdir(ROOT):
+        path = os.path.join(ROOT, f)
+        if f.endswith(".py") and path not in allowed:
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", open(path).read(), flags=re.M), f
+    # bench.py: the oracle appears only in the CPU legs (functions whose names start with _cpu_ / run_reference)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    for m in re.finditer(r"^\s*from oracle import", bench, flags=re.M):
+        head = bench[: m.start()]
+        fn = re.findall(r"^def (\w+)", head, flags=re.M)[-1]
+        assert fn.startswith("_cpu_") or fn == "run_reference", fn
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
 

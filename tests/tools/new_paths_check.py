@@ -1,5 +1,5 @@
 """Timing + error margins of the front-end paths added late in round 1 (direct-DFT frame sizes, librosa convention).
-    python benchmarks/new_paths_check.py
+    python tests/tools/new_paths_check.py
 """
 import json
 import os
@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import speech_signal_processing_b200 as ssp  # noqa: E402
 from oracle import frontend as ofe  # noqa: E402  (checker only)
 from speech_signal_processing_b200 import synth  # noqa: E402

@@ -1,8 +1,8 @@
 """CPU probe behind DESIGN.md section 8: how many (frame, component) exponentials of the config-4 scoring are negligible at
 FP32 resolution, and how many 32 x 32 epilogue blocks become skippable after reordering components and frames.
-Oracle features (checker code) on bench-style audio; numpy only.  python benchmarks/probe_pruning_cpu.py"""
+Oracle features (checker code) on bench-style audio; numpy only.  python tests/tools/probe_pruning_cpu.py"""
 import numpy as np, sys, torch, time
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import frontend as ofe
 from speech_signal_processing_b200 import synth
 K,D=1024,39
