@@ -63,14 +63,28 @@ def sidekit_filterbank(fs, nfft, lowfreq, maxfreq, nlogfilt):
     return _area_triangles(edges, nfft, fs, nfft // 2 + 1, drop_last_falling=True)
 
 
+def _talkbox_edges() -> np.ndarray:
+    """The 42 triangle corner frequencies of utils/processing.py:49-63: 13 linear (133.33 Hz + k * 66.67) and 29
+    log-spaced (x 1.0711703) points."""
+    edges = np.zeros(42)
+    edges[:13] = 133.33 + (200.0 / 3.0) * np.arange(13)
+    edges[13:] = edges[12] * 1.0711703 ** np.arange(1, 30)
+    return edges
+
+
+def mfccInitFilterBanks(fs, nfft):
+    """``utils.processing.mfccInitFilterBanks`` (utils/processing.py:42-88): ``(fbank (40, nfft), freqs (42,))`` on the
+    reference's TWO-sided bin grid k*fs/nfft, k < nfft.  A host-side table (it is what :func:`processing_recipe` folds
+    onto nfft/2+1 bins and uploads), not a kernel."""
+    edges = _talkbox_edges()
+    return _area_triangles(edges, int(nfft), fs, int(nfft), drop_last_falling=False), edges
+
+
 def processing_filterbank(fs, nfft):
     """utils/processing.py:42-88 evaluated on ALL nfft bins, then folded onto 0..nfft/2: the
     reference multiplies the two-sided magnitude spectrum (|X[k]| == |X[nfft-k]|) by a filterbank
     whose edges can exceed fs/2 (they do at fs = 8000)."""
-    edges = np.zeros(42)
-    edges[:13] = 133.33 + (200.0 / 3.0) * np.arange(13)
-    edges[13:] = edges[12] * 1.0711703 ** np.arange(1, 30)
-    two_sided = _area_triangles(edges, nfft, fs, nfft, drop_last_falling=False)
+    two_sided = _area_triangles(_talkbox_edges(), nfft, fs, nfft, drop_last_falling=False)
     half = nfft // 2
     fb = two_sided[:, : half + 1].copy()
     mirror = two_sided[:, :half:-1]  # bins nfft-1 ... half+1 fold onto 1 ... (half-1 for even nfft, half for odd)

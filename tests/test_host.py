@@ -36,6 +36,11 @@ def test_recipe_tables_match_oracle(golden):
         np.testing.assert_allclose(folded @ x[:257], two_sided @ x, rtol=1e-12)
     with pytest.raises(NotImplementedError):
         ssp.processing_recipe(16000, 5000, 160)
+    # the drop-in of utils.processing.mfccInitFilterBanks itself (utils/processing.py:42-88), against its own output
+    fb, freqs = ssp.mfccInitFilterBanks(16000, 512)
+    np.testing.assert_allclose(fb, g["fbank_16k_512"], atol=1e-14)
+    np.testing.assert_allclose(freqs, g["freqs_16k_512"], atol=1e-12)
+    np.testing.assert_allclose(ssp.mfccInitFilterBanks(8000, 512)[0], g["fbank_8k_512"], atol=1e-14)
 
 
 @pytest.mark.parametrize("fs,frame_size,step,tag", [(16000, 400, 160, "c"), (8000, 512, 256, "a"), (8000, 255, 100, None)])
