@@ -149,6 +149,8 @@ def identify_pcm(host_pcm, sample_offsets, front_end, speakers, ubm_index=None, 
     n_utts = len(sample_offsets) - 1
     if out is None:
         out = torch.empty(n_utts, dtype=torch.int64, pin_memory=True)
+    if n_utts == 0:
+        return out, 0
     nfr = front_end.frame_counts(np.diff(sample_offsets))
     n_head = split_for_overlap(nfr, head_fraction, min_split_frames)
     cur = torch.cuda.current_stream(dev)
