@@ -196,6 +196,15 @@ rows = torch.arange(hi - lo, dtype=torch.float64)[:, None] + 100.0 * comm.rank
 full = comm.gather_rows(rows, [shard_range(len(x), r, comm.world_size)[1] - shard_range(len(x), r, comm.world_size)[0]
                                for r in range(comm.world_size)])
 assert full.shape[0] == len(x)
+assert full[:, 0].tolist() == list(range(501)) + [100.0 + i for i in range(500)]  # rank order, padding rows dropped
+# uneven shards incl. an empty one (1 speaker on 2 ranks in map_enrol_sharded): rank 1 contributes nothing
+one = [shard_range(1, r, comm.world_size) for r in range(comm.world_size)]
+mine = torch.full((one[comm.rank][1] - one[comm.rank][0], 2, 3), 7.0 + comm.rank, dtype=torch.float64)
+got = comm.gather_rows(mine, [b - a for a, b in one])
+assert got.shape == (1, 2, 3) and float(got.sum()) == 7.0 * 6 + 6.0 * [c for c, (a, b) in enumerate(one) if b > a][0]
+mx = torch.tensor([1.0 + comm.rank, 5.0 - comm.rank])
+comm.allreduce_max(mx)
+assert mx.tolist() == [2.0, 5.0]
 b = torch.tensor([float(comm.rank)])
 comm.broadcast(b, 0)
 assert b.item() == 0.0
