@@ -123,7 +123,10 @@ def config3(scale):
     return {"config": "3: 512-comp UBM EM, 36 M x 39-d frames", "n_frames": n, "ms_per_iteration": ms,
             "frames_per_s": n / (ms * 1e-3), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "lower_bound_monotone": mono,
             "lower_bounds": [round(b, 4) for b in gm.lower_bounds_],
-            "note": "FP32 CUDA-core E-step + statistics (posteriors need FP32-grade logits); tensor-core version is next"}
+            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                         "executed_tflops": 2.0 * 80 * k * (3 + 3 + 2) * n / (ms * 1e-3) / 1e12},
+            "note": "tcgen05 3xTF32 E-step (logits evaluated in both passes: log-sum-exp, then statistics) + TMEM-accumulated "
+                    "statistics GEMM (hi + lo); achieved = algorithmic 8*D*K FLOP per frame, executed = 2*80*K*(3+3+2)"}
 
 
 def config5(scale):
