@@ -56,8 +56,17 @@ def scale(x: np.ndarray) -> np.ndarray:
     mean = x64.mean(axis=0)
     xc = x64 - mean
     std = np.sqrt((xc * xc).mean(axis=0))
+    # _data.py:266-277: a mean that could not be represented exactly leaves a residue; sklearn removes it once more
+    mean_1 = xc.mean(axis=0)
+    if not np.allclose(mean_1, 0):
+        xc = xc - mean_1
     std = np.where(std < 10 * np.finfo(x64.dtype).eps, 1.0, std)
     out = xc / std
+    # _data.py:281-296: ... and again after the division when the deviation itself is at rounding level (a column that
+    # is constant up to the inexact mean comes out as 0, not as +-1)
+    mean_2 = out.mean(axis=0)
+    if not np.allclose(mean_2, 0):
+        out = out - mean_2
     return out.astype(x.dtype if x.dtype.kind == "f" else np.float64)
 
 

@@ -272,3 +272,69 @@ def test_config1_reference_run_is_reproduced_by_the_oracle(golden, config1_corpu
     np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=5e-4)
     assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
     assert (pred.argmax(axis=1) == np.asarray(y_te)).mean() == 1.0 and "test acc 100.00%" in str(g["printed"])
+
+
+def test_sidekit_restatement_known_answers():
+    """Properties the sidekit restatement must have whatever the absent package's exact code is (parity unpinned):
+    the published conventions of SURVEY 8(c) -- mel-spaced area-normalised triangles between 100 Hz and 8 kHz, a pure
+    tone lands in the band whose centre is nearest, per-frame pre-emphasis, frame energy of the un-windowed frame."""
+    fb, edges = ofe.sidekit_trfbank(16000, 512, 100, 8000, 0, 24)
+    assert fb.shape == (24, 257) and edges.shape == (26,)
+    assert edges[0] == pytest.approx(100.0) and edges[-1] == pytest.approx(8000.0)
+    np.testing.assert_allclose(np.diff(ofe.hz2mel(edges)), np.diff(ofe.hz2mel(edges))[0], rtol=1e-9)  # equal mel steps
+    assert ofe.hz2mel(1000.0) == pytest.approx(2595.0 * np.log10(1.0 + 1000.0 / 700.0))  # report/GMM_UBM.pdf p.4
+    assert (fb >= 0).all() and (fb.sum(axis=1) > 0).all()
+    peak_bin = fb.argmax(axis=1)
+    assert (np.diff(peak_bin) > 0).all()                                   # bands ordered in frequency
+    centre_bin = np.floor(edges[1:-1] * 512 / 16000).astype(int)
+    assert (np.abs(peak_bin - centre_bin) <= 1).all()                      # each triangle peaks at its centre bin
+    # pure tones: the strongest band is one whose passband contains the tone
+    t = np.arange(16000) / 16000.0
+    for f0 in (300.0, 1000.0, 2500.0, 6000.0):
+        tone = np.round(8000.0 * np.sin(2 * np.pi * f0 * t)).astype(np.int16)
+        framed = ofe.sidekit_frames(tone.astype(np.float64), 400, 160)
+        framed = framed - 0.97 * np.concatenate([framed[:, :1], framed[:, :-1]], axis=1)
+        spec = np.abs(np.fft.rfft(framed * np.hanning(400), 512, axis=1)) ** 2
+        band = int((spec @ fb.T).mean(axis=0).argmax())
+        assert edges[band] < f0 < edges[band + 2], (f0, band)
+    # frame log-energy is that of the pre-emphasised, un-windowed frame; first sample uses itself as predecessor
+    sig = np.arange(1, 801, dtype=np.float64)
+    out = ofe.sidekit_mfcc(sig)
+    fr = ofe.sidekit_frames(sig, 400, 160)
+    pre = fr - 0.97 * np.concatenate([fr[:, :1], fr[:, :-1]], axis=1)
+    np.testing.assert_allclose(out[1], np.log((pre ** 2).sum(axis=1)), rtol=1e-6)
+    assert fr.shape == (3, 400) and fr[1, 0] == 161.0
+    # c0 is dropped: adding a gain changes no cepstrum (log-spectrum offset lives in c0 only)
+    a = ofe.sidekit_mfcc(1000.0 * np.sin(2 * np.pi * 440.0 * t) + 50 * np.cos(2 * np.pi * 3000.0 * t))[0]
+    b = ofe.sidekit_mfcc(4000.0 * np.sin(2 * np.pi * 440.0 * t) + 200 * np.cos(2 * np.pi * 3000.0 * t))[0]
+    np.testing.assert_allclose(a, b, atol=2e-3)
+
+
+def test_delta_and_scale_properties():
+    """GMM_UBM.delta / preprocessing.scale restatements: linearity, constant and ramp inputs, idempotence."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra import numpy as hnp
+    import warnings
+
+    from sklearn import preprocessing
+
+    @settings(max_examples=40, deadline=None, derandomize=True, database=None)
+    @given(hnp.arrays(np.float64, st.tuples(st.integers(1, 40), st.integers(1, 6)), elements=st.floats(-1e3, 1e3)),
+           st.integers(1, 4), st.floats(-5, 5))
+    def prop(x, n, a):
+        d = ofe.delta(x, n)
+        assert d.shape == x.shape
+        np.testing.assert_allclose(ofe.delta(a * x, n), a * d, atol=1e-9 * (1 + np.abs(x).max()))   # homogeneous
+        np.testing.assert_allclose(ofe.delta(x + 3.25, n), d, atol=1e-9 * (1 + np.abs(x).max()))     # offsets vanish
+        s = ofe.scale(x)
+        np.testing.assert_allclose(s.mean(axis=0), 0.0, atol=1e-7)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np.testing.assert_allclose(s, preprocessing.scale(x), atol=1e-9)   # incl. columns constant up to rounding
+
+    prop()
+    ramp = np.arange(30, dtype=np.float64)[:, None] * np.array([[2.0, -0.5]])
+    d = ofe.delta(ramp, 2)
+    np.testing.assert_allclose(d[2:-2], np.tile([[2.0, -0.5]], (26, 1)), atol=1e-12)  # interior = slope
+    np.testing.assert_allclose(d[0], np.array([2.0, -0.5]) * (1 * 1 + 2 * 2) / 10.0, atol=1e-12)  # edge padding: (c1-c0)+2(c2-c0) over 10
