@@ -378,6 +378,12 @@ def run_b200(a):
         peak = peaks["bf16_tflops_sustained"] / 2.0
         peak_note = peak_src + ": bf16_tflops_sustained / 2 -- kind::tf32 MMAs issue at half the bf16 rate"
         bound = "tensor"
+        try:  # a measured TF32 GEMM figure (benchmarks/measure_tf32_peak.py) beats the derived one
+            with open(os.path.join(ROOT, "profiles", "tf32_peak.json")) as f:
+                peak = float(json.load(f)["tf32_tflops_sustained"])
+            peak_note = "measured (profiles/tf32_peak.json): torch.matmul TF32 8192^3 sustained"
+        except (OSError, KeyError, ValueError):
+            pass
     else:
         peak, peak_note, bound = 70.0, "nominal FP32 CUDA-core FMA peak (no measured figure)", "tensor"
     kernel = "gmm_score_sv_kernel" if shared else ("gmm_score_tc_kernel" if a.precision == "tf32" else "gmm_score_simt_kernel")
