@@ -34,8 +34,9 @@ What is restated, and how each piece is pinned
   (imported, never called, at /root/reference/GMM_UBM.py:13; BASELINE config 1
   quotes its 26-filter default).  Absent here: **parity unpinned**.
 * ``oracle.frontend.librosa_mfcc`` / ``mfcc_lib`` restate ``librosa.feature.mfcc`` as /root/reference/MFCC_DTW.py:27-30
-  calls it.  librosa is absent and un-pinned: **parity unpinned**; cross-checked (not pinned) against torchaudio's
-  independent implementation of the same conventions in ``tests/test_oracle.py``.
+  calls it.  librosa is absent and un-pinned: **parity unpinned**; cross-checked (not pinned) against two
+  independent implementations of the same conventions (torchaudio's MFCC transform, ``transformers.audio_utils``) in
+  ``tests/test_oracle.py``.
 * ``oracle.gmm.map_adapt`` is Reynolds/Quatieri/Dunn (2000) mean-only (and full)
   relevance MAP.  The reference has NO MAP code: **parity unpinned**,
   defined by formula.

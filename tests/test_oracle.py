@@ -361,3 +361,20 @@ def test_fixtures_regenerate_from_the_unmodified_reference(golden):
         np.testing.assert_array_equal(gu.delta(d[f"x{i}"], int(d[f"n{i}"])), d[f"d{i}"])
     with pytest.raises(ValueError):
         gu.delta(d["x0"], 0)  # GMM_UBM.py:59-60
+
+
+def test_librosa_restatement_agrees_with_transformers_audio_utils():
+    """Second independent cross-check of the librosa restatement (parity unpinned): ``transformers.audio_utils`` is a
+    numpy re-implementation written to reproduce librosa's mel filters and dB spectrogram."""
+    au = pytest.importorskip("transformers.audio_utils")
+    from speech_signal_processing_b200 import synth
+
+    mf = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=128, min_frequency=0.0, max_frequency=4000.0,
+                            sampling_rate=8000, norm="slaney", mel_scale="slaney")
+    np.testing.assert_allclose(mf.T, ofe.librosa_mel_filters(8000, 2048), atol=1e-13)
+    for n in (12000, 3000):
+        sig = synth.synth_utterance(3, n % 5, n, 8000).astype(np.float64)
+        db = au.spectrogram(sig, au.window_function(2048, "hann", periodic=True), frame_length=2048, hop_length=512,
+                            fft_length=2048, power=2.0, center=True, pad_mode="reflect", mel_filters=mf, log_mel="dB",
+                            reference=1.0, min_value=1e-10, db_range=80.0)
+        np.testing.assert_allclose(ofe.dct2_ortho_matrix(13, 128) @ db, ofe.librosa_mfcc(sig), atol=1e-4)
