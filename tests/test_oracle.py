@@ -378,3 +378,21 @@ def test_librosa_restatement_agrees_with_transformers_audio_utils():
                             fft_length=2048, power=2.0, center=True, pad_mode="reflect", mel_filters=mf, log_mel="dB",
                             reference=1.0, min_value=1e-10, db_range=80.0)
         np.testing.assert_allclose(ofe.dct2_ortho_matrix(13, 128) @ db, ofe.librosa_mfcc(sig), atol=1e-4)
+
+
+def test_sidekit_filterbank_against_an_independent_htk_mel_implementation():
+    """The sidekit ``trfbank`` restatement (parity unpinned) against ``transformers.audio_utils.mel_filter_bank`` with
+    the HTK mel scale and area normalisation: identical weights (1e-16) wherever the restatement is non-zero; the only
+    difference is the quirk SURVEY 8(c) attributes to SIDEKIT -- the last bin of each falling edge is dropped
+    (``rid[:-1]``), one bin per filter except the last, whose edge ends on the Nyquist bin."""
+    au = pytest.importorskip("transformers.audio_utils")
+    fb, _ = ofe.sidekit_trfbank(16000, 512, 100, 8000, 0, 24)
+    mf = au.mel_filter_bank(num_frequency_bins=257, num_mel_filters=24, min_frequency=100.0, max_frequency=8000.0,
+                            sampling_rate=16000, norm="slaney", mel_scale="htk").T
+    nz = fb > 0
+    np.testing.assert_allclose(fb[nz], mf[nz], atol=1e-15)
+    extra = np.argwhere(np.abs(fb - mf) > 1e-12)
+    assert all(fb[i, j] == 0.0 for i, j in extra)
+    assert np.bincount(extra[:, 0], minlength=24).tolist() == [1] * 23 + [0]
+    for i, j in extra:  # the dropped bin is the last one of the falling edge
+        assert j == np.nonzero(mf[i])[0][-1]
