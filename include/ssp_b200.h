@@ -3,8 +3,8 @@
  *
  * The reference (kleinzcy/speech_signal_processing) is pure Python; its "plugin API" for
  * this path is a set of module-level Python names.  Each entry point below
- * names the reference call it replaces; speech_signal_processing_b200/*.py binds them with
- * ctypes and re-exposes the reference's own signatures (mfcc, MFCC, delta, scale,
+ * names the reference call it replaces; the modules of speech_signal_processing_b200 bind them with
+ * ctypes and re-expose the reference's own signatures (mfcc, MFCC, delta, scale,
  * GaussianMixture.fit/score, GMM()).  See INTEGRATION.md for the reference-side binding.
  *
  * Conventions

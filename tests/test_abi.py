@@ -76,3 +76,36 @@ def test_null_arguments_fail_without_touching_the_gpu(lib):
     assert lib.ssp_gmm_pack_models(None, None, None, C.byref(d), None, None) == -1
     assert b"null" in lib.ssp_last_error()
     assert lib.ssp_delta(None, 10, 13, 0, None, None) == -1
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/ssp_b200.h must compile as C99 (no C++ or torch types in the signatures) and a
+    C translation unit that calls the host-only entry points must link against the library."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_abi.c"
+    src.write_text(
+        '#include "ssp_b200.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "  ssp_frontend_cfg c = {400, 160, 512, 24, 13, 0, 1, 0.97f, 0, 1.0f, 0, 0.0f, 0.0f, 1, 2, 2, 1, 0};\n"
+        "  ssp_gmm_dims d = {1001, 1024, 39};\n"
+        '  printf("%d %lld %lld\\n", ssp_abi_version(), (long long)ssp_frontend_num_frames(&c, 48000),\n'
+        "         (long long)(ssp_gmm_pack_bytes(&d) > 0));\n"
+        "  return ssp_frontend_batch(0, 0, 1, &c, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0) == SSP_EINVAL ? 0 : 1;\n"
+        "}\n")
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    from speech_signal_processing_b200 import _lib
+
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["1", "298", "1"]
