@@ -10,7 +10,6 @@ import pytest
 
 import speech_signal_processing_b200 as ssp
 from oracle import frontend as ofe
-from oracle import gmm as ogmm
 from speech_signal_processing_b200 import dist as sdist
 from speech_signal_processing_b200 import frontend as pfe
 from speech_signal_processing_b200 import synth
