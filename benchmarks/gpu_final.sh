@@ -1,5 +1,7 @@
 # Round-end check on one B200 within a small GPU budget: parity tests, the bench line (with the CPU baseline leg),
 # smoke(), the ncu launch list of the bench command.
+# Budget note (round 1): this script ran 60 s on the box and was charged 177 s of the gpurun budget (acquire + push +
+# overheads count); pytest-only calls ran 16-20 s and were charged 37-67 s; a 2-GPU call of 35 s was charged 127 s.
 cd $GRAFT_REPO_ROOT
 TAG=${1:-r1j}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv,noheader
