@@ -109,3 +109,26 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert out.stdout.split() == ["1", "298", "1"]
+
+
+def test_host_framing_rule_equals_the_abi_rule(lib):
+    """FrontEnd.frame_counts (vectorised, used to build frame_offsets) == ssp_frontend_num_frames for every framing mode
+    (sidekit / psf / processing.py / librosa centred, reflect and zero padded)."""
+    import numpy as np
+
+    import speech_signal_processing_b200 as ssp
+    from speech_signal_processing_b200 import _lib
+
+    rs = np.random.RandomState(0)
+    lens = np.concatenate([np.arange(0, 1300), rs.randint(0, 200000, size=500)])
+    recipes = [ssp.sidekit_recipe(), ssp.psf_recipe(), ssp.processing_recipe(16000, 400, 160), ssp.processing_recipe(8000, 512, 256),
+               ssp.librosa_recipe(), ssp.librosa_recipe(pad_mode="constant", n_fft=512, hop_length=128), ssp.librosa_recipe(center=False)]
+    for r in recipes:
+        fe = ssp.FrontEnd.__new__(ssp.FrontEnd)   # host-side rule only: no device needed
+        fe.recipe = r
+        got = fe.frame_counts(lens)
+        cfg = _lib.FrontendCfg(r.frame_len, r.frame_shift, r.nfft, r.fbank.shape[0], r.dct.shape[0], r.framing, r.preemph_mode,
+                               r.preemph, r.spec_type, r.spec_scale, r.log_type, r.log_add, r.log_zero_floor, r.energy_mode, 0, 2, 0, 0)
+        want = np.array([lib.ssp_frontend_num_frames(C.byref(cfg), int(n)) for n in lens])
+        assert (got == want).all(), (r.name, r.framing, lens[np.nonzero(got != want)[0][:5]])
+        assert want[lens > 4096].min() > 0   # the configuration was accepted (0 would mean "rejected")
