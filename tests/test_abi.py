@@ -132,3 +132,5 @@ def test_host_framing_rule_equals_the_abi_rule(lib):
         want = np.array([lib.ssp_frontend_num_frames(C.byref(cfg), int(n)) for n in lens])
         assert (got == want).all(), (r.name, r.framing, lens[np.nonzero(got != want)[0][:5]])
         assert want[lens > 4096].min() > 0   # the configuration was accepted (0 would mean "rejected")
+        # the fused single-pass kernel holds a 3 s utterance of every convention (librosa keeps 128 bands per frame)
+        assert lib.ssp_frontend_max_frames(C.byref(cfg)) >= max(300, int(fe.frame_counts([3 * 16000])[0]) if r.name != "librosa" else 100)
