@@ -32,10 +32,12 @@ extern "C" {
 
 int ssp_abi_version(void);
 const char* ssp_last_error(void);
-/* Names of the kernels this library has launched since load (comma separated) and how many
- * launches in total; evidence for bench.py's "gpu_launches". */
+/* How many kernels this library has launched since load / the last reset, and which:
+ * "kernel_name:count,kernel_name:count,..." (valid until the next call); evidence for bench.py's
+ * "gpu_launches" and for the tests that assert WHICH kernel served a call. */
 int64_t ssp_launch_count(void);
 void ssp_reset_launch_count(void);
+const char* ssp_launch_log(void);
 
 /* ------------------------------------------------------------------------------------------
  * Front-end: PCM -> cepstra (+delta, +delta-delta, +per-utterance CMVN) in ONE kernel.
@@ -191,7 +193,12 @@ int ssp_gmm_pack_models(const double* weights, const double* means, const double
                         const ssp_gmm_dims* dims, void* out_pack, void* stream);
 
 #define SSP_PREC_FP32 0 /* CUDA-core FP32 FMA, ~1e-7 relative                              */
-#define SSP_PREC_TF32 1 /* tcgen05 kind::tf32 MMA, FP32 accumulate in TMEM, ~3e-5 relative */
+#define SSP_PREC_TF32 1 /* tcgen05 kind::tf32 MMA, FP32 accumulate in TMEM: one pass, operands rounded to TF32;
+                           1e-4 relative on the utterance score at K >= 512 components and ~300 frames          */
+#define SSP_PREC_TF32X2 2 /* two passes, A.B_hi + A.B_lo: the model operand exact to 2^-22 (its rounding is the
+                             systematic part of the one-pass error), frames still rounded                       */
+#define SSP_PREC_TF32X3 3 /* three passes (3xTF32), A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: FP32-grade, ~5e-7 relative;
+                             what LLRs of small models / short utterances need (abs 1e-3)                       */
 
 /*
  * scores[u, m] = mean over the frames of utterance u of log sum_c w_c N(x_t; mu_mc, var_mc)
@@ -243,8 +250,9 @@ int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs
                   int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n,
                   double* out_f, double* out_s, double* out_loglik, void* workspace, int64_t workspace_bytes,
                   void* stream);
-/* Scratch bytes ssp_gmm_stats needs for these dims (0: none).  The tensor-core path (3xTF32 tcgen05, D <= 39)
- * keeps per-component-tile log-sum-exp partials there; without enough workspace the FP32 CUDA-core path runs. */
+/* Scratch bytes ssp_gmm_stats needs for these dims (0: none).  The tensor-core path (tcgen05, D <= 39) keeps its
+ * operand images and per-component-tile log-sum-exp partials there; a NULL or short workspace is SSP_EINVAL (the FP32
+ * CUDA-core kernels serve D > 39 only, never as a silent fallback). */
 int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames);
 
 /*

@@ -6,6 +6,7 @@ when a kernel is requested, the call raises.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
@@ -13,6 +14,8 @@ LIB_PATH = os.environ.get("SSP_B200_LIB") or os.path.join(PKG, "libssp_b200.so")
 
 PREC_FP32 = 0
 PREC_TF32 = 1
+PREC_TF32X2 = 2
+PREC_TF32X3 = 3
 
 
 class SspError(RuntimeError):
@@ -48,6 +51,7 @@ PROTOTYPES = {
     "ssp_last_error": (C.c_char_p, []),
     "ssp_launch_count": (_I64, []),
     "ssp_reset_launch_count": (None, []),
+    "ssp_launch_log": (C.c_char_p, []),
     "ssp_frontend_num_frames": (_I64, [C.POINTER(FrontendCfg), _I64]),
     "ssp_frontend_max_frames": (_I64, [C.POINTER(FrontendCfg)]),
     "ssp_frontend_batch": (C.c_int, [_P, _P, _I64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
@@ -112,6 +116,18 @@ def require_cuda():
     return torch
 
 
+def on_device(fn):
+    """Method decorator: run with ``self.device`` as the current CUDA device, so that the kernels launch in that
+    device's context on ITS current stream (``stream_ptr``) whatever device the caller had selected."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        import torch
+
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 def ptr(t) -> int:
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else t.data_ptr()
@@ -125,3 +141,9 @@ def stream_ptr() -> int:
 
 def launch_count() -> int:
     return int(load().ssp_launch_count())
+
+
+def launch_log() -> dict:
+    """{kernel name: launches} since the last ``ssp_reset_launch_count``."""
+    text = load().ssp_launch_log().decode()
+    return {k: int(v) for k, v in (item.rsplit(":", 1) for item in text.split(",") if item)}

@@ -11,6 +11,12 @@ namespace ssp {
 
 static thread_local char g_err[1024] = "";
 static std::atomic<int64_t> g_launches{0};
+// per-kernel launch counts since the last reset (names are string literals: compared by content, few entries)
+static std::mutex g_log_mu;
+static const char* g_log_name[64];
+static int64_t g_log_count[64];
+static int g_log_n = 0;
+static char g_log_text[4096];
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,14 +24,33 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launch(const char* name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_log_mu);
+  for (int i = 0; i < g_log_n; ++i)
+    if (g_log_name[i] == name || strcmp(g_log_name[i], name) == 0) { ++g_log_count[i]; return; }
+  if (g_log_n < 64) { g_log_name[g_log_n] = name; g_log_count[g_log_n++] = 1; }
+}
 
 }  // namespace ssp
 
 extern "C" int ssp_abi_version(void) { return SSP_ABI_VERSION; }
 extern "C" const char* ssp_last_error(void) { return ssp::g_err; }
 extern "C" int64_t ssp_launch_count(void) { return ssp::g_launches.load(); }
-extern "C" void ssp_reset_launch_count(void) { ssp::g_launches.store(0); }
+extern "C" void ssp_reset_launch_count(void) {
+  ssp::g_launches.store(0);
+  std::lock_guard<std::mutex> lk(ssp::g_log_mu);
+  ssp::g_log_n = 0;
+}
+extern "C" const char* ssp_launch_log(void) {
+  std::lock_guard<std::mutex> lk(ssp::g_log_mu);
+  size_t o = 0;
+  ssp::g_log_text[0] = 0;
+  for (int i = 0; i < ssp::g_log_n && o + 128 < sizeof(ssp::g_log_text); ++i)
+    o += snprintf(ssp::g_log_text + o, sizeof(ssp::g_log_text) - o, "%s%s:%lld", i ? "," : "", ssp::g_log_name[i],
+                  (long long)ssp::g_log_count[i]);
+  return ssp::g_log_text;
+}
 
 extern "C" int64_t ssp_gmm_pack_bytes(const ssp_gmm_dims* dims) {
   ssp::PackLayout L;
@@ -53,8 +78,10 @@ extern "C" int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, i
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == SSP_PREC_FP32)
     return ssp::launch_score_simt(feats, frame_offsets, n_utts, total_frames, pack, L, true, out_scores, out_frame_lse, st);
-  if (precision == SSP_PREC_TF32)
-    return ssp::launch_score_tc(feats, frame_offsets, n_utts, total_frames, pack, L, true, out_scores, out_frame_lse, st);
+  if (precision == SSP_PREC_TF32 || precision == SSP_PREC_TF32X2 || precision == SSP_PREC_TF32X3)
+    return ssp::launch_score_tc(feats, frame_offsets, n_utts, total_frames, pack, L,
+                                precision == SSP_PREC_TF32 ? 1 : precision == SSP_PREC_TF32X2 ? 2 : 3, true, out_scores,
+                                out_frame_lse, st);
   SSP_REQUIRE(false, "ssp_gmm_score: unknown precision %d", precision);
 }
 
@@ -96,14 +123,15 @@ extern "C" int ssp_gmm_score_shared(const float* feats, const int64_t* frame_off
                               workspace, (cudaStream_t)stream);
 }
 
-static bool stats_use_tc(const ssp::PackLayout& L, int64_t total_frames, int64_t workspace_bytes, const void* workspace) {
-  static int impl = -1;  // SSP_STATS_IMPL=simt forces the FP32 CUDA-core kernels (A/B testing)
+// The tensor-core kernels serve every feature width they support (D <= 39); the FP32 CUDA-core kernels are the
+// documented path for wider features only (and SSP_STATS_IMPL=simt, an explicit A/B switch).
+static bool stats_want_tc(const ssp::PackLayout& L) {
+  static int impl = -1;
   if (impl < 0) {
     const char* e = getenv("SSP_STATS_IMPL");
     impl = (e && strcmp(e, "simt") == 0) ? 0 : 1;
   }
-  return impl == 1 && ssp::stats_tc_supported(L) && workspace &&
-         workspace_bytes >= ssp::stats_tc_workspace_bytes(L, total_frames);
+  return impl == 1 && ssp::stats_tc_supported(L);
 }
 
 extern "C" int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames) {
@@ -122,10 +150,16 @@ extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int
   SSP_REQUIRE(n_segs >= 0 && total_frames >= 0, "ssp_gmm_stats: negative size");
   if (n_segs == 0) return SSP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (stats_use_tc(L, total_frames, workspace_bytes, workspace))
+  if (stats_want_tc(L)) {
+    // no silent 10x slower path: a short workspace is the caller's error
+    const int64_t need = ssp::stats_tc_workspace_bytes(L, total_frames);
+    SSP_REQUIRE(need == 0 || (workspace && workspace_bytes >= need),
+                "ssp_gmm_stats: workspace of %lld bytes, the tensor-core path needs %lld (ssp_gmm_stats_workspace_bytes)",
+                (long long)(workspace ? workspace_bytes : 0), (long long)need);
     return ssp::launch_stats_tc(feats, seg_offsets, n_segs, total_frames, pack, L, frame_lse, out_n, out_f, out_s, out_loglik,
                                 workspace, st);
-  // FP32 CUDA-core path.  pass 1: per-frame log-likelihood and the per-segment sum of frame log-likelihoods (the EM
+  }
+  // FP32 CUDA-core path (D > 39).  pass 1: per-frame log-likelihood and the per-segment sum of frame log-likelihoods (the EM
   // lower bound numerator, sklearn _base.py:558); pass 2: posteriors and N/F/S
   int rc = ssp::launch_score_simt(feats, seg_offsets, n_segs, total_frames, pack, L, false, out_loglik, frame_lse, st);
   if (rc != SSP_OK) return rc;

@@ -53,7 +53,7 @@ struct PackLayout {
   int Kp;  // K rounded up to kTileN (padded components have cst = -1e30, zero rows)
   int DP;  // D padded for the CUDA-core kernels: 16, 32, 40, 64 or 80
   int KD;  // contraction length of the tensor kernel: roundup(2D + 2, 8)
-  size_t off_ab, off_cst, off_tile, off_tile_lo, bytes;  // off_tile_lo == 0: no residual tiles (n_models > 1)
+  size_t off_ab, off_cst, off_tile, off_tile_lo, bytes;
   size_t tile_floats() const { return (size_t)kTileN * KD; }
 };
 
@@ -105,12 +105,9 @@ inline bool make_layout(const ssp_gmm_dims* dims, PackLayout* L) {
   o = up(o + (size_t)L->n_models * L->Kp * sizeof(float));
   L->off_tile = o;
   o = up(o + (size_t)L->n_models * L->Kp * L->KD * sizeof(float));
-  // residual ("lo") tiles for the 3xTF32 EM kernels: only single-model packs (the UBM) carry them
-  L->off_tile_lo = 0;
-  if (L->n_models == 1) {
-    L->off_tile_lo = o;
-    o = up(o + (size_t)L->Kp * L->KD * sizeof(float));
-  }
+  // residual ("lo") tiles: B = hi + lo to ~2^-22 -- the 3xTF32 EM kernels and the 2- / 3-pass scoring rungs
+  L->off_tile_lo = o;
+  o = up(o + (size_t)L->n_models * L->Kp * L->KD * sizeof(float));
   L->bytes = o;
   return true;
 }
@@ -162,7 +159,7 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
 int launch_score_simt(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
                       const PackLayout& L, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
 int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
-                    const PackLayout& L, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
+                    const PackLayout& L, int parts, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
 int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames, const void* pack,
                     const PackLayout& L, float* frame_lse, double* out_n, double* out_f, double* out_s, double* out_loglik,
                     void* workspace, cudaStream_t st);

@@ -30,14 +30,18 @@ namespace ssp {
 
 namespace tc {
 constexpr int BM = 128;      // rows per accumulator (TMEM lanes)
-constexpr int MB = 2;        // row blocks per unit
-constexpr int UNIT = BM * MB;
 constexpr int BN = kTileN;   // components per tile
 constexpr int NSTAGE = 3;
 constexpr int NSLOT = 4;     // TMEM accumulator slots (BN fp32 columns each) = all 512 columns
-constexpr int EPI_WARPS = 16;  // 4 per SM sub-partition: two row blocks x two 64-column halves x four lane quadrants
-constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int MAX_KD = 80;
+// Precision rungs (SURVEY section 7 ladder), all FP32 accumulation in TMEM:
+//   NPARTS 1: A_hi.B_hi                       single-pass TF32, 1e-4 relative at the named workloads (K >= 512)
+//   NPARTS 2: + A_hi.B_lo                     model side exact to 2^-22 (the systematic part of the error)
+//   NPARTS 3: + A_lo.B_hi                     FP32-grade (3xTF32): frame side split as well
+// MB = row blocks of 128 frames per unit: 2 (16 epilogue warps: 4 per SM sub-partition = two row blocks x two 64-column
+// halves x four lane quadrants), or 1 for the 3-part rung, whose A_lo operand takes the second row block's shared
+// memory (8 epilogue warps).
+constexpr int threads_of(int mb) { return 64 + 8 * mb * 32; }
 // Measured on B200 under the 1 kW cap (10k utts x 1001 models): pairs 0/2/4/6/8 -> 523/539/526/496/486 TFLOP/s.
 // The kernel is power-bound, not pipe-bound: a MUFU ex2 costs less energy than the ~7 FMA-pipe instructions that
 // replace it, so only a small share is worth moving.
@@ -118,19 +122,23 @@ struct Args {
   const int64_t* offsets;
   int64_t n_utts, total_frames;
   const float* tiles;  // [n_models][Kp/BN][KD/4][BN] float4 images
+  const float* tiles_lo;  // residual images (same layout), parts 2 and 3
   int n_models, tiles_per_model, D, KD;
   int normalize;
   double* scores;
   float* frame_lse;
 };
 
-template <int kPolyPairs>
-__global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) {
+template <int kPolyPairs, int MB, int NPARTS>
+__global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const Args a) {
+  static_assert(NPARTS >= 1 && NPARTS <= 3 && (MB == 1 || MB == 2) && (NPARTS < 3 || MB == 1), "see the rung table");
+  constexpr int UNIT = BM * MB, EPI_WARPS = 8 * MB;
+  constexpr int A_IMAGES = MB * (NPARTS == 3 ? 2 : 1);  // hi images of every row block, then the lo images
   extern __shared__ __align__(1024) unsigned char smem[];
   const int KD = a.KD;
   const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
-  float* sA = reinterpret_cast<float*>(smem);                     // [MB][KC][BM][4]
-  unsigned char* sB = smem + (size_t)MB * tile_bytes;             // [NSTAGE][KC][BN][4]
+  float* sA = reinterpret_cast<float*>(smem);                     // [A_IMAGES][KC][BM][4]
+  unsigned char* sB = smem + (size_t)A_IMAGES * tile_bytes;       // [NSTAGE][KC][BN][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NSTAGE * tile_bytes);
   uint64_t* b_full = bars;
   uint64_t* b_empty = bars + NSTAGE;
@@ -169,14 +177,18 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
     // ===================== producer: stream every model's tiles, once per unit =====================
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-      for (int t = 0; t < tiles_per_unit; ++t, ++it) {
-        const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-        mbar_wait(b_empty + stage, ph ^ 1u);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(b_full + stage, tile_bytes);
-          bulk_g2s(sB + (size_t)stage * tile_bytes, a.tiles + (size_t)t * tile_floats, tile_bytes, b_full + stage);
+      for (int t = 0; t < tiles_per_unit; ++t) {
+#pragma unroll
+        for (int part = 0; part < (NPARTS >= 2 ? 2 : 1); ++part, ++it) {  // the hi image, then the residual image
+          const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+          mbar_wait(b_empty + stage, ph ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(b_full + stage, tile_bytes);
+            bulk_g2s(sB + (size_t)stage * tile_bytes, (part == 0 ? a.tiles : a.tiles_lo) + (size_t)t * tile_floats, tile_bytes,
+                     b_full + stage);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -191,26 +203,39 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
       mbar_wait(a_full, unit_idx & 1u);
       tc_fence_after();
-      for (int t = 0; t < tiles_per_unit; ++t, ++it) {
+      for (int t = 0; t < tiles_per_unit; ++t) {
         const uint32_t stage = it % NSTAGE, ph = (it / NSTAGE) & 1u;
         mbar_wait(b_full + stage, ph);
+        uint32_t stage_lo = 0;
+        if (NPARTS >= 2) {
+          stage_lo = (it + 1) % NSTAGE;
+          mbar_wait(b_full + stage_lo, ((it + 1) / NSTAGE) & 1u);
+        }
+        it += NPARTS >= 2 ? 2 : 1;
         tc_fence_after();
-        const uint64_t bd0 = b_desc0 + (uint64_t)(stage * tile_units);
+        const uint64_t bd0 = b_desc0 + (uint64_t)(stage * tile_units), bl0 = b_desc0 + (uint64_t)(stage_lo * tile_units);
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb, ++q) {
           const uint32_t slot = q % NSLOT, sph = (q / NSLOT) & 1u;
           mbar_wait(t_empty + slot, sph ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * BN;
-          const uint64_t ad0 = a_desc0 + (uint64_t)(mb * tile_units);
+          const uint64_t ad0 = a_desc0 + (uint64_t)(mb * tile_units), al0 = a_desc0 + (uint64_t)((MB + mb) * tile_units);
           if (elect_one()) {
             tc_mma_tf32(d_tmem, ad0, bd0, kIdesc, 0u);
             for (int k = 1; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), kIdesc, 1u);
+            if (NPARTS >= 2)
+              for (int k = 0; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bl0 + (uint64_t)(k * kstep), kIdesc, 1u);
+            if (NPARTS == 3)
+              for (int k = 0; k < ksteps; ++k) tc_mma_tf32(d_tmem, al0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), kIdesc, 1u);
             tc_commit(t_full + slot);
           }
           __syncwarp();
         }
-        if (elect_one()) tc_commit(b_empty + stage);
+        if (elect_one()) {
+          tc_commit(b_empty + stage);
+          if (NPARTS >= 2) tc_commit(b_empty + stage_lo);
+        }
         __syncwarp();
       }
       if (elect_one()) tc_commit(a_empty);
@@ -221,8 +246,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
     const int etid = tid - 64;                 // 0..511
     const int ew = warp - 2;                   // 0..15
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int g = (ew >> 2) & 1;               // row block whose accumulators this thread reads
-    const int half = ew >> 3;                  // which 64 of the tile's 128 columns
+    const int g = MB == 2 ? (ew >> 2) & 1 : 0;  // row block whose accumulators this thread reads
+    const int half = ew >> (MB == 2 ? 3 : 2);  // which 64 of the tile's 128 columns
     const int row = quad * 32 + lane;          // accumulator row within the row block
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float LN2 = 0.69314718055994530942f;
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
       // ---- A operand: row r of block mb at float index ((mb*KC + j/4)*BM + r)*4 + j%4; two threads per row
       mbar_wait(a_empty, (unit_idx & 1u) ^ 1u);
       {
-        const int brow = etid & (UNIT - 1), part = etid >> 8;
+        const int brow = etid & (UNIT - 1), part = etid / UNIT;
         const int64_t fr = frame0 + brow;
         const bool live = fr < a.total_frames;
         const float* xr = a.feats + fr * a.D;
@@ -240,10 +265,12 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
         const int j0 = part * (KD >> 1), j1 = j0 + (KD >> 1);
         for (int j = j0; j < j1; ++j) {
           float v = 0.f;
-          if (j < a.D) v = live ? rna_tf32(xr[j]) : 0.f;
-          else if (j < 2 * a.D) { float x = live ? xr[j - a.D] : 0.f; v = rna_tf32(x * x); }
+          if (j < a.D) v = live ? xr[j] : 0.f;
+          else if (j < 2 * a.D) { float x = live ? xr[j - a.D] : 0.f; v = x * x; }
           else if (j < 2 * a.D + 2) v = 1.f;
-          dst[(size_t)(j >> 2) * (BM * 4) + (j & 3)] = v;
+          const float hi = rna_tf32(v);
+          dst[(size_t)(j >> 2) * (BM * 4) + (j & 3)] = hi;
+          if (NPARTS == 3) dst[(size_t)MB * tile_floats + (size_t)(j >> 2) * (BM * 4) + (j & 3)] = rna_tf32(v - hi);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(a_full);
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
       for (int model = 0; model < a.n_models; ++model) {
         float s_run = 0.f;
         for (int t = 0; t < a.tiles_per_model; ++t, ++n) {
-          const uint32_t slot = 2u * (n & 1u) + (uint32_t)g, ph = (n >> 1) & 1u;
+          const uint32_t qj = n * MB + (uint32_t)g, slot = qj % NSLOT, ph = (qj / NSLOT) & 1u;
           mbar_wait(t_full + slot, ph);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + slot * BN + half * 64;
@@ -324,12 +351,14 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_tc_kernel(const Args a) 
 }  // namespace tc
 
 int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
-                    const PackLayout& L, bool normalize, double* scores, float* frame_lse, cudaStream_t st) {
+                    const PackLayout& L, int parts, bool normalize, double* scores, float* frame_lse, cudaStream_t st) {
   using namespace tc;
   if (L.KD > MAX_KD) {
     set_error("ssp_gmm_score(tf32): feature dim %d needs a contraction of %d > %d; use SSP_PREC_FP32", L.D, L.KD, MAX_KD);
     return SSP_EUNSUP;
   }
+  SSP_REQUIRE(parts >= 1 && parts <= 3, "ssp_gmm_score: %d TF32 passes requested (1, 2 or 3)", parts);
+  SSP_REQUIRE(parts == 1 || L.off_tile_lo != 0, "ssp_gmm_score: this pack carries no residual tiles");
   SSP_CUDA_OK(cudaMemsetAsync(scores, 0, sizeof(double) * n_utts * L.n_models, st));
   if (total_frames == 0) return SSP_OK;
   Args a;
@@ -338,6 +367,7 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.n_utts = n_utts;
   a.total_frames = total_frames;
   a.tiles = (const float*)((const char*)pack + L.off_tile);
+  a.tiles_lo = (const float*)((const char*)pack + L.off_tile_lo);
   a.n_models = L.n_models;
   a.tiles_per_model = L.Kp / BN;
   a.D = L.D;
@@ -345,34 +375,41 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.normalize = normalize ? 1 : 0;
   a.scores = scores;
   a.frame_lse = frame_lse;
+  const int mb = parts == 3 ? 1 : 2, unit = BM * mb;
   const size_t tile_bytes = (size_t)BN * L.KD * 4;
-  const size_t smem = (MB + NSTAGE) * tile_bytes + (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 +
-                      2 * MB * BM * sizeof(float2);
+  const size_t smem = (2 + NSTAGE) * tile_bytes + (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 +
+                      2 * mb * BM * sizeof(float2);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     SSP_CUDA_OK(cudaGetDevice(&dev));
     SSP_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int64_t n_units = (total_frames + UNIT - 1) / UNIT;
+  const int64_t n_units = (total_frames + unit - 1) / unit;
   const unsigned grid = (unsigned)(n_units < num_sms ? n_units : num_sms);
-  // share of the exponentials evaluated on the FMA pipe (pairs out of 16 per 32 columns); tuning knob
+  // share of the exponentials evaluated on the FMA pipe (pairs out of 16 per 32 columns); tuning knob of the 1-pass rung
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SSP_TC_POLY_PAIRS");
     poly = e ? atoi(e) : kDefaultPolyPairs;
   }
-#define SSP_TC_LAUNCH(pp)                                                                                              \
-  case pp:                                                                                                             \
-    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    gmm_score_tc_kernel<pp><<<grid, THREADS, smem, st>>>(a);                                                           \
-    break;
-  switch (poly) {
-    SSP_TC_LAUNCH(0) SSP_TC_LAUNCH(2) SSP_TC_LAUNCH(4) SSP_TC_LAUNCH(6) SSP_TC_LAUNCH(8)
+#define SSP_TC_LAUNCH(pp, MBv, NP)                                                                                              \
+  do {                                                                                                                          \
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gmm_score_tc_kernel<pp, MBv, NP><<<grid, threads_of(MBv), smem, st>>>(a);                                                  \
+  } while (0)
+  if (parts == 2) SSP_TC_LAUNCH(kDefaultPolyPairs, 2, 2);
+  else if (parts == 3) SSP_TC_LAUNCH(kDefaultPolyPairs, 1, 3);
+  else switch (poly) {
+    case 0: SSP_TC_LAUNCH(0, 2, 1); break;
+    case 2: SSP_TC_LAUNCH(2, 2, 1); break;
+    case 4: SSP_TC_LAUNCH(4, 2, 1); break;
+    case 6: SSP_TC_LAUNCH(6, 2, 1); break;
+    case 8: SSP_TC_LAUNCH(8, 2, 1); break;
     default: SSP_REQUIRE(false, "SSP_TC_POLY_PAIRS must be 0, 2, 4, 6 or 8 (got %d)", poly);
   }
 #undef SSP_TC_LAUNCH
-  SSP_LAUNCH_CHECK("gmm_score_tc_kernel");
+  SSP_LAUNCH_CHECK(parts == 1 ? "gmm_score_tc_kernel" : parts == 2 ? "gmm_score_tc_kernel<2 passes>" : "gmm_score_tc_kernel<3 passes>");
   return SSP_OK;
 }
 

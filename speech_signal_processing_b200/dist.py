@@ -117,7 +117,7 @@ def map_enrol_sharded(comm: Comm, ubm, speaker_frames, relevance: float = 16.0):
     return sms
 
 
-def identify_sharded(comm: Comm, utts, speakers, ubm=None, precision="tf32"):
+def identify_sharded(comm: Comm, utts, speakers, ubm=None, precision="auto"):
     """Each rank scores its contiguous block of utterances against ALL (replicated) speaker models;
     every rank returns the full (N, S) LLR matrix and decisions."""
     import torch

@@ -334,6 +334,7 @@ class FrontEnd:
             hv[o : o + len(s)] = s.astype(dt, copy=False)
         return host, offs
 
+    @_lib.on_device
     def extract(self, signals, want_log_energy: bool = False):
         """signals: list of 1-D arrays.  Returns (feats (sum T, out_dim) cuda float32,
         frame_offsets np.int64 (n+1,), log_energy cuda float32 | None)."""
@@ -342,6 +343,7 @@ class FrontEnd:
         return self.extract_device(pcm, offs, want_log_energy)
 
     # -- device entry: PCM already resident in HBM --------------------------------------------
+    @_lib.on_device
     def extract_device(self, pcm, sample_offsets: np.ndarray, want_log_energy: bool = False, out=None):
         torch = _lib.require_cuda()
         if pcm.dtype == torch.int16:
@@ -464,6 +466,9 @@ _FRONTENDS: dict = {}
 
 
 def _cached(key, make):
+    """Front-ends of the numpy drop-ins, one per (parameters, CURRENT device): the tables live on a device."""
+    torch = _lib.require_cuda()
+    key = (key, torch.cuda.current_device())
     fe = _FRONTENDS.get(key)
     if fe is None:
         fe = _FRONTENDS[key] = make()
@@ -502,6 +507,7 @@ class PlpFrontEnd:
         up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)  # noqa: E731
         self.t_eql, self.t_idft, self.t_lift = up(ex["eql"]), up(ex["idft"]), up(ex["lift"])
 
+    @_lib.on_device
     def extract(self, signals, want_log_energy: bool = False):
         """Returns (feats (sum T, out_dim) cuda float32, frame_offsets np.int64, log_energy | None)."""
         torch = _lib.require_cuda()
@@ -548,6 +554,7 @@ class MelDbFrontEnd:
         self.top_db = float(ex["top_db"])
         self.t_dct = torch.as_tensor(np.ascontiguousarray(ex["dct"], dtype=np.float32), device=self.device)
 
+    @_lib.on_device
     def extract(self, signals):
         """Returns (ceps (sum T, n_mfcc) cuda float32, frame_offsets np.int64)."""
         torch = _lib.require_cuda()
@@ -635,13 +642,14 @@ def extract_feature(x, y, is_train=False, feature_type="MFCC", delta_order=1, re
     ``train_data[label]`` their per-speaker vertical stack.  ``delta_order=2`` gives the 39-d
     north-star features.
     """
+    # only the default recipes are cached; a caller's Recipe object gets a fresh front-end (caching under id(recipe)
+    # would hand a recycled id the stale tables)
     if feature_type == "PLP":      # GMM_UBM.py:94-99
-        fe = _cached(("xf-plp", id(recipe) if recipe else 0, delta_order),
-                     lambda: PlpFrontEnd(recipe, delta_order=delta_order, delta_n=2, cmvn=True))
+        make = lambda: PlpFrontEnd(recipe, delta_order=delta_order, delta_n=2, cmvn=True)  # noqa: E731
+        fe = make() if recipe is not None else _cached(("xf-plp", delta_order, 2), make)
     elif feature_type == "MFCC":
-        rec = recipe or sidekit_recipe()
-        fe = _cached(("xf", rec.name, id(recipe) if recipe else 0, delta_order),
-                     lambda: FrontEnd(rec, delta_order=delta_order, delta_n=2, cmvn=True))
+        make = lambda: FrontEnd(recipe or sidekit_recipe(), delta_order=delta_order, delta_n=2, cmvn=True)  # noqa: E731
+        fe = make() if recipe is not None else _cached(("xf-sidekit", delta_order, 2), make)
     else:
         raise NameError(feature_type)  # GMM_UBM.py:100-101
     feats, offs, _ = fe.extract(list(x))

@@ -17,7 +17,22 @@ import numpy as np
 
 from . import _lib
 
-PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "tf32x2": _lib.PREC_TF32X2, "tf32x3": _lib.PREC_TF32X3}
+# Below this many components the single-pass TF32 rounding no longer averages out to 1e-4 of the utterance score /
+# 1e-3 of an LLR; "auto" then takes the 3-pass (FP32-grade) tensor rung.
+SINGLE_PASS_MIN_COMPONENTS = 512
+
+
+def resolve_precision(precision: str, n_comp: int, n_feat: int) -> str:
+    """``"auto"`` -> the cheapest rung that keeps LLRs within 1e-3 absolute: tensor cores whenever the contraction
+    fits the tcgen05 tile (2D + 2 <= 80), one TF32 pass for large models, three for small ones."""
+    if precision != "auto":
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)} or 'auto' (got {precision!r})")
+        return precision
+    if 2 * n_feat + 2 > 80:
+        return "fp32"
+    return "tf32" if n_comp >= SINGLE_PASS_MIN_COMPONENTS else "tf32x3"
 
 
 def _as_feats(x, device):
@@ -73,6 +88,7 @@ class ModelSet:
         self.pack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.repack(w, mu, var)
 
+    @_lib.on_device
     def repack(self, w, mu, var):
         """Re-derive the packed operands from (device, float64) parameters -- one tiny kernel."""
         self._params = (w, mu, var)
@@ -80,13 +96,15 @@ class ModelSet:
                                                 _lib.ptr(self.pack), _lib.stream_ptr()), "ssp_gmm_pack_models")
 
     # ---------------------------------------------------------------------------------------
-    def score(self, feats, frame_offsets, precision="tf32", want_frame_lse=False):
-        """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None)."""
+    @_lib.on_device
+    def score(self, feats, frame_offsets, precision="auto", want_frame_lse=False):
+        """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None).
+        ``precision``: "fp32" (CUDA cores), "tf32" / "tf32x2" / "tf32x3" (tcgen05, 1 / 2 / 3 TF32 passes) or "auto"
+        (:func:`resolve_precision`)."""
         torch = _lib.require_cuda()
         frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
         n_utts, total = len(frame_offsets) - 1, int(frame_offsets[-1])
-        if precision == "auto":  # tensor cores whenever the contraction fits the tcgen05 kernel's tile
-            precision = "tf32" if 2 * self.n_feat + 2 <= 80 else "fp32"
+        precision = resolve_precision(precision, self.n_comp, self.n_feat)
         if feats.shape[1] != self.n_feat:
             raise ValueError(f"X has {feats.shape[1]} features, but the models expect {self.n_feat}")
         d_off = torch.as_tensor(frame_offsets, device=self.device)
@@ -99,6 +117,7 @@ class ModelSet:
         self._keep = d_off
         return scores, lse
 
+    @_lib.on_device
     def stats(self, feats, seg_offsets):
         """N (S,K), F (S,K,D), S2 (S,K,D), loglik (S,) float64 cuda, under this (single) model."""
         torch = _lib.require_cuda()
@@ -154,8 +173,9 @@ class SharedModelSet:
         if nbytes <= 0:
             raise ValueError(f"unsupported dims K={self.n_comp} D={self.n_feat} for the shared-variance kernel (need D <= 62)")
         self.pack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.ssp_gmm_pack_shared(_lib.ptr(w), _lib.ptr(var), _lib.ptr(mu), C.byref(self.dims), _lib.ptr(self.pack),
-                                                _lib.stream_ptr()), "ssp_gmm_pack_shared")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ssp_gmm_pack_shared(_lib.ptr(w), _lib.ptr(var), _lib.ptr(mu), C.byref(self.dims),
+                                                    _lib.ptr(self.pack), _lib.stream_ptr()), "ssp_gmm_pack_shared")
         self._params = (w, var, mu)
         self._ws = torch.empty(int(self.lib.ssp_gmm_score_shared_workspace_bytes(C.byref(self.dims))), dtype=torch.uint8,
                                device=self.device)
@@ -169,11 +189,13 @@ class SharedModelSet:
         weights, variances = np.asarray(weights), np.asarray(variances)
         return bool((weights == weights[:1]).all() and (variances == variances[:1]).all())
 
+    @_lib.on_device
     def score(self, feats, frame_offsets, precision="tf32", want_frame_lse=False):
         """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None)."""
         torch = _lib.require_cuda()
         if precision not in ("tf32", "auto"):
-            raise ValueError("the shared-variance kernel computes in TF32; expand to a ModelSet for precision='fp32'")
+            raise ValueError("the shared-variance kernel computes in single-pass TF32; expand() to a ModelSet for the "
+                             "other precisions")
         frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
         n_utts, total = len(frame_offsets) - 1, int(frame_offsets[-1])
         if feats.shape[1] != self.n_feat:
@@ -194,7 +216,7 @@ class SharedModelSet:
         return ModelSet(w[None].expand(self.n_models, -1), mu, var[None].expand(self.n_models, -1, -1), device=self.device)
 
 
-def score_matrix(utts, models, precision="tf32", device=None):
+def score_matrix(utts, models, precision="auto", device=None):
     """``pred[j, i] = models[i].score(utts[j])`` for all pairs in one launch (GMM_UBM.py:182-185,
     191-194 without the Python double loop).  ``models``: list of fitted :class:`GaussianMixture`
     (or anything with ``weights_/means_/covariances_``) or a :class:`ModelSet`.  Returns float64 numpy."""
@@ -287,7 +309,13 @@ class GaussianMixture:
             k, d = ms.n_comp, ms.n_feat
             cnt = torch.tensor([float(feats.shape[0])], dtype=torch.float64, device=feats.device)
             flat = torch.cat([n.reshape(-1), f.reshape(-1), s.reshape(-1), ll.reshape(-1), cnt])
+            timing = getattr(self, "allreduce_events", None)  # bench.py: a list to append (start, end) CUDA events to
+            if timing is not None:
+                timing.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                timing[-1][0].record()
             flat = self.comm.allreduce_sum(flat)
+            if timing is not None:
+                timing[-1][1].record()
             n, f, s = flat[:k].reshape(1, k), flat[k : k + k * d].reshape(1, k, d), flat[k + k * d : k + 2 * k * d].reshape(1, k, d)
             ll, n_total = flat[k + 2 * k * d : k + 2 * k * d + 1], float(flat[-1].item())
         rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), ms.n_comp, ms.n_feat, float(self.reg_covar),
@@ -311,7 +339,10 @@ class GaussianMixture:
             rows = torch.zeros((count, d), dtype=torch.float64, device=feats.device)
             if comm is None or comm.rank == 0:
                 m = int(min(n_frames, max(20 * k, 4096)))
-                sub = feats[torch.as_tensor(rs.choice(n_frames, size=m, replace=False), device=feats.device)].to(torch.float64)
+                # indices WITH replacement: a permutation of all frames (rs.choice(replace=False)) is 288 MB of host
+                # work at 36 M frames, and duplicates among <= 20k of millions of frames are harmless for seeding
+                pick = rs.permutation(n_frames)[:m] if n_frames <= 4 * m else rs.randint(n_frames, size=m)
+                sub = feats[torch.as_tensor(pick, device=feats.device)].to(torch.float64)
                 u = torch.as_tensor(rs.uniform(size=count), device=feats.device)
                 if avoid is None:
                     rows[0] = sub[int(rs.randint(m))]
@@ -347,10 +378,17 @@ class GaussianMixture:
             rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), k, d, float(self.reg_covar), float(nk_eps),
                                       _lib.ptr(w), _lib.ptr(mu), _lib.ptr(var), _lib.stream_ptr())
             _lib.check(rc, "ssp_gmm_mstep")
+            empty = (n[0] < 0.5).nonzero().flatten()
             if it == iters:
+                # clusters still empty after the last Lloyd step would enter EM with mean 0 / var reg_covar; sklearn's
+                # KMeans relocates them instead -- give each a frame far from every centre and the global variance
+                if empty.numel():
+                    mu[0, empty] = seed_rows(int(empty.numel()), avoid=mu[0])
+                    var[0, empty] = gvar
+                    w[0, empty] = 1.0 / n_frames if comm is None else 1.0 / float(cnt.item())
+                    w /= w.sum()
                 break
             w.fill_(1.0 / k)
-            empty = (n[0] < 0.5).nonzero().flatten()
             if empty.numel():
                 mu[0, empty] = seed_rows(int(empty.numel()), avoid=mu[0])
 

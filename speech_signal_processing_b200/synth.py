@@ -100,3 +100,73 @@ def synth_features_torch(n_frames: int, d: int, mu_spk, var, labels_per_frame, s
     m = mu_spk[labels_per_frame, comp].to(torch.float32)
     s = var[comp].to(torch.float32).sqrt()
     return (m + s * noise).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Counter-based torch generator: the SAME audio on any device (bench.py: GPU arm, CPU arm, oracle check)
+# ------------------------------------------------------------------------------------------------
+def _hash_u32(x):
+    """Integer hash of an int64 tensor -> values in [0, 2^32) (int64).  Only integer ops that are exact and identical
+    on CPU and CUDA; intermediate products stay below 2^63."""
+    x = x & 0xFFFFFFFF
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+    return (x ^ (x >> 16)) & 0xFFFFFFFF
+
+
+def _hash_uniform(x):
+    """[0, 1) float32 from integer keys."""
+    return _hash_u32(x).to(dtype=_torch().float32) * (1.0 / 4294967296.0)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+N_VOWELS, N_HARM, SEG_SAMPLES = 5, 12, 1600
+
+
+def synth_pcm_torch(speakers, utts, n_samples: int, device, fs: int = 16000):
+    """int16 PCM (n, n_samples) for utterance ``utts[i]`` of speaker ``speakers[i]`` (int64 tensors or sequences).
+
+    Voiced-speech-like and speaker-discriminative AFTER per-utterance CMVN: every speaker has a pitch and an inventory
+    of N_VOWELS two-formant spectral envelopes; an utterance hops between them every 100 ms in a hash-chosen order, so
+    the spread of the cepstra around the utterance mean is the speaker's own.  A pure function of (speaker, utt, sample
+    index): integer hashes instead of an RNG stream, so any device, batch split or process regenerates the same
+    samples (up to the last ulp of sin() before the int16 rounding).  RMS ~3000, never digital silence."""
+    torch = _torch()
+    spk = torch.as_tensor(speakers, dtype=torch.int64, device=device).reshape(-1)
+    utt = torch.as_tensor(utts, dtype=torch.int64, device=device).reshape(-1)
+    n = spk.numel()
+    f32 = torch.float32
+    f0 = 90.0 + 140.0 * _hash_uniform(spk * 7919 + 11)                                  # (n,)
+    f0 = f0 * (1.0 + 0.04 * (_hash_uniform(spk * 104729 + utt * 31 + 5) - 0.5))
+    v = torch.arange(N_VOWELS, device=device, dtype=torch.int64)
+    key_sv = spk[:, None] * 977 + v[None] * 131                                          # (n, V)
+    form1 = 300.0 + 600.0 * _hash_uniform(key_sv + 1)
+    form2 = 1000.0 + 1600.0 * _hash_uniform(key_sv + 2)
+    h = torch.arange(1, N_HARM + 1, device=device, dtype=f32)
+    fh = f0[:, None, None] * h[None, None]                                               # (n, 1, H)
+    amp = (torch.exp(-((fh - form1[..., None]) / 180.0) ** 2) + 0.7 * torch.exp(-((fh - form2[..., None]) / 260.0) ** 2)
+           + 0.03) / h[None, None]                                                       # (n, V, H)
+    n_seg = (n_samples + SEG_SAMPLES - 1) // SEG_SAMPLES
+    seg = torch.arange(n_seg, device=device, dtype=torch.int64)
+    key_us = spk[:, None] * 1000003 + utt[:, None] * 7717 + seg[None] * 13               # (n, n_seg)
+    vowel = _hash_u32(key_us + 3) % N_VOWELS
+    gain = 0.6 + 0.8 * _hash_uniform(key_us + 4)
+    amp_seg = torch.gather(amp, 1, vowel[..., None].expand(n, n_seg, N_HARM)) * gain[..., None]   # (n, n_seg, H)
+    t = torch.arange(n_samples, device=device, dtype=f32) / float(fs)
+    seg_of_t = torch.arange(n_samples, device=device, dtype=torch.int64) // SEG_SAMPLES
+    sig = torch.zeros((n, n_samples), dtype=f32, device=device)
+    phase0 = 6.2831853 * _hash_uniform(spk[:, None] * 613 + utt[:, None] * 17 + torch.arange(N_HARM, device=device)[None] + 9)
+    for k in range(N_HARM):
+        a_t = amp_seg[:, :, k][:, seg_of_t]                                              # (n, n_samples)
+        sig += a_t * torch.sin(6.2831853 * (k + 1) * f0[:, None] * t[None] + phase0[:, k : k + 1])
+    sample = torch.arange(n_samples, device=device, dtype=torch.int64)
+    noise = _hash_uniform((spk[:, None] * 9176 + utt[:, None]) * 1048583 + sample[None]) - 0.5
+    sig += 0.35 * sig.pow(2).mean(dim=1, keepdim=True).sqrt() * noise
+    sig *= 3000.0 / (sig.pow(2).mean(dim=1, keepdim=True).sqrt() + 1e-12)
+    pcm = sig.round().clamp(-32768, 32767).to(torch.int16)
+    return torch.where(pcm == 0, torch.ones_like(pcm), pcm)

@@ -21,7 +21,8 @@ import numpy as np
 
 from . import _lib
 from . import frontend as fe
-from .mixture import GaussianMixture, ModelSet, SharedModelSet, concat_utterances
+from .mixture import (SINGLE_PASS_MIN_COMPONENTS, GaussianMixture, ModelSet, SharedModelSet, concat_utterances,
+                      resolve_precision)
 
 
 def map_adapt(ubm: GaussianMixture, speaker_frames, relevance: float = 16.0, adapt=("means",), device=None):
@@ -65,49 +66,78 @@ def map_enrol(ubm: GaussianMixture, speaker_frames, relevance: float = 16.0, dev
     return sms
 
 
-def identify(utts, speakers, ubm=None, precision="tf32", device=None):
+def _base_params(model):
+    """(weights (K,), variances (K, D)) of a fitted GaussianMixture-like or a single-model ModelSet as numpy, else None."""
+    if isinstance(model, ModelSet):
+        if model.n_models != 1:
+            return None
+        w, _, var = model._params
+        return w[0].cpu().numpy(), var[0].cpu().numpy()
+    return np.asarray(model.weights_), np.asarray(model.covariances_)
+
+
+def identify(utts, speakers, ubm=None, precision="auto", device=None):
     """LLR matrix and decisions for all (utterance, speaker) pairs (GMM_UBM.py:191-197).
 
-    ``speakers``: :class:`ModelSet`, or list of fitted GaussianMixture-likes.  ``ubm``: fitted
-    GaussianMixture-like or None.  Returns ``(pred (N,S) float64 numpy, argmax (N,) int64)``.
-    The UBM term is constant per utterance, so decisions depend on the speaker scores only
-    (SURVEY F9); it is evaluated ONCE per utterance, not once per speaker.
+    ``speakers``: :class:`ModelSet` / :class:`SharedModelSet`, or list of fitted GaussianMixture-likes.  ``ubm``: fitted
+    GaussianMixture-like, single-model :class:`ModelSet`, or None.  Returns ``(pred (N,S) float64 numpy, argmax (N,)
+    int64)``; ``pred`` is always the LLR ``speaker score - UBM score`` when a UBM is given, whichever kernel serves the
+    call.  The UBM term is constant per utterance, so decisions depend on the speaker scores only; it is
+    evaluated ONCE per utterance, not once per speaker.
+
+    ``precision``: "auto" (default) keeps every LLR within 1e-3 absolute of float64: one TF32 pass for models of
+    >= 512 components (mean-only MAP sets then go through the shared-variance kernel), three passes (FP32-grade) for
+    smaller ones, FP32 CUDA cores for D > 39.  "tf32" forces the single pass, "tf32x2" / "tf32x3" / "fp32" the others.
     """
     torch = _lib.require_cuda()
     dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-    feats, offs = concat_utterances(utts, dev)
-    if isinstance(speakers, SharedModelSet) and getattr(speakers, "ubm_index", None) is not None and ubm is None:
-        # the UBM rides along as one of the mean sets (map_enrol): one launch scores everything
-        scores, _ = speakers.score(feats, offs)
-        k = speakers.ubm_index
-        keep = [i for i in range(speakers.n_models) if i != k]
-        pred = (scores[:, keep] - scores[:, k : k + 1]).cpu().numpy()
-        return pred, pred.argmax(axis=1)
-    if isinstance(speakers, (ModelSet, SharedModelSet)):
-        ms = speakers
-    else:
-        sw = np.stack([np.asarray(m.weights_) for m in speakers])
-        smu = np.stack([np.asarray(m.means_) for m in speakers])
-        svar = np.stack([np.asarray(m.covariances_) for m in speakers])
-        uw, uvar = (np.asarray(ubm.weights_), np.asarray(ubm.covariances_)) if ubm is not None and not isinstance(ubm, ModelSet) else (None, None)
-        if (precision == "tf32" and smu.shape[2] <= 62 and SharedModelSet.shares_base(sw, svar)
-                and (uw is None or (np.array_equal(uw, sw[0]) and np.array_equal(uvar, svar[0])))):
-            # mean-only MAP speakers (e.g. unpickled models adapted from this UBM): shared-variance kernel, UBM included
-            means = smu if uw is None else np.concatenate([smu, np.asarray(ubm.means_)[None]])
-            sms = SharedModelSet(sw[0], svar[0], means, ref_model=-1, device=dev)
-            scores, _ = sms.score(feats, offs)
-            if uw is not None:
-                scores = scores[:, :-1] - scores[:, -1:]
-            pred = scores.cpu().numpy()
+    with torch.cuda.device(dev):
+        feats, offs = concat_utterances(utts, dev)
+        if isinstance(speakers, SharedModelSet) and getattr(speakers, "ubm_index", None) is not None and ubm is None:
+            # the UBM rides along as one of the mean sets (map_enrol): one launch scores everything
+            scores, _ = speakers.score(feats, offs)
+            k = speakers.ubm_index
+            keep = [i for i in range(speakers.n_models) if i != k]
+            pred = (scores[:, keep] - scores[:, k : k + 1]).cpu().numpy()
             return pred, pred.argmax(axis=1)
-        ms = ModelSet(sw, smu, svar, device=dev)
-    scores, _ = ms.score(feats, offs, precision=precision)
-    if ubm is not None:
-        ums = ubm if isinstance(ubm, ModelSet) else ModelSet(ubm.weights_, ubm.means_, ubm.covariances_, device=dev)
-        base, _ = ums.score(feats, offs, precision=precision)
-        scores = scores - base
-    pred = scores.cpu().numpy()
-    return pred, pred.argmax(axis=1)
+        if isinstance(speakers, (ModelSet, SharedModelSet)):
+            ms = speakers
+        else:
+            sw = np.stack([np.asarray(m.weights_) for m in speakers])
+            smu = np.stack([np.asarray(m.means_) for m in speakers])
+            svar = np.stack([np.asarray(m.covariances_) for m in speakers])
+            single_pass = precision == "tf32" or (precision == "auto" and sw.shape[1] >= SINGLE_PASS_MIN_COMPONENTS)
+            base = _base_params(ubm) if ubm is not None else None
+            # mean-only MAP speakers (e.g. unpickled models adapted from this UBM): shared-variance kernel, with the UBM
+            # as one more mean set -- only when the UBM (if any) is KNOWN to carry the same weights and variances
+            if (single_pass and smu.shape[2] <= 62 and SharedModelSet.shares_base(sw, svar)
+                    and (ubm is None or (base is not None and np.array_equal(base[0], sw[0]) and np.array_equal(base[1], svar[0])))):
+                if ubm is None:
+                    means = smu
+                elif isinstance(ubm, ModelSet):
+                    means = np.concatenate([smu, ubm._params[1].cpu().numpy()])
+                else:
+                    means = np.concatenate([smu, np.asarray(ubm.means_)[None]])
+                sms = SharedModelSet(sw[0], svar[0], means, ref_model=-1, device=dev)
+                scores, _ = sms.score(feats, offs)
+                if ubm is not None:
+                    scores = scores[:, :-1] - scores[:, -1:]
+                pred = scores.cpu().numpy()
+                return pred, pred.argmax(axis=1)
+            ms = ModelSet(sw, smu, svar, device=dev)
+        if isinstance(ms, SharedModelSet) and precision not in ("tf32", "auto"):
+            ms = ms.expand()
+        scores, _ = ms.score(feats, offs, precision=precision)
+        if ubm is not None:
+            ums = ubm if isinstance(ubm, ModelSet) else ModelSet(ubm.weights_, ubm.means_, ubm.covariances_, device=dev)
+            if ums.n_models != 1:
+                raise ValueError("ubm must be ONE model (got a ModelSet of %d)" % ums.n_models)
+            # same rung as the speakers: the model-side rounding of a shared base then cancels in the LLR
+            base_prec = resolve_precision(precision, ms.n_comp, ms.n_feat)
+            ubm_score, _ = ums.score(feats, offs, precision=base_prec)
+            scores = scores - ubm_score
+        pred = scores.cpu().numpy()
+        return pred, pred.argmax(axis=1)
 
 
 # frames one wave of the persistent scoring kernels covers: 148 CTAs x 256-frame units
@@ -129,7 +159,7 @@ def split_for_overlap(frame_counts, head_fraction: float = 0.1, min_frames: int 
     return n if 0 < n < len(cum) else 0
 
 
-def identify_pcm(host_pcm, sample_offsets, front_end, speakers, ubm_index=None, precision="tf32", out=None,
+def identify_pcm(host_pcm, sample_offsets, front_end, speakers, ubm_index=None, precision="auto", out=None,
                  head_fraction: float = 0.1, min_split_frames: int = 4 * _WAVE_FRAMES):
     """Raw PCM on the host -> speaker decisions on the host, for one batch of utterances: the front-end of
     GMM_UBM.py:129 and the scoring / argmax of :191-197 as one call.
@@ -231,7 +261,7 @@ def chunk_features(audio, feature_type="MFCC", fs=16000, seconds=1.0):
     return [host[offs[i] : offs[i + 1]] for i in range(n_chunks)]
 
 
-def chunk_identify(features, gmms, ubm, precision="tf32"):
+def chunk_identify(features, gmms, ubm, precision="auto"):
     """``_GMM_test`` of the final GUI (UI/tmp.py:337-349) and ``test`` of the GMM-UBM GUI (UI/GMM_UBM_GUI.py:102-113)
     for a list of chunk feature matrices: ``pred[j, i] = GMM[i].score(x_j) - UBM.score(x_j)`` in one launch, the GUI's
     "probability" ``exp(pred.max(1)) / exp(pred).sum(1)`` and the argmax.  Returns ``(pred, prob, decisions)``."""
@@ -301,7 +331,7 @@ def main(path="dataset/ASR_GMM"):
 
 
 def GMM(train, x_train, y_train, x_test, y_test, n_components=16, model=False, label_encoder=None, random_state=None,
-        precision="tf32"):
+        precision="auto"):
     """``GMM_UBM.GMM`` (GMM_UBM.py:134-199) on the GPU; prints the reference's result line and
     returns ``(acc_train, acc_test, pred_test)`` (the reference returns None).
 
@@ -340,7 +370,7 @@ def GMM(train, x_train, y_train, x_test, y_test, n_components=16, model=False, l
     return acc_train, acc, pred
 
 
-def install(gmm_ubm_module, delta_order: int = 1):
+def install(gmm_ubm_module):
     """Rebind the names GMM_UBM.py:16-20 imports so the reference script runs on the GPU:
 
         import GMM_UBM, speech_signal_processing_b200 as ssp

@@ -15,10 +15,17 @@ from speech_signal_processing_b200 import synth  # noqa: E402
 #   single-pass TF32 tensor kernel: 1e-4 at the named workloads (K = 1024, ~300 frames per utterance, see
 #   test_tf32_matches_fp32_kernel_1024_components) and 5e-4 worst case for tiny models / very short utterances,
 #   where the unbiased A-operand rounding averages over fewer frames and components.
-REL = {"fp32": 2e-6, "tf32": 5e-4}
+#   3-pass TF32 (tf32x3, what "auto" picks below 512 components): FP32-grade, 2e-6; 2-pass (split model operand): the
+#   frame-side rounding remains, same per-score bound as one pass but a 3-5x smaller LLR error.
+REL = {"fp32": 2e-6, "tf32": 5e-4, "tf32x2": 5e-4, "tf32x3": 2e-6}
+# LLR within 1e-3 absolute, per-utterance score within 1e-4 relative
+LLR_ATOL, SCORE_RTOL = 1e-3, 1e-4
+# the kernels that must serve ssp_gmm_stats for D <= 39 (tcgen05), and the FP32 CUDA-core pair for wider features
+EM_TENSOR_KERNELS = {"gmm_em_lse_kernel", "gmm_em_stats_kernel"}
+EM_SIMT_KERNELS = {"gmm_score_simt_kernel", "gmm_stats_simt_kernel"}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2", "tf32x3"])
 @pytest.mark.parametrize("tag", ["s", "m", "l"])
 def test_score_matches_sklearn(golden, tag, precision):
     g = golden("sklearn_gmm.npz")
@@ -29,13 +36,13 @@ def test_score_matches_sklearn(golden, tag, precision):
     assert got.shape == want.shape
     # per frame: TF32 operand rounding (2^-12 relative on ~80 products of magnitude up to ~40) is a few 1e-2
     # absolute on |L| ~ 50; it is unbiased on the frame side and averages out in the utterance mean below
-    np.testing.assert_allclose(got, want, rtol=5e-5 if precision == "fp32" else 3e-3, atol=0)
+    np.testing.assert_allclose(got, want, rtol=5e-5 if precision in ("fp32", "tf32x3") else 3e-3, atol=0)
     s = gm.score(x)
     assert isinstance(s, float)
     assert abs(s - float(g[f"{tag}_score"])) <= REL[precision] * abs(float(g[f"{tag}_score"]))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2", "tf32x3"])
 def test_score_matrix_ragged_matches_oracle(precision):
     k, d, n_spk = 64, 39, 5
     w, mu, var = synth.synth_ubm(k, d, seed=3)
@@ -45,7 +52,7 @@ def test_score_matrix_ragged_matches_oracle(precision):
     models = [ssp.GaussianMixture.from_params(w, spk_mu[i], var) for i in range(n_spk)]
     got = ssp.score_matrix(utts, models, precision=precision)
     want = np.array([[ogmm.score(u, w, spk_mu[i], var) for i in range(n_spk)] for u in utts])
-    np.testing.assert_allclose(got, want, rtol=REL[precision] * (6 if precision == "tf32" else 1), atol=0)
+    np.testing.assert_allclose(got, want, rtol=REL[precision] * (6 if precision in ("tf32", "tf32x2") else 1), atol=0)
     long_enough = np.array(lens) >= 31
     np.testing.assert_allclose(got[long_enough], want[long_enough], rtol=REL[precision], atol=0)
     assert (got.argmax(axis=1) == want.argmax(axis=1))[long_enough].all()
@@ -112,7 +119,12 @@ def test_stats_match_oracle(k, d):
     ms = ssp.ModelSet(w, mu, var)
     import torch
 
+    from speech_signal_processing_b200 import _lib
+
+    _lib.load().ssp_reset_launch_count()
     n, f, s, ll = ms.stats(torch.as_tensor(x, device="cuda"), seg)
+    # the tensor-core kernels serve every D <= 39; only wider features take the FP32 CUDA-core path
+    assert set(_lib.launch_log()) == (EM_TENSOR_KERNELS if d <= 39 else EM_SIMT_KERNELS), _lib.launch_log()
     n, f, s, ll = (t.cpu().numpy() for t in (n, f, s, ll))
     for i, ln in enumerate(lens):
         xs = x[seg[i] : seg[i + 1]].astype(np.float64)
@@ -204,10 +216,11 @@ def test_reference_pipeline_decisions(golden, tmp_path, monkeypatch):
     with open("Model/UBM_MFCC_model.pkl", "wb") as f:
         pickle.dump(sk(g["ubm_w"], g["ubm_mu"], g["ubm_var"]), f)
     feats = [x.astype(np.float32) for x in g["feat_test"]]
-    for precision in ("fp32", "tf32"):
+    # "auto" (the default of ssp.GMM) is the 3-pass tensor rung at this model size: LLRs within the survey's 1e-3
+    for precision, atol in (("fp32", 2e-4), ("auto", 2e-4), ("tf32x3", 2e-4), ("tf32x2", 1e-2), ("tf32", 2e-2)):
         acc_tr, acc, pred = ssp.GMM({}, feats, list(g["y_test"]), feats, list(g["y_test"]), n_components=4, model=True,
                                     precision=precision)
-        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=2e-4 if precision == "fp32" else 2e-2)
+        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=atol)
         assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
         assert f"test acc {acc:.2%}" in str(g["printed"])
 
@@ -404,16 +417,28 @@ def test_identify_routes_shared_base_model_lists_to_the_shared_variance_kernel()
     ubm = ssp.GaussianMixture.from_params(w, mu, var)
     models = [ssp.GaussianMixture.from_params(w, spk_mu[i], var) for i in range(n_spk)]
     tests = [synth.sample_gmm(w, spk_mu[i % n_spk], var, 200 + 11 * i, seed=700 + i) for i in range(2 * n_spk)]
-    before = _lib.launch_count()
-    pred, who = ssp.identify(tests, models, ubm)
-    assert _lib.launch_count() - before == 3          # pack + shared-variance kernel + its fix-up pass
+    _lib.load().ssp_reset_launch_count()
+    pred, who = ssp.identify(tests, models, ubm, precision="tf32")
+    assert _lib.launch_log() == {"gmm_pack_sv_kernel": 1, "gmm_score_sv_kernel": 1, "sv_fixup_kernel": 1}
     ref, who_ref = ssp.identify(tests, models, ubm, precision="fp32")
     np.testing.assert_allclose(pred, ref, rtol=0, atol=1.2e-2)
     assert (who == who_ref).all() and (who == np.arange(len(tests)) % n_spk).all()
     # a model with its own variances switches the whole call to the general kernel
     odd = ssp.GaussianMixture.from_params(w, spk_mu[0], var * 1.1)
-    pred2, _ = ssp.identify(tests, models[:-1] + [odd], ubm)
+    pred2, _ = ssp.identify(tests, models[:-1] + [odd], ubm, precision="tf32")
     np.testing.assert_allclose(pred2[:, :-1], ref[:, :-1], rtol=0, atol=1.2e-2)
+    # default precision at K = 64: the 3-pass general tensor kernel for speakers and UBM, LLRs at the survey's bar
+    _lib.load().ssp_reset_launch_count()
+    pred3, who3 = ssp.identify(tests, models, ubm)
+    assert _lib.launch_log() == {"gmm_pack_kernel": 2, "gmm_score_tc_kernel<3 passes>": 2}
+    np.testing.assert_allclose(pred3, ref, rtol=0, atol=LLR_ATOL)
+    assert (who3 == who_ref).all()
+    # a UBM handed over as a ModelSet: pred is still the LLR, whichever kernel is selected (speaker score - UBM score)
+    ums = ssp.ModelSet(w, mu, var)
+    for precision in ("auto", "tf32", "fp32"):
+        pred4, who4 = ssp.identify(tests, models, ums, precision=precision)
+        np.testing.assert_allclose(pred4, ref, rtol=0, atol=1.2e-2 if precision == "tf32" else LLR_ATOL)
+        assert (who4 == who_ref).all()
 
 
 @pytest.mark.parametrize("split", [False, True])
@@ -475,12 +500,18 @@ def test_config1_reference_pipeline_at_full_size(golden, config1_corpus, tmp_pat
         pickle.dump([sk(g["gmm_w"][i], g["gmm_mu"][i], g["gmm_var"][i]) for i in range(10)], f)
     with open("Model/UBM_MFCC_model.pkl", "wb") as f:
         pickle.dump(sk(g["ubm_w"], g["ubm_mu"], g["ubm_var"]), f)
-    for precision in ("fp32", "tf32"):
-        acc_tr, acc, pred = ssp.GMM({}, feats, labels, feats, labels, n_components=64, model=True, precision=precision)
-        # an LLR is the difference of two scores of magnitude 30 .. 100; the single-pass TF32 kernel is good to 5e-4
-        # relative per score at this model size (K = 64; measured here: 4.4e-4 of the LLR at worst), the FP32 kernel
-        # sees only the front-end's float32 differences
-        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=2e-3 if precision == "fp32" else 5e-2)
+    # An LLR is the difference of two scores of magnitude 30 .. 100.  The default rung ("auto" -> 3-pass TF32 at K = 64)
+    # and the FP32 kernel see only the front-end's float32 differences; the single-pass TF32 kernel is good to 5e-4
+    # relative per score at this model size (measured: 4.4e-4 of the LLR at worst) and stays an opt-in.
+    default_pred = None
+    for precision, atol in ((None, 2e-3), ("fp32", 2e-3), ("tf32x3", 2e-3), ("tf32x2", 2e-2), ("tf32", 5e-2)):
+        kw = {} if precision is None else {"precision": precision}
+        acc_tr, acc, pred = ssp.GMM({}, feats, labels, feats, labels, n_components=64, model=True, **kw)
+        np.testing.assert_allclose(pred, g["pred"], rtol=0, atol=atol)
+        if precision is None:
+            default_pred = pred
+        elif precision == "fp32":  # tensor path vs CUDA-core path on the SAME features: the survey's LLR bar
+            np.testing.assert_allclose(default_pred, pred, rtol=0, atol=LLR_ATOL)
         assert (pred.argmax(axis=1) == g["pred"].argmax(axis=1)).all()
         assert acc == 1.0 and "test acc 100.00%" in str(g["printed"])
     assert float(g["min_top2_margin"]) > 100 * 5e-2  # decisions are far from the tolerance
@@ -524,3 +555,113 @@ def test_chunked_gui_path_matches_oracle(feature_type):
     assert ssp.chunk_features(audio[:15999], feature_type) == []
     with pytest.raises(NameError):
         ssp.chunk_features(audio, "LPCC")
+
+
+# ------------------------------------------------------------------------------------------------
+# the named configs of BASELINE.json at their own model sizes (K = 2048 scoring, K = 512 statistics)
+# ------------------------------------------------------------------------------------------------
+def test_config5_2048_components_scoring_matches_oracle():
+    """BASELINE configs[4]: K = 2048, D = 39 -- 16 component tiles per model in the general tensor kernel, 32 in the
+    shared-variance one.  Utterance scores, per-frame log-likelihoods and decisions against the float64 oracle."""
+    k, d, n_spk = 2048, 39, 4
+    w, mu, var = synth.synth_ubm(k, d, seed=61)
+    spk_mu = np.concatenate([synth.synth_speaker_means(mu, n_spk, seed=62, shift=0.25), mu[None]])  # last = UBM
+    lens = [64, 298, 130, 257, 98, 2998 // 4]
+    utts = [synth.sample_gmm(w, spk_mu[i % n_spk], var, n, seed=900 + i) for i, n in enumerate(lens)]
+    x = np.concatenate(utts)
+    want = np.array([[ogmm.score(u, w, m, var) for m in spk_mu] for u in utts])
+    want_llr = want[:, :n_spk] - want[:, n_spk:]
+    ms = ssp.ModelSet(np.tile(w, (n_spk + 1, 1)), spk_mu, np.tile(var, (n_spk + 1, 1, 1)))
+    feats, offs = ssp.mixture.concat_utterances(utts, ms.device)
+    for precision, rtol, llr_atol in (("tf32", SCORE_RTOL, 5e-3), ("tf32x3", 2e-6, 1e-4), ("fp32", 2e-6, 1e-4)):
+        got, lse = ms.score(feats, offs, precision=precision, want_frame_lse=True)
+        got, lse = got.cpu().numpy(), lse.cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=0)
+        np.testing.assert_allclose(got[:, :n_spk] - got[:, n_spk:], want_llr, rtol=0, atol=llr_atol)
+        assert ((got[:, :n_spk]).argmax(axis=1) == want[:, :n_spk].argmax(axis=1)).all()
+        for i in (0, n_spk):
+            np.testing.assert_allclose(lse[i], ogmm.score_samples(x, w, spk_mu[i], var), rtol=3e-3 if precision == "tf32" else 5e-5)
+    sms = ssp.SharedModelSet(w, var, spk_mu)
+    got, lse = sms.score(feats, offs, want_frame_lse=True)
+    got, lse = got.cpu().numpy(), lse.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=SCORE_RTOL, atol=0)
+    np.testing.assert_allclose(got[:, :n_spk] - got[:, n_spk:], want_llr, rtol=0, atol=5e-3)
+    assert (got[:, :n_spk].argmax(axis=1) == want[:, :n_spk].argmax(axis=1)).all()
+    for i in (1, n_spk):
+        np.testing.assert_allclose(lse[i], ogmm.score_samples(x, w, spk_mu[i], var), rtol=3e-3)
+
+
+def test_config3_512_component_statistics_match_oracle():
+    """BASELINE configs[2] at its model size: N / F / S and the log-likelihood under a K = 512, D = 39 UBM over 240 000
+    frames in 4 segments (one empty) -- thousands of frame blocks accumulated in TMEM per CTA -- against the float64
+    oracle evaluated chunk by chunk."""
+    import torch
+
+    from speech_signal_processing_b200 import _lib
+
+    k, d = 512, 39
+    w, mu, var = synth.synth_ubm(k, d, seed=71, spread=1.0)
+    lens = [150_000, 0, 60_001, 29_999]
+    x = synth.sample_gmm(w, mu * 0.9, var * 1.1, sum(lens), seed=72)
+    seg = np.concatenate([[0], np.cumsum(lens)])
+    ms = ssp.ModelSet(w, mu, var)
+    _lib.load().ssp_reset_launch_count()
+    n, f, s, ll = (t.cpu().numpy() for t in ms.stats(torch.as_tensor(x, device="cuda"), seg))
+    assert set(_lib.launch_log()) == EM_TENSOR_KERNELS, _lib.launch_log()
+    for i, ln in enumerate(lens):
+        if ln == 0:
+            assert np.all(n[i] == 0) and np.all(f[i] == 0) and np.all(s[i] == 0) and ll[i] == 0
+            continue
+        rn, rf, rs_, rll = np.zeros(k), np.zeros((k, d)), np.zeros((k, d)), 0.0
+        for lo in range(seg[i], seg[i + 1], 20_000):
+            part = ogmm.suff_stats(x[lo : min(lo + 20_000, seg[i + 1])].astype(np.float64), w, mu, var)
+            rn += part[0]; rf += part[1]; rs_ += part[2]; rll += part[3]
+        # gamma is TF32-rounded (2^-11 relative, unbiased) before the statistics GEMM: the error of a sum over n_c
+        # frames grows like sqrt(n_c), far below these bounds at n_c ~ ln / k
+        np.testing.assert_allclose(n[i], rn, rtol=1e-4, atol=1e-4 * ln / k)
+        np.testing.assert_allclose(f[i], rf, rtol=1e-4, atol=3e-4 * ln / k)
+        np.testing.assert_allclose(s[i], rs_, rtol=1e-4, atol=6e-4 * ln / k)
+        assert abs(ll[i] - rll) <= 1e-6 * abs(rll)
+        assert abs(n[i].sum() - ln) < 1e-5 * ln
+    # the M-step the EM loop would take from these statistics equals the oracle's
+    tot = [a.sum(axis=0) for a in (n, f, s)]
+    rw, rmu, rvar = ogmm.m_step(*(np.asarray(t, dtype=np.float64) for t in tot))
+    gw, gmu, gvar = (torch.empty(sh, dtype=torch.float64, device="cuda") for sh in ((k,), (k, d), (k, d)))
+    tn, tf_, ts = (torch.as_tensor(t, device="cuda") for t in tot)
+    _lib.check(_lib.load().ssp_gmm_mstep(_lib.ptr(tn), _lib.ptr(tf_), _lib.ptr(ts), k, d, 1e-6, 10 * np.finfo(np.float64).eps,
+                                         _lib.ptr(gw), _lib.ptr(gmu), _lib.ptr(gvar), _lib.stream_ptr()), "ssp_gmm_mstep")
+    np.testing.assert_allclose(gw.cpu().numpy(), rw, rtol=1e-12)
+    np.testing.assert_allclose(gmu.cpu().numpy(), rmu, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(gvar.cpu().numpy(), rvar, rtol=1e-9)
+
+
+def test_install_runs_the_reference_call_pattern(tmp_path, monkeypatch):
+    """a stand-in module with the names GMM_UBM.py:16-20,53 binds, ssp.install() on it, then
+    the reference's own extract_feature -> GMM call pattern (GMM_UBM.py:86-93, :154-170, :182-197) through those names."""
+    import types
+
+    from oracle import frontend as ofe
+
+    mod = types.ModuleType("GMM_UBM")
+    for name in ("GaussianMixture", "preprocessing", "mfcc", "plp", "delta"):
+        setattr(mod, name, None)
+    assert ssp.install(mod) is mod
+    x, y = synth.synth_corpus(3, 6, 16000)
+    feats = []
+    for sig in x:                                        # GMM_UBM.py:86-93
+        c = mod.mfcc(sig)
+        assert isinstance(c, np.ndarray) and c.shape == (98, 13)
+        dl = mod.delta(c, 2)
+        feats.append(mod.preprocessing.scale(np.hstack((c, dl))))
+    want = ofe.features(x[0], preset="sidekit", delta_order=1, cmvn=True)
+    np.testing.assert_allclose(feats[0], want, rtol=0, atol=5e-4)
+    p = mod.plp(x[0])
+    assert p.shape[0] == 98 and np.isfinite(p).all()
+    train = {s: np.vstack([f for f, lab in zip(feats, y) if lab == s]) for s in range(3)}
+    gmms = [mod.GaussianMixture(n_components=4, covariance_type="diag", random_state=0).fit(train[s]) for s in range(3)]
+    ubm = mod.GaussianMixture(n_components=4, covariance_type="diag", random_state=0).fit(np.vstack([train[s] for s in range(3)]))
+    pred = np.array([[gmms[i].score(f) - ubm.score(f) for i in range(3)] for f in feats])   # GMM_UBM.py:182-185
+    assert (pred.argmax(axis=1) == np.array(y)).mean() >= 0.9
+    # the same numbers as the batched entry point
+    ref, _ = ssp.identify(feats, gmms, ubm, precision="fp32")
+    np.testing.assert_allclose(pred, ref, rtol=0, atol=1e-4)

@@ -242,3 +242,54 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_install_rebinds_the_reference_module_names():
+    """ssp.install() replaces exactly the names GMM_UBM.py:16-20,53 binds (no GPU needed to
+    rebind; the GPU test test_install_runs_the_reference_call_pattern runs the call pattern through them)."""
+    import types
+
+    mod = types.ModuleType("GMM_UBM")
+    mod.untouched = object()
+    keep = mod.untouched
+    assert ssp.install(mod) is mod
+    assert mod.GaussianMixture is ssp.GaussianMixture and mod.delta is ssp.delta
+    assert mod.preprocessing.scale is ssp.scale and callable(mod.mfcc) and callable(mod.plp)
+    assert mod.untouched is keep
+    import inspect
+
+    assert list(inspect.signature(ssp.install).parameters) == ["gmm_ubm_module"]
+
+
+def test_auto_precision_rule():
+    from speech_signal_processing_b200.mixture import resolve_precision
+
+    assert resolve_precision("auto", 64, 26) == "tf32x3"      # config 1: small models need the FP32-grade rung
+    assert resolve_precision("auto", 1024, 39) == "tf32"      # config 4
+    assert resolve_precision("auto", 2048, 39) == "tf32"      # config 5
+    assert resolve_precision("auto", 1024, 40) == "fp32"      # contraction 2D + 2 > 80: CUDA cores
+    assert resolve_precision("tf32x2", 8, 5) == "tf32x2"
+    with pytest.raises(ValueError):
+        resolve_precision("bf16", 8, 5)
+
+
+def test_counter_based_audio_is_a_pure_function_of_its_ids():
+    """bench.py's three consumers (GPU arm, CPU arm, oracle check) regenerate utterances independently: any batch split
+    must give the same samples."""
+    import torch
+
+    from speech_signal_processing_b200 import synth
+
+    a = synth.synth_pcm_torch([3, 3, 7, 11], [0, 1, 100, 5], 4000, "cpu")
+    b = torch.cat([synth.synth_pcm_torch([3], [0], 4000, "cpu"), synth.synth_pcm_torch([3, 7, 11], [1, 100, 5], 4000, "cpu")])
+    assert a.dtype == torch.int16 and a.shape == (4, 4000) and torch.equal(a, b)
+    assert not torch.equal(a[0], a[1]) and int((a == 0).sum()) == 0
+    rms = a.float().pow(2).mean(dim=1).sqrt()
+    assert torch.all((rms > 2900) & (rms < 3100))
+    sys.path.insert(0, ROOT)
+    import bench
+
+    spk, utt = bench.test_ids(0, 2500, 1000)
+    assert spk[1234] == 234 and utt[1234] == bench.TEST_UTT_BASE + 1 and utt.min() >= bench.TEST_UTT_BASE > bench.ENROL_UTTS
+    pcm = bench.gen_pcm(spk[:3], utt[:3], "cpu", n_samples=2000, chunk=2)
+    assert torch.equal(pcm.reshape(3, 2000), synth.synth_pcm_torch(spk[:3], utt[:3], 2000, "cpu"))
