@@ -1,28 +1,33 @@
-// EM / MAP sufficient statistics on the tensor cores (sm_100a): posteriors and N/F/S as two chained GEMMs.
+// EM / MAP sufficient statistics on the tensor cores (sm_100a): posteriors and N/F/S as two chained GEMMs fed by
+// bulk copies of operand images that are built ONCE per set of frames.
 //
-// Posteriors need FP32-grade logits (a 4e-3 logit error is a 0.4 % responsibility error), so the logit GEMM runs
-// as 3xTF32: hi.hi + lo.hi + hi.lo with the frame operand [x, x^2, 1, 1] and the model operand
-// log2(e) [mu/var, -1/(2var), c...] both split into TF32 hi + lo pieces (the constant rides as three exact
-// pieces), FP32 accumulation in TMEM.  kind::tf32 only takes K-major shared-memory operands (an MN-major
-// descriptor silently yields zeros on sm_100a), so every operand is laid out with its contraction index
-// contiguous.
+// The frames of an EM run never change, only the model does.  ssp_gmm_stats therefore splits into
 //
-//   grid = (frame chunks, component tiles of 128); frame blocks stream through each CTA.  Two passes (the per-frame
-//   normaliser needs ALL component tiles):
+//   prepare (once per feats / seg_offsets; skipped when the caller says the workspace still holds the images):
+//     em_plan_kernel   segments are padded to multiples of 64 frames ("blocks"); block -> (segment, first frame, frames)
+//     em_prep_kernel   per block: the tcgen05 shared-memory images of its frames
+//                        Fb  [x, x^2, 1, 1, 0..] as BF16 hi + lo, K-major rows of 128 frames  (logit GEMMs, both passes)
+//                        Xt  the same columns as TF32 hi + lo with the FRAME index contiguous (statistics GEMM)
+//   per call (one EM iteration / one enrolment):
+//     gmm_em_lse_kernel    logits[frame, comp] for a PAIR of 128-component tiles per CTA, 128 frames per step:
+//                          3 x BF16 (hi.hi + lo.hi + hi.lo, FP32 accumulation in TMEM; emulated on the CPU: per-frame
+//                          log-likelihood within 4e-7 relative of float64, N/F/S indistinguishable from 3xTF32 --
+//                          the TF32 rounding of gamma below dominates) at twice the TF32 issue rate;
+//                          thread == frame row -> (max, sum 2^x) per 64-component half tile -> workspace
+//     em_merge_kernel      partials -> per-frame log2-likelihood, frame_lse, per-segment log-likelihood
+//     gmm_em_stats_kernel  TRANSPOSED logits[comp, frame] (same images, model tile as the M-side operand), 64 frames
+//                          per step, thread == component row: gamma = 2^(L - lse[frame]) is written by tcgen05.st IN
+//                          PLACE over the logits and is the TMEM-side operand of the statistics GEMM
+//                          stats[comp, :] += gamma . Xt (TF32, hi + lo), accumulated in TMEM over all blocks of a
+//                          segment and added to the float64 N / F / S outputs at segment ends.
 //
-//   pass LSE   (gmm_em_lse_kernel, 128-frame blocks): logits[frame, comp]; the frame operand lives double-buffered in
-//              TENSOR MEMORY (tcgen05.st, thread == frame row), the model tile (hi + lo) in shared memory; thread ==
-//              frame row -> per-tile (max, sum 2^x) partials to the workspace.
-//   pass STATS (gmm_em_stats_kernel, 64-frame blocks): TRANSPOSED logits[comp, frame] = B . F^T with the model tile
-//              (hi + lo) resident in TENSOR MEMORY, so that thread == component row: gamma = 2^(L2 - lse2[frame]) (lse2
-//              from the partials) is written by tcgen05.st IN PLACE over the logits and is the TMEM-side operand of
-//              GEMM 2:  stats[comp, :] += gamma . [x, x^2, 1, 1] over the frames, accumulated in TMEM across all blocks
-//              of a segment, hi + lo passes of the frame-contiguous feature operand Xt.  At a segment end the
-//              128 x (2D+2) accumulator is added to the double-precision N / F / S outputs.
-//   Both passes keep two blocks in flight (double / triple-buffered operands): the 16 builder / epilogue warps split
-//   block k and post-process block k - 1 while the tensor core multiplies.
-// Blocks never straddle a segment, so one kernel pair serves UBM EM (one segment) and batched MAP enrolment
-// (one segment per speaker).
+// No thread builds an operand any more: the producer warp streams images with cp.async.bulk, one warp issues the MMAs,
+// sixteen warps do the exponentials.  (Round 1 split the frames into hi / lo in every CTA of every pass of every
+// iteration -- 8x per iteration at K = 512 -- and was bound by that thread work: tensor pipe 37-40 % busy.)
+// Blocks never straddle a segment, so one kernel set serves UBM EM (one segment) and batched MAP enrolment (one
+// segment per speaker).
+#include <cuda_bf16.h>
+
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -32,158 +37,78 @@ namespace em {
 
 using namespace tc;
 
-constexpr int BN = 128;   // components per CTA
-constexpr int BM1 = 128;  // frames per block, pass LSE
-constexpr int BM2 = 64;   // frames per block, pass STATS
-constexpr int EPI = 512;  // 16 builder / epilogue warps, four per TMEM lane quadrant: the thread work around the MMAs (operand
-                          // split, exponentials) is latency-bound, more warps hide more of it (8 warps: 7 % slower)
+constexpr int BN = 128;        // components per tile
+constexpr int IMG = 128;       // frames per Fb image = rows of one LSE step
+constexpr int BLK = 64;        // frames per block: padding granule of a segment, rows of one STATS step
+constexpr int EPI = 512;       // 16 epilogue warps
 constexpr int THREADS = 64 + EPI;
 constexpr int MAX_KD = 80;
+constexpr int NS_L = 3;        // Fb stages of the LSE pass
+constexpr int NS_S = 2;        // (Fb half, Xt, lse) stages of the STATS pass
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct Ws {
+  int64_t nb_max, P;           // upper bound on the number of blocks (even), padded frames = nb_max * BLK
+  int KDb;                     // contraction length, a multiple of 16: roundup(2D + 2, 16); also the N of the statistics GEMM
+  size_t o_blk_start, o_blk_seg, o_blk_t0, o_blk_nt, o_lse2, o_partial, o_fb, o_xt, bytes;
+  size_t img_bytes() const { return (size_t)512 * KDb; }   // Fb image of 128 frames == model tile image of 128 components
+  size_t xt_bytes() const { return (size_t)512 * KDb; }    // Xt image of one 64-frame block (hi + lo)
+};
+static Ws ws_layout(const PackLayout& L, int64_t total_frames, int64_t n_segs) {
+  Ws w;
+  w.KDb = (2 * L.D + 2 + 15) / 16 * 16;
+  w.nb_max = (total_frames / BLK + n_segs + 2) & ~(int64_t)1;
+  w.P = w.nb_max * BLK;
+  auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+  size_t o = 0;
+  w.o_blk_start = o; o = up(o + sizeof(int64_t) * (n_segs + 2));
+  w.o_blk_seg = o;   o = up(o + sizeof(int32_t) * w.nb_max);
+  w.o_blk_t0 = o;    o = up(o + sizeof(int64_t) * w.nb_max);
+  w.o_blk_nt = o;    o = up(o + sizeof(int32_t) * w.nb_max);
+  w.o_lse2 = o;      o = up(o + sizeof(float) * w.P);
+  w.o_partial = o;   o = up(o + sizeof(float2) * 2 * (L.Kp / BN) * w.P);
+  w.o_fb = o;        o = up(o + w.img_bytes() * (w.nb_max / 2));
+  w.o_xt = o;        o = up(o + w.xt_bytes() * w.nb_max);
+  w.bytes = o;
+  return w;
+}
 
 struct Args {
   const float* feats;
   const int64_t* seg;
-  int64_t n_segs, total_frames, chunk;
-  const float* tiles_hi;  // [Kp/128][KD/4][128] float4
-  const float* tiles_lo;
-  int K, D, KD, n_tiles;
-  float2* partial;        // [2 * n_tiles][total_frames]: (max, sum 2^(x-max)) per 64-component half tile, log2 domain
-  float* frame_lse;       // natural-log per-frame likelihood (written by tile 0 in the STATS pass)
+  int64_t n_segs, total_frames;
+  // workspace
+  int64_t* blk_start;       // [n_segs + 1]; blk_start[n_segs] = number of blocks
+  int32_t* blk_seg;         // [nb_max] segment of a block, -1: padding
+  int64_t* blk_t0;          // [nb_max] first frame
+  int32_t* blk_nt;          // [nb_max] frames (1..64; 0: padding)
+  float* lse2;              // [P] per padded frame: log2-likelihood; 3e38 for dead rows
+  float2* partial;          // [2 n_tiles][P]
+  const unsigned char* fb;  // [nb_max / 2] images: [hi | lo][KDb/8][128 rows][8 bf16]
+  const unsigned char* xt;  // [nb_max] images:     [hi | lo][16][KDb rows][4 fp32]
+  int64_t nb_max, P;
+  // model
+  const unsigned char* tiles;  // [n_tiles] images [hi | lo][KDb/8][128 comps][8 bf16]
+  int K, D, KDb, n_tiles;
+  // outputs
+  float* frame_lse;
   double* out_n;
   double* out_f;
   double* out_s;
   double* out_loglik;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// Every role walks the same block sequence: [t0, t0 + nt) inside one segment and inside this CTA's chunk.
-template <int BM>
-struct Walk {
-  const int64_t* seg;
-  int64_t n_segs, end, t0, seg_end;
-  int cur;
-  __device__ bool start(const int64_t* s, int64_t n, int64_t b, int64_t e) {
-    seg = s; n_segs = n; end = e; t0 = b;
-    if (b >= e) return false;
-    cur = find_segment(seg, n_segs, t0);
-    if (cur < 0) return false;
-    seg_end = seg[cur + 1];
-    return true;
-  }
-  __device__ int nt() const { return (int)min((int64_t)BM, min(end, seg_end) - t0); }
-  // advance; returns false when the chunk is exhausted.  `flush`: the block just finished was the last one of its
-  // segment inside this chunk.
-  __device__ bool next(int n, bool& flush) {
-    t0 += n;
-    flush = (t0 >= seg_end) || (t0 >= end);
-    if (t0 >= end) return false;
-    if (t0 >= seg_end) {
-      cur = find_segment(seg, n_segs, t0);
-      if (cur < 0) return false;
-      seg_end = seg[cur + 1];
-    }
-    return true;
-  }
-};
-
-// [x, x^2, 1, 1, 0..] element j of a frame row held in shared memory, split into TF32 hi / lo
-__device__ __forceinline__ void feat_split(const float* xr, int j, int D, bool live, float& hi, float& lo) {
-  float v = 0.f;
-  if (live) {
-    if (j < D) v = xr[j];
-    else if (j < 2 * D) { const float x = xr[j - D]; v = x * x; }
-    else if (j < 2 * D + 2) v = 1.f;
-  }
-  hi = rna_tf32(v);
-  lo = rna_tf32(v - hi);
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-
-// The four elements of K chunk jc of a frame row, split into TF32 hi / lo.  A chunk is almost always all-x or all-x^2
-// (only the chunks that contain column D, 2D or the ones are mixed), and jc is warp-uniform, so the common case is
-// straight-line: load, (square), round, subtract, round.
-__device__ __forceinline__ void chunk_split(const float* xr, int jc, int D, bool live, float (&h)[4], float (&l)[4]) {
-  const int j0 = 4 * jc;
-  if (!live) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { h[e] = 0.f; l[e] = 0.f; }
-  } else if (j0 + 3 < D) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float v = xr[j0 + e];
-      h[e] = rna_tf32(v);
-      l[e] = rna_tf32(v - h[e]);
-    }
-  } else if (j0 >= D && j0 + 3 < 2 * D) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x = xr[j0 + e - D];
-      const float v = x * x;
-      h[e] = rna_tf32(v);
-      l[e] = rna_tf32(v - h[e]);
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) feat_split(xr, j0 + e, D, true, h[e], l[e]);
-  }
-}
-
-// Each of the 128 builder threads keeps its share of the NEXT block's features in registers: the global loads are
-// issued right after the current block's operands are handed to the MMA warp and land while the tensor core and
-// the epilogue work, instead of being waited for at the top of every block.
-template <int R>
-__device__ __forceinline__ void prefetch_block(const float* __restrict__ src, int n, int et, float (&pf)[R]) {
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int idx = et + EPI * r;
-    pf[r] = idx < n ? __ldg(src + idx) : 0.f;
-  }
-}
-template <int R>
-__device__ __forceinline__ void store_block(float* dst, int n, int et, const float (&pf)[R]) {
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int idx = et + EPI * r;
-    if (idx < n) dst[idx] = pf[r];
-  }
-}
-
-// ================================================================================================ pass STATS
-// Two frame blocks in flight, so that the tensor core works on one block while the 16 builder / epilogue warps work
-// on its neighbours:
-//   * the CTA's model tile (TF32 hi + lo) is copied ONCE into tensor memory (160 columns) and is the TMEM-side (A)
-//     operand of the logit GEMM (component == TMEM lane): 80 KB of shared memory become operand buffers;
-//   * gamma is written by tcgen05.st IN PLACE over the logits it came from and is the TMEM-side operand of the
-//     statistics GEMM: it never touches shared memory;
-//   * two F buffers (frames as rows, GEMM 1), three Xt buffers (frames contiguous, GEMM 2) and two 64-column logit
-//     buffers; thread program per block k: build F / Xt of block k, then turn the logits of block k - 1 into gamma;
-//     MMA program: GEMM1(k), GEMM2(k - 1).  The builders never wait for a GEMM that was issued less than a block
-//     ago, so in steady state the period is max(thread work, 1600 tensor cycles) per 64 frames.
-namespace p3 {
-constexpr int NF = 2, NX = 3;
-constexpr uint32_t COL_BHI = 0, COL_BLO = 80;   // model tile, hi and lo (MAX_KD columns each)
-constexpr uint32_t COL_LOGIT = 160;             // + 64 * (k & 1)
-constexpr uint32_t COL_STAT = 288;              // statistics accumulator, n2 <= 80 columns
-struct Carve {
-  int n2, xrows;
-  size_t f_bytes, x_bytes, o_x, o_stage, o_lse, o_bar, bytes;  // F buffers at 0 (hi | lo each), Xt buffers at o_x
-};
-__host__ __device__ inline Carve carve(int KD) {
-  Carve c;
-  c.n2 = (KD + 15) & ~15;
-  c.xrows = c.n2 + 1;
-  c.f_bytes = (size_t)BM2 * KD * 4;
-  c.x_bytes = (size_t)(BM2 / 4) * c.xrows * 16;
-  c.o_x = NF * 2 * c.f_bytes;
-  c.o_stage = c.o_x + NX * 2 * c.x_bytes;
-  c.o_lse = c.o_stage + (size_t)BM2 * (MAX_KD / 2) * 4;
-  c.o_bar = c.o_lse + NX * BM2 * 4;
-  c.bytes = c.o_bar + 128;
-  return c;
-}
-}  // namespace p3
-
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -192,58 +117,191 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]),
-               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
+// kind::f16 with BF16 operands, FP32 accumulate: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
       :
       : "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
-        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+        "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+        "f"(v[30]), "f"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) {
-  using namespace p3;
+// sum over 32 accumulator columns of 2^(r - cm); kPoly of the 16 column pairs on the FMA pipe (degree-4 minimax
+// polynomial after a magic-number range reduction, 2.7e-6 relative), the rest MUFU ex2 (see gmm_score_sv.cu)
+template <int kPoly>
+__device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], float cm) {
+  static_assert(kPoly % 2 == 0 && kPoly <= 16, "pairs are consumed two at a time");
+  const float MAGIC = 12582912.f;  // 1.5 * 2^23
+  const float2 mg = make_float2(MAGIC, MAGIC), nmg = make_float2(-MAGIC, -MAGIC), neg1 = make_float2(-1.f, -1.f);
+  const float2 ncm = make_float2(-cm, -cm);
+  float2 accp = make_float2(0.f, 0.f), accm0 = accp, accm1 = accp;
+#pragma unroll
+  for (int i = 0; i < kPoly; ++i) {
+    float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), ncm);
+    d.x = fmaxf(d.x, -126.f);
+    d.y = fmaxf(d.y, -126.f);
+    const float2 t = __fadd2_rn(d, mg);
+    const float2 nn = __fadd2_rn(t, nmg);
+    const float2 f = __ffma2_rn(nn, neg1, d);
+    float2 p = __ffma2_rn(make_float2(0.009570102207362652f, 0.009570102207362652f), f, make_float2(0.05591785907745361f, 0.05591785907745361f));
+    p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
+    p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
+    p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
+    float2 e;
+    e.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    accp = __fadd2_rn(accp, e);
+  }
+#pragma unroll
+  for (int i = kPoly; i < 16; i += 2) {
+    const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), ncm);
+    const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3])), ncm);
+    accm0 = __fadd2_rn(accm0, make_float2(ex2(d0.x), ex2(d0.y)));
+    accm1 = __fadd2_rn(accm1, make_float2(ex2(d1.x), ex2(d1.y)));
+  }
+  const float2 tot = __fadd2_rn(__fadd2_rn(accm0, accm1), accp);
+  return tot.x + tot.y;
+}
+
+// ================================================================================================ prepare
+// blk_start[s] = number of 64-frame blocks of the segments before s (one block, chunked scan)
+__global__ void __launch_bounds__(1024) em_plan_kernel(const Args a) {
+  __shared__ int64_t part[1024];
+  const int tid = threadIdx.x;
+  const int64_t per = (a.n_segs + 1023) / 1024;
+  const int64_t s0 = min((int64_t)tid * per, a.n_segs), s1 = min(s0 + per, a.n_segs);
+  int64_t sum = 0;
+  for (int64_t s = s0; s < s1; ++s) sum += (a.seg[s + 1] - a.seg[s] + BLK - 1) / BLK;
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int64_t run = 0;
+    for (int i = 0; i < 1024; ++i) { const int64_t v = part[i]; part[i] = run; run += v; }
+    a.blk_start[a.n_segs] = run;
+  }
+  __syncthreads();
+  int64_t run = part[tid];
+  for (int64_t s = s0; s < s1; ++s) {
+    a.blk_start[s] = run;
+    run += (a.seg[s + 1] - a.seg[s] + BLK - 1) / BLK;
+  }
+}
+
+__device__ __forceinline__ float feat_col(const float* xr, int j, int D) {
+  if (j < D) return xr[j];
+  if (j < 2 * D) { const float x = xr[j - D]; return x * x; }
+  return j < 2 * D + 2 ? 1.f : 0.f;
+}
+
+// one CTA per block: block table entry + the block's half of an Fb image + its Xt image
+__global__ void __launch_bounds__(256) em_prep_kernel(const Args a) {
+  __shared__ float sx[BLK * (MAX_KD / 2)];
+  __shared__ int s_seg, s_nt;
+  __shared__ int64_t s_t0;
+  const int64_t b = blockIdx.x;
+  const int64_t nb = a.blk_start[a.n_segs];
+  if (b >= ((nb + 1) & ~(int64_t)1)) return;
+  const int tid = threadIdx.x, D = a.D, KDb = a.KDb;
+  if (tid == 0) {
+    int seg = -1, nt = 0;
+    int64_t t0 = 0;
+    if (b < nb) {
+      seg = find_segment(a.blk_start, a.n_segs, b);
+      t0 = a.seg[seg] + (b - a.blk_start[seg]) * BLK;
+      nt = (int)min((int64_t)BLK, a.seg[seg + 1] - t0);
+    }
+    s_seg = seg; s_nt = nt; s_t0 = t0;
+    a.blk_seg[b] = seg;
+    a.blk_t0[b] = t0;
+    a.blk_nt[b] = nt;
+  }
+  __syncthreads();
+  const int nt = s_nt;
+  const float* src = a.feats + s_t0 * D;
+  for (int i = tid; i < BLK * D; i += 256) sx[i] = i < nt * D ? __ldg(src + i) : 0.f;
+  __syncthreads();
+  // ---- Fb: rows (b & 1) * 64 .. + 63 of image b / 2; item = (chunk of 8 columns, row) -> 16 bytes of hi and of lo
+  {
+    unsigned char* img = const_cast<unsigned char*>(a.fb) + (size_t)(b >> 1) * 512 * KDb;
+    const size_t part_bytes = (size_t)256 * KDb;  // [KDb/8][128][16 B]
+    const int row0 = (int)(b & 1) * BLK;
+    for (int it = tid; it < (KDb >> 3) * BLK; it += 256) {
+      const int c = it / BLK, r = it % BLK;
+      const bool live = r < nt;
+      const float* xr = sx + r * D;
+      __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = live ? feat_col(xr, 8 * c + e, D) : 0.f;
+        h[e] = __float2bfloat16_rn(v);
+        l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
+      }
+      const size_t off = ((size_t)c * IMG + row0 + r) * 16;
+      *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(img + part_bytes + off) = *reinterpret_cast<const uint4*>(l);
+    }
+  }
+  // ---- Xt: item = (chunk of 4 frames, column j) -> float4 of hi and of lo
+  {
+    float* img = reinterpret_cast<float*>(const_cast<unsigned char*>(a.xt) + (size_t)b * 512 * KDb);
+    const size_t part_floats = (size_t)16 * KDb * 4;
+    for (int it = tid; it < 16 * KDb; it += 256) {
+      const int fc = it / KDb, j = it % KDb;
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = 4 * fc + e;
+        // column 2D + 1 (the second "one" of the logit operand) is dead weight here: N is column 2D
+        const float v = (r < nt && j <= 2 * D) ? feat_col(sx + r * D, j, D) : 0.f;
+        h[e] = rna_tf32(v);
+        l[e] = rna_tf32(v - h[e]);
+      }
+      reinterpret_cast<float4*>(img)[it] = make_float4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<float4*>(img + part_floats)[it] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ================================================================================================ pass LSE
+// grid = (image chunks, tile pairs).  Shared memory: the pair's model tiles (BF16 hi + lo) + NS_L Fb stages; tensor
+// memory: 2 tiles x 2 buffers of 128 accumulator columns.
+template <int kPoly>
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int BM = BM2;
-  const int KD = a.KD, KC = KD >> 2, D = a.D;
-  const Carve cv = carve(KD);
-  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
-  float* sStage = reinterpret_cast<float*>(smem + cv.o_stage);
-  float* sLse = reinterpret_cast<float*>(smem + cv.o_lse);  // [3][BM]: written while building block k, read by its epilogue one block later
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.o_bar);
-  uint64_t* b_loaded = bars;       // model tile images landed in shared memory (start-up only)
-  uint64_t* a_full = bars + 1;     // [2] F / Xt of block k are built               (k & 1)
-  uint64_t* l_full = bars + 3;     // [2] logits of block k are in TMEM, F[k & 1] is free again
-  uint64_t* g_full = bars + 5;     // [2] gamma of block k is in TMEM
-  uint64_t* x_free = bars + 7;     // [3] GEMM 2 of block k has completed: Xt[k % 3] free, statistics include block k
-  uint64_t* drained = bars + 10;   // the statistics accumulator has been read out after a segment end
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  const int KDb = a.KDb;
+  const uint32_t TB = 512u * (uint32_t)KDb;  // bytes of one image (hi + lo)
+  unsigned char* sB = smem;                  // [2][TB]
+  unsigned char* sF = smem + 2 * (size_t)TB; // [NS_L][TB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sF + (size_t)NS_L * TB);
+  uint64_t* b_full = bars;                   // model tiles landed
+  uint64_t* f_full = bars + 1;               // [NS_L]
+  uint64_t* f_empty = f_full + NS_L;         // [NS_L]
+  uint64_t* t_full = f_empty + NS_L;         // [4] accumulator (buffer, tile) holds a step's logits
+  uint64_t* t_empty = t_full + 4;            // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.y;
+  const int tile0 = 2 * blockIdx.y;
+  const int ntl = min(2, a.n_tiles - tile0);
   if (tid == 0) {
-    mbar_init(b_loaded, 1);
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(a_full + g, EPI);
-      mbar_init(l_full + g, 1);
-      mbar_init(g_full + g, EPI);
-    }
-    for (int g = 0; g < NX; ++g) mbar_init(x_free + g, 1);
-    mbar_init(drained, EPI);
+    mbar_init(b_full, 1);
+    for (int i = 0; i < NS_L; ++i) { mbar_init(f_full + i, 1); mbar_init(f_empty + i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 2 * IMG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -254,259 +312,93 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
-  const int64_t end = min(begin + a.chunk, a.total_frames);
-  if (begin >= end) {  // (uniform) nothing to do for this CTA
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    return;
-  }
+  const int64_t nb = a.blk_start[a.n_segs];
+  const int64_t n_img = (nb + 1) >> 1;
+  const int64_t per = (n_img + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * per, i1 = min(i0 + per, n_img);
 
-  // ---- start-up: model tile hi / lo -> shared memory (the F buffers as scratch) -> tensor memory
-  float* scratch = reinterpret_cast<float*>(smem);  // 2 x tile_bytes == NF x 2 x f_bytes
-  if (warp == 0 && elect_one()) {
-    mbar_arrive_expect_tx(b_loaded, 2u * tile_bytes);
-    bulk_g2s(scratch, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_loaded);
-    bulk_g2s(scratch + BN * KD, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_loaded);
-  }
-  if (warp >= 2 && warp < 10) {
-    const int which = (warp - 2) >> 2;           // warps 2..5 copy hi, 6..9 copy lo
-    const int row = ((warp & 3) << 5) | lane;    // component row == TMEM lane
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    mbar_wait(b_loaded, 0);
-    const float4* img = reinterpret_cast<const float4*>(scratch + (size_t)which * BN * KD) + row;
-    for (int k = 0; k < (KD >> 3); ++k) {
-      const float4 c0 = img[(2 * k) * BN], c1 = img[(2 * k + 1) * BN];
-      const float v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      tc_st8(tmem_base + lane_addr + (which ? COL_BLO : COL_BHI) + 8u * k, v);
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (i0 < i1) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full, (uint32_t)ntl * TB);
+        for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, a.tiles + (size_t)(tile0 + t) * TB, TB, b_full);
+      }
+      __syncwarp();
+      uint32_t k = 0;
+      for (int64_t i = i0; i < i1; ++i, ++k) {
+        const uint32_t st = k % NS_L, ph = (k / NS_L) & 1u;
+        mbar_wait(f_empty + st, ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(f_full + st, TB);
+          bulk_g2s(sF + (size_t)st * TB, a.fb + (size_t)i * TB, TB, f_full + st);
+        }
+        __syncwarp();
+      }
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tc_fence_before();
-  }
-  __syncthreads();  // scratch is free again; the tile is visible to the MMA warp
-  tc_fence_after();
-
-  if (warp == 1) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr uint32_t lbo_f = BM * 16u, sbo = 128u;
-      constexpr uint32_t ks_f = (2u * lbo_f) >> 4;
-      const uint32_t lbo_x = (uint32_t)cv.xrows * 16u, ks_x = (2u * lbo_x) >> 4;
-      const uint32_t base = smem_u32(smem);
-      const int ksteps = KD >> 3;
-      const uint32_t idesc1 = make_idesc_tf32(BN, BM, 0, 0);
-      const uint32_t idesc2 = make_idesc_tf32(BN, cv.n2, 0, 0);
-      const uint32_t t_bhi = tmem_base + COL_BHI, t_blo = tmem_base + COL_BLO, t_stat = tmem_base + COL_STAT;
-      uint32_t k = 0, n_drains = 0;
-      bool prev_first = true, prev_flush = false, pending_drain = false, first_in_seg = true, more = true;
-      // GEMM 2 of block p: statistics += gamma (TMEM, in the logit columns of p) . Xt[p % 3] (shared memory)
-      auto gemm2 = [&](uint32_t p, bool first, bool flush) {
-        mbar_wait(g_full + (p & 1u), (p >> 1) & 1u);
-        if (pending_drain) {
-          mbar_wait(drained, n_drains & 1u);
-          ++n_drains;
-          pending_drain = false;
-        }
+    if (i0 < i1) {
+      constexpr uint32_t lbo = IMG * 16u, sbo = 128u;  // 128-row K-major images: chunk stride 2 KB, 8-row groups contiguous
+      constexpr uint32_t kstep = (2u * lbo) >> 4;      // one K = 16 step = two 16-byte chunks
+      const uint32_t idesc = make_idesc_bf16(IMG, BN);
+      const int ksteps = KDb >> 4;
+      const uint32_t half_units = (TB >> 1) >> 4;      // hi -> lo inside an image, in descriptor units
+      const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo, sbo), f_desc0 = make_desc(smem_u32(sF), lbo, sbo);
+      mbar_wait(b_full, 0);
+      uint32_t k = 0;
+      for (int64_t i = i0; i < i1; ++i, ++k) {
+        const uint32_t st = k % NS_L, ph = (k / NS_L) & 1u;
+        mbar_wait(f_full + st, ph);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t xb = base + (uint32_t)(cv.o_x + (size_t)(p % NX) * 2 * cv.x_bytes);
-          const uint64_t xhi = make_desc(xb, lbo_x, sbo), xlo = make_desc(xb + (uint32_t)cv.x_bytes, lbo_x, sbo);
-          const uint32_t t_gam = tmem_base + COL_LOGIT + 64u * (p & 1u);
-          for (int q = 0; q < BM / 8; ++q) tc_mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
-          for (int q = 0; q < BM / 8; ++q) tc_mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
-          tc_commit(x_free + (p % NX));
-        }
-        __syncwarp();
-        if (flush) pending_drain = true;
-      };
-      while (more) {
-        const int nt = w.nt();
-        mbar_wait(a_full + (k & 1u), (k >> 1) & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t fb = base + (uint32_t)((size_t)(k & 1u) * 2 * cv.f_bytes);
-          const uint64_t fhi = make_desc(fb, lbo_f, sbo), flo = make_desc(fb + (uint32_t)cv.f_bytes, lbo_f, sbo);
-          const uint32_t t_log = tmem_base + COL_LOGIT + 64u * (k & 1u);
-          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_log, t_bhi + 8u * q, fhi + (uint64_t)(q * ks_f), idesc1, q > 0 ? 1u : 0u);
-          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_log, t_bhi + 8u * q, flo + (uint64_t)(q * ks_f), idesc1, 1u);
-          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_log, t_blo + 8u * q, fhi + (uint64_t)(q * ks_f), idesc1, 1u);
-          tc_commit(l_full + (k & 1u));
-        }
-        __syncwarp();
-        if (k > 0) gemm2(k - 1, prev_first, prev_flush);
-        bool flush;
-        more = w.next(nt, flush);
-        prev_first = first_in_seg;
-        prev_flush = flush;
-        first_in_seg = flush;
-        ++k;
-      }
-      gemm2(k - 1, prev_first, prev_flush);
-    }
-  } else if (warp >= 2) {
-    // ===================== operand builders (thread == frame) and epilogue (thread == component) =====================
-    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == component row within the tile
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int et = tid - 64;                   // 0..511
-    const int cq = (warp - 2) >> 2;            // which 16 of a block's 64 frame columns this warp turns into gamma
-    const int fr = et & (BM - 1), part = et >> 6;  // frame row this thread builds, and which eighth of its K chunks
-    const bool norm_thread = part == 7;        // these 64 threads also own the per-frame normaliser
-    const float LN2 = 0.69314718055994530942f;
-    const int n_part = 2 * a.n_tiles;
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
-      constexpr int PT = 8;
-      float pf[R];
-      float2 pp[PT];
-      auto prefetch = [&](const Walk<BM>& wb) {
-        prefetch_block<R>(a.feats + wb.t0 * D, wb.nt() * D, et, pf);
-        if (norm_thread && fr < wb.nt()) {
-#pragma unroll
-          for (int y = 0; y < PT; ++y)
-            if (y < n_part) pp[y] = a.partial[(size_t)y * a.total_frames + wb.t0 + fr];
-        }
-      };
-      prefetch(w);
-      uint32_t k = 0, n_drained = 0;
-      bool more = true, prev_flush = false;
-      int prev_seg = -1, ll_seg = -1;
-      float ll_acc = 0.f;
-      auto flush_ll = [&]() {
-        if (tile == 0 && ll_seg >= 0) {
-          const float tot = warp_sum(ll_acc);
-          if (lane == 0 && tot != 0.f) atomicAdd(a.out_loglik + ll_seg, (double)tot);
-        }
-        ll_acc = 0.f;
-      };
-      // logits of block p -> gamma in place; at a segment end also read out the statistics
-      auto epilogue = [&](uint32_t p, int seg_id, bool flush) {
-        mbar_wait(l_full + (p & 1u), (p >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t t_log = tmem_base + lane_addr + COL_LOGIT + 64u * (p & 1u) + 16u * cq;
-        const float* lse = sLse + (p % NX) * BM + 16 * cq;
-        uint32_t r[16];
-        tc_ld16(t_log, r);
-        float gam[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 ls = *reinterpret_cast<const float4*>(lse + 4 * q);
-          gam[4 * q + 0] = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
-          gam[4 * q + 1] = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
-          gam[4 * q + 2] = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
-          gam[4 * q + 3] = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
-        }
-        tc_st16(t_log, gam);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(g_full + (p & 1u));
-        if (flush) {
-          mbar_wait(x_free + (p % NX), (p / NX) & 1u);  // GEMM 2 of block p (and of everything before it) is complete
+        const uint64_t fh = f_desc0 + (uint64_t)(st * (TB >> 4)), fl = fh + half_units;
+        for (int t = 0; t < ntl; ++t) {
+          const uint32_t slot = 2u * (k & 1u) + (uint32_t)t;
+          mbar_wait(t_empty + slot, ((k >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const int comp = tile * BN + row;
-          const uint32_t saddr = tmem_base + lane_addr + COL_STAT;
-#pragma unroll 1
-          for (int c0 = 16 * cq; c0 < KD; c0 += 64) {
-            uint32_t s16[16];
-            tc_ld16(saddr + c0, s16);
-            if (comp < a.K) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int jj = c0 + e;
-                const double v = (double)__uint_as_float(s16[e]);
-                if (jj < D) atomicAdd(a.out_f + ((int64_t)seg_id * a.K + comp) * D + jj, v);
-                else if (jj < 2 * D) atomicAdd(a.out_s + ((int64_t)seg_id * a.K + comp) * D + (jj - D), v);
-                else if (jj == 2 * D) atomicAdd(a.out_n + (int64_t)seg_id * a.K + comp, v);
-              }
-            }
+          if (elect_one()) {
+            const uint32_t d = tmem_base + slot * BN;
+            const uint64_t bh = b_desc0 + (uint64_t)(t * (TB >> 4)), bl = bh + half_units;
+            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, fh + (uint64_t)(q * kstep), bh + (uint64_t)(q * kstep), idesc, q > 0 ? 1u : 0u);
+            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, fl + (uint64_t)(q * kstep), bh + (uint64_t)(q * kstep), idesc, 1u);
+            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, fh + (uint64_t)(q * kstep), bl + (uint64_t)(q * kstep), idesc, 1u);
+            tc_commit(t_full + slot);
           }
-          tc_fence_before();
-          mbar_arrive(drained);
-          ++n_drained;
+          __syncwarp();
         }
-      };
-      while (more) {
-        const int nt = w.nt();
-        const int64_t t0 = w.t0;
-        const int seg_id = w.cur;
-        if (seg_id != ll_seg) {
-          flush_ll();
-          ll_seg = seg_id;
-        }
-        // ---- build block k: F[k & 1] was released by GEMM1(k - 2) (waited for in the epilogue of k - 2), Xt[k % 3] by
-        // GEMM2(k - 3)
-        mbar_wait(x_free + (k % NX), ((k / NX) & 1u) ^ 1u);
-        store_block<R>(sStage, nt * D, et, pf);
-        if (norm_thread) {
-          float lse2 = 3.0e38f;  // dead frames: gamma = 2^(x - huge) = 0
-          if (fr < nt) {
-            float m = -3.0e38f;
-#pragma unroll
-            for (int y = 0; y < PT; ++y)
-              if (y < n_part) m = fmaxf(m, pp[y].x);
-            for (int y = PT; y < n_part; ++y) m = fmaxf(m, a.partial[(size_t)y * a.total_frames + t0 + fr].x);
-            float ssum = 0.f;
-#pragma unroll
-            for (int y = 0; y < PT; ++y)
-              if (y < n_part) ssum += pp[y].y * ex2(pp[y].x - m);
-            for (int y = PT; y < n_part; ++y) {
-              const float2 p = a.partial[(size_t)y * a.total_frames + t0 + fr];
-              ssum += p.y * ex2(p.x - m);
-            }
-            lse2 = m + lg2(ssum);
-            if (tile == 0) {
-              const float lse = lse2 * LN2;
-              a.frame_lse[t0 + fr] = lse;
-              ll_acc += lse;
-            }
-          }
-          sLse[(k % NX) * BM + fr] = lse2;
-        }
-        named_bar_sync(1, EPI);
-        {
-          const bool live = fr < nt;
-          const float* xr = sStage + fr * D;
-          unsigned char* fb = smem + (size_t)(k & 1u) * 2 * cv.f_bytes;
-          unsigned char* xb = smem + cv.o_x + (size_t)(k % NX) * 2 * cv.x_bytes;
-          float4* dhi = reinterpret_cast<float4*>(fb) + fr;
-          float4* dlo = reinterpret_cast<float4*>(fb + cv.f_bytes) + fr;
-          float* xth = reinterpret_cast<float*>(xb) + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
-          float* xtl = reinterpret_cast<float*>(xb + cv.x_bytes) + ((size_t)(fr >> 2) * cv.xrows) * 4 + (fr & 3);
-          for (int jc = part; jc < KC; jc += 8) {
-            float h[4], l[4];
-            chunk_split(xr, jc, D, live, h, l);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              xth[(4 * jc + e) * 4] = h[e];
-              xtl[(4 * jc + e) * 4] = l[e];
-            }
-            dhi[jc * BM] = make_float4(h[0], h[1], h[2], h[3]);
-            dlo[jc * BM] = make_float4(l[0], l[1], l[2], l[3]);
-          }
-          if (part == 0)
-            for (int jx = KD; jx < cv.n2; ++jx) { xth[jx * 4] = 0.f; xtl[jx * 4] = 0.f; }
-        }
-        named_bar_sync(1, EPI);  // staging consumed before the next block's store
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(a_full + (k & 1u));
-        {
-          Walk<BM> wn = w;
-          bool fl;
-          if (wn.next(nt, fl)) prefetch(wn);
-        }
-        // ---- gamma of the previous block while the tensor core works on this one
-        if (k > 0) epilogue(k - 1, prev_seg, prev_flush);
-        bool flush;
-        more = w.next(nt, flush);
-        prev_seg = seg_id;
-        prev_flush = flush;
-        ++k;
+        if (elect_one()) tc_commit(f_empty + st);
+        __syncwarp();
       }
-      epilogue(k - 1, prev_seg, prev_flush);
-      flush_ll();
-      (void)n_drained;
+    }
+  } else {
+    // ===================== epilogue: thread == (frame row, 64 of a tile's 128 columns) =====================
+    const int ew = warp - 2;
+    const int t = ew >> 3, half = (ew >> 2) & 1, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    if (t < ntl && i0 < i1) {
+      float2* dst = a.partial + (size_t)(2 * (tile0 + t) + half) * a.P + row;
+      uint32_t k = 0;
+      for (int64_t i = i0; i < i1; ++i, ++k) {
+        const uint32_t slot = 2u * (k & 1u) + (uint32_t)t;
+        mbar_wait(t_full + slot, (k >> 1) & 1u);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        const uint32_t taddr = tmem_base + lane_addr + slot * BN + half * 64;
+        tc_ld32_issue(taddr, ra);
+        tc_ld32_issue(taddr + 32, rb);
+        tc_ld_wait2(ra, rb);
+        tc_fence_before();
+        mbar_arrive(t_empty + slot);
+        float cm = max3(__uint_as_float(ra[0]), __uint_as_float(ra[1]), __uint_as_float(rb[0]));
+#pragma unroll
+        for (int e = 2; e < 32; e += 2) cm = max3(cm, __uint_as_float(ra[e]), __uint_as_float(ra[e + 1]));
+#pragma unroll
+        for (int e = 1; e < 31; e += 2) cm = max3(cm, __uint_as_float(rb[e]), __uint_as_float(rb[e + 1]));
+        cm = fmaxf(cm, __uint_as_float(rb[31]));
+        const float s = exp_sum32<kPoly>(ra, cm) + exp_sum32<kPoly>(rb, cm);
+        dst[i * IMG] = make_float2(cm, s);
+      }
     }
   }
   tc_fence_before();
@@ -514,44 +406,68 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-
-// ================================================================================================ pass LSE
-// The frame operand [x, x^2, 1, 1] (TF32 hi + lo) is written straight into
-// tensor memory (tcgen05.st, thread == frame row == TMEM lane) and double-buffered there (2 x 160 columns), the model
-// tile stays in shared memory as the N-side operand, one 128-column accumulator.  Thread program per block k: build
-// A[k & 1] (needs GEMM(k - 2) done), then the epilogue of block k - 1 (tcgen05.ld, release the accumulator at once,
-// max / exp / sum from registers); MMA program: GEMM(k) once A[k & 1] is built and the accumulator has been read.
-// The split of block k + 1 overlaps GEMM(k); in steady state the period is ~1920 tensor cycles + one TMEM read.
-namespace l2 {
-constexpr uint32_t COL_A = 0;      // + 160 * (k & 1): hi at +0, lo at +80
-constexpr uint32_t COL_ACC = 320;  // 128 columns
+// partials -> lse2 per padded frame, frame_lse per frame, log-likelihood per segment.  4 blocks per CTA.
+__global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
+  const int64_t nb = a.blk_start[a.n_segs];
+  const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int r = threadIdx.x & 63, lane = threadIdx.x & 31;
+  if (b >= ((nb + 1) & ~(int64_t)1)) return;
+  const int nt = a.blk_nt[b];
+  const int64_t p = b * BLK + r;
+  float lse2 = 3.0e38f, ll = 0.f;  // dead rows: gamma = 2^(x - huge) = 0
+  if (r < nt) {
+    const int n_part = 2 * a.n_tiles;
+    float m = -3.0e38f;
+    for (int y = 0; y < n_part; ++y) m = fmaxf(m, a.partial[(size_t)y * a.P + p].x);
+    float s = 0.f;
+    for (int y = 0; y < n_part; ++y) {
+      const float2 q = a.partial[(size_t)y * a.P + p];
+      s += q.y * ex2(q.x - m);
+    }
+    lse2 = m + lg2(s);
+    ll = lse2 * 0.69314718055994530942f;
+    a.frame_lse[a.blk_t0[b] + r] = ll;
+  }
+  a.lse2[p] = lse2;
+  const float tot = warp_sum(ll);
+  if (lane == 0 && nt > 0 && tot != 0.f) atomicAdd(a.out_loglik + a.blk_seg[b], (double)tot);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
-  using namespace l2;
+// ================================================================================================ pass STATS
+// grid = (block chunks, tile pairs).  Shared memory: the pair's model tiles + NS_S stages of (Fb half image, Xt image,
+// 64 lse values); tensor memory: logits / gamma [tile][buffer] 64 columns each, statistics [tile] KDb columns.
+namespace p3 {
+constexpr uint32_t COL_LOGIT = 0;    // + 64 * (2 * tile + buffer)
+constexpr uint32_t COL_STAT = 256;   // + KDb * tile
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) {
+  using namespace p3;
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int BM = BM1;
-  const int KD = a.KD, D = a.D;
-  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
-  float* sBhi = reinterpret_cast<float*>(smem);
-  float* sBlo = sBhi + BN * KD;
-  float* sX = sBlo + BN * KD;  // feature staging: BM x D floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + BM * MAX_KD / 2);
-  uint64_t* b_full = bars;
-  uint64_t* a_full = bars + 1;    // [2] A[k & 1] is built
-  uint64_t* l_full = bars + 3;    // [2] GEMM(k) complete: accumulator holds block k, A[k & 1] is free
-  uint64_t* acc_free = bars + 5;  // the epilogue warps hold the accumulator's contents in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int KDb = a.KDb, D = a.D;
+  const uint32_t TB = 512u * (uint32_t)KDb;     // model tile image; also one Xt image
+  const uint32_t FB = TB >> 1;                  // the 64-row half of an Fb image (hi + lo)
+  const uint32_t STAGE = FB + TB + 256u;        // + 64 lse values
+  unsigned char* sB = smem;                     // [2][TB]
+  unsigned char* sS = smem + 2 * (size_t)TB;    // [NS_S][STAGE]: F half | Xt | lse
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)NS_S * STAGE);
+  uint64_t* b_full = bars;           // model tiles landed
+  uint64_t* s_full = bars + 1;       // [NS_S]
+  uint64_t* s_empty = s_full + NS_S; // [NS_S] statistics GEMMs of the step are complete
+  uint64_t* l_full = s_empty + NS_S; // [4] logits of (tile, buffer) are in TMEM
+  uint64_t* g_full = l_full + 4;     // [4] gamma of (tile, buffer) is in TMEM
+  uint64_t* st_done = g_full + 4;    // [2] per tile: every statistics GEMM issued so far is complete
+  uint64_t* drained = st_done + 2;   // [2] per tile: the accumulator has been read out after a segment end
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.y;
+  const int tile0 = 2 * blockIdx.y;
+  const int ntl = min(2, a.n_tiles - tile0);
   if (tid == 0) {
     mbar_init(b_full, 1);
-    mbar_init(a_full, EPI);
-    mbar_init(a_full + 1, EPI);
-    mbar_init(l_full, 1);
-    mbar_init(l_full + 1, 1);
-    mbar_init(acc_free, EPI / 2);
+    for (int i = 0; i < NS_S; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(l_full + i, 1); mbar_init(g_full + i, EPI / 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(st_done + i, 1); mbar_init(drained + i, EPI / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -562,130 +478,167 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int64_t begin = (int64_t)blockIdx.x * a.chunk;
-  const int64_t end = min(begin + a.chunk, a.total_frames);
+  const int64_t nb = a.blk_start[a.n_segs];
+  const int64_t per = (nb + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = (int64_t)blockIdx.x * per, b1 = min(b0 + per, nb);
 
   if (warp == 0) {
-    if (begin < end && elect_one()) {
-      mbar_arrive_expect_tx(b_full, 2u * tile_bytes);
-      bulk_g2s(sBhi, a.tiles_hi + (size_t)tile * BN * KD, tile_bytes, b_full);
-      bulk_g2s(sBlo, a.tiles_lo + (size_t)tile * BN * KD, tile_bytes, b_full);
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr uint32_t lbo = BN * 16u, sbo = 128u;
-      constexpr uint32_t kstep = (2u * lbo) >> 4;
-      const uint64_t bhi = make_desc(smem_u32(sBhi), lbo, sbo), blo = make_desc(smem_u32(sBlo), lbo, sbo);
-      const int ksteps = KD >> 3;
-      const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
-      const uint32_t t_acc = tmem_base + COL_ACC;
-      mbar_wait(b_full, 0);
+    // ===================== producer =====================
+    if (b0 < b1) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full, (uint32_t)ntl * TB);
+        for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, a.tiles + (size_t)(tile0 + t) * TB, TB, b_full);
+      }
+      __syncwarp();
+      const int n_pieces = 2 * (KDb >> 3);  // (hi | lo) x chunk: 1 KB each, 64 rows x 16 B out of a 128-row chunk
       uint32_t k = 0;
-      bool more = true;
-      while (more) {
-        const int nt = w.nt();
-        mbar_wait(a_full + (k & 1u), (k >> 1) & 1u);
-        if (k > 0) mbar_wait(acc_free, (k - 1) & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t ahi = tmem_base + COL_A + 160u * (k & 1u), alo = ahi + 80u;
-          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_acc, ahi + 8u * q, bhi + (uint64_t)(q * kstep), idesc, q > 0 ? 1u : 0u);
-          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_acc, alo + 8u * q, bhi + (uint64_t)(q * kstep), idesc, 1u);
-          for (int q = 0; q < ksteps; ++q) tc_mma_tf32_ts(t_acc, ahi + 8u * q, blo + (uint64_t)(q * kstep), idesc, 1u);
-          tc_commit(l_full + (k & 1u));
+      for (int64_t b = b0; b < b1; ++b, ++k) {
+        const uint32_t st = k % NS_S, ph = (k / NS_S) & 1u;
+        mbar_wait(s_empty + st, ph ^ 1u);
+        unsigned char* dst = sS + (size_t)st * STAGE;
+        if (lane == 0) mbar_arrive_expect_tx(s_full + st, STAGE);
+        __syncwarp();
+        const unsigned char* img = a.fb + (size_t)(b >> 1) * TB + (size_t)(b & 1) * (BLK * 16);
+        for (int pc = lane; pc < n_pieces; pc += 32) bulk_g2s(dst + (size_t)pc * 1024, img + (size_t)pc * 2048, 1024u, s_full + st);
+        if (lane == 31) {
+          bulk_g2s(dst + FB, a.xt + (size_t)b * TB, TB, s_full + st);
+          bulk_g2s(dst + FB + TB, a.lse2 + b * BLK, 256u, s_full + st);
         }
         __syncwarp();
-        bool flush;
-        more = w.next(nt, flush);
-        ++k;
       }
     }
-  } else {
-    const int row = ((warp & 3) << 5) | lane;  // TMEM lane == frame row (built AND reduced by this thread's warp quadrant)
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int et = tid - 64;                   // 0..511
-    const int part = (warp - 2) >> 2;          // 0..3: which K columns this thread builds; epilogue: parts 0, 1 take 64 columns each
-    const bool epi_warp = part < 2;
-    Walk<BM> w;
-    if (w.start(a.seg, a.n_segs, begin, end)) {
-      constexpr int R = (BM * (MAX_KD / 2 - 1) + EPI - 1) / EPI;  // D <= 39
-      float pf[R];
-      prefetch_block<R>(a.feats + w.t0 * D, w.nt() * D, et, pf);
-      uint32_t k = 0;
-      bool more = true;
-      int prev_nt = 0;
-      int64_t prev_t0 = 0;
-      // block p: accumulator -> registers -> (max, sum 2^(x - max)) over this thread's 64 columns
-      auto epilogue = [&](uint32_t p, int nt_p, int64_t t0_p) {
-        mbar_wait(l_full + (p & 1u), (p >> 1) & 1u);
-        tc_fence_after();
-        uint32_t ra[32], rb[32];
-        const uint32_t taddr = tmem_base + lane_addr + COL_ACC + part * 64;
-        tc_ld32_issue(taddr, ra);
-        tc_ld32_issue(taddr + 32, rb);
-        tc_ld_wait2(ra, rb);
-        tc_fence_before();
-        mbar_arrive(acc_free);
-        float cm = max3(__uint_as_float(ra[0]), __uint_as_float(ra[1]), __uint_as_float(rb[0]));
-#pragma unroll
-        for (int e = 2; e < 32; e += 2) cm = max3(cm, __uint_as_float(ra[e]), __uint_as_float(ra[e + 1]));
-#pragma unroll
-        for (int e = 1; e < 31; e += 2) cm = max3(cm, __uint_as_float(rb[e]), __uint_as_float(rb[e + 1]));
-        cm = fmaxf(cm, __uint_as_float(rb[31]));
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          acc0 += ex2(__uint_as_float(ra[e]) - cm);
-          acc1 += ex2(__uint_as_float(ra[e + 1]) - cm);
-          acc2 += ex2(__uint_as_float(rb[e]) - cm);
-          acc3 += ex2(__uint_as_float(rb[e + 1]) - cm);
-        }
-        if (row < nt_p) a.partial[(size_t)(2 * tile + part) * a.total_frames + t0_p + row] = make_float2(cm, (acc0 + acc1) + (acc2 + acc3));
-      };
-      while (more) {
-        const int nt = w.nt();
-        const int64_t t0 = w.t0;
-        // ---- build A[k & 1]: GEMM(k - 2), its last reader, must be complete
-        if (k >= 2) {
-          mbar_wait(l_full + (k & 1u), ((k - 2) >> 1) & 1u);
-          tc_fence_after();
-        }
-        store_block<R>(sX, nt * D, et, pf);
-        named_bar_sync(1, EPI);
-        {
-          Walk<BM> wn = w;
-          bool fl;
-          if (wn.next(nt, fl)) prefetch_block<R>(a.feats + wn.t0 * D, wn.nt() * D, et, pf);
-        }
-        {
-          const bool live = row < nt;
-          const float* xr = sX + row * D;
-          const uint32_t t_hi = tmem_base + lane_addr + COL_A + 160u * (k & 1u), t_lo = t_hi + 80u;
-          for (int c = part; c < (KD >> 3); c += 4) {  // 8 contraction columns at a time
-            float h0[4], l0[4], h1[4], l1[4];
-            chunk_split(xr, 2 * c, D, live, h0, l0);
-            chunk_split(xr, 2 * c + 1, D, live, h1, l1);
-            const float hv[8] = {h0[0], h0[1], h0[2], h0[3], h1[0], h1[1], h1[2], h1[3]};
-            const float lv[8] = {l0[0], l0[1], l0[2], l0[3], l1[0], l1[1], l1[2], l1[3]};
-            tc_st8(t_hi + 8u * c, hv);
-            tc_st8(t_lo + 8u * c, lv);
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (b0 < b1) {
+      constexpr uint32_t sbo = 128u;
+      constexpr uint32_t lbo_b = BN * 16u, lbo_f = BLK * 16u;
+      constexpr uint32_t ks_b = (2u * lbo_b) >> 4, ks_f = (2u * lbo_f) >> 4;
+      const uint32_t lbo_x = (uint32_t)KDb * 16u, ks_x = (2u * lbo_x) >> 4;
+      const uint32_t idesc1 = make_idesc_bf16(BN, BLK);
+      const uint32_t idesc2 = make_idesc_tf32(BN, KDb, 0, 0);
+      const int ksteps = KDb >> 4;
+      const uint32_t sB_u = smem_u32(sB), sS_u = smem_u32(sS);
+      mbar_wait(b_full, 0);
+      bool pending_drain[2] = {false, false};
+      uint32_t n_drains[2] = {0u, 0u};
+      // statistics GEMM of step p: stats[tile] += gamma (TMEM, in the logit columns of (tile, p & 1)) . Xt (stage p % NS_S)
+      auto gemm2 = [&](uint32_t p, bool first, bool flush) {
+        const uint32_t st = p % NS_S;
+        const uint32_t xb = sS_u + st * STAGE + FB;
+        const uint64_t xhi = make_desc(xb, lbo_x, sbo), xlo = make_desc(xb + (TB >> 1), lbo_x, sbo);
+        for (int t = 0; t < ntl; ++t) {
+          const uint32_t lb = 2u * (uint32_t)t + (p & 1u);
+          mbar_wait(g_full + lb, (p >> 1) & 1u);
+          if (pending_drain[t]) {
+            mbar_wait(drained + t, n_drains[t] & 1u);
+            ++n_drains[t];
+            pending_drain[t] = false;
           }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t t_gam = tmem_base + COL_LOGIT + 64u * lb, t_stat = tmem_base + COL_STAT + (uint32_t)(t * KDb);
+            for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
+            for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
+            if (flush) tc_commit(st_done + t);
+            if (t == ntl - 1) tc_commit(s_empty + st);
+          }
+          __syncwarp();
+          if (flush) pending_drain[t] = true;
         }
-        named_bar_sync(1, EPI);  // staged rows consumed before the next block overwrites them
-        tc_fence_before();
-        mbar_arrive(a_full + (k & 1u));
-        // ---- epilogue of the previous block while the tensor core works on this one
-        if (k > 0 && epi_warp) epilogue(k - 1, prev_nt, prev_t0);
-        prev_nt = nt;
-        prev_t0 = t0;
-        bool flush;
-        more = w.next(nt, flush);
-        ++k;
+      };
+      uint32_t k = 0;
+      bool prev_first = true, prev_flush = false;
+      int seg_cur = a.blk_seg[b0];
+      bool first_in_seg = true;
+      for (int64_t b = b0; b < b1; ++b, ++k) {
+        const uint32_t st = k % NS_S;
+        mbar_wait(s_full + st, (k / NS_S) & 1u);
+        tc_fence_after();
+        const uint32_t fb_u = sS_u + st * STAGE;
+        const uint64_t fh = make_desc(fb_u, lbo_f, sbo), fl = make_desc(fb_u + (FB >> 1), lbo_f, sbo);
+        for (int t = 0; t < ntl; ++t) {
+          // the logit buffer (t, k & 1) was last read by the statistics GEMM of step k - 2, issued before this one
+          if (elect_one()) {
+            const uint32_t lb = 2u * (uint32_t)t + (k & 1u);
+            const uint32_t d = tmem_base + COL_LOGIT + 64u * lb;
+            const uint64_t bh = make_desc(sB_u + (uint32_t)t * TB, lbo_b, sbo), bl = make_desc(sB_u + (uint32_t)t * TB + (TB >> 1), lbo_b, sbo);
+            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, bh + (uint64_t)(q * ks_b), fh + (uint64_t)(q * ks_f), idesc1, q > 0 ? 1u : 0u);
+            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, bh + (uint64_t)(q * ks_b), fl + (uint64_t)(q * ks_f), idesc1, 1u);
+            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, bl + (uint64_t)(q * ks_b), fh + (uint64_t)(q * ks_f), idesc1, 1u);
+            tc_commit(l_full + lb);
+          }
+          __syncwarp();
+        }
+        if (k > 0) gemm2(k - 1, prev_first, prev_flush);
+        const int seg_next = (b + 1 < b1) ? a.blk_seg[b + 1] : -2;
+        prev_first = first_in_seg;
+        prev_flush = seg_next != seg_cur;
+        first_in_seg = prev_flush;
+        seg_cur = seg_next;
       }
-      if (epi_warp) epilogue(k - 1, prev_nt, prev_t0);
+      gemm2(k - 1, prev_first, prev_flush);
+    }
+  } else {
+    // ===================== epilogue: thread == (component row, 32 of a step's 64 frames) =====================
+    const int ew = warp - 2;
+    const int t = ew >> 3, cq = (ew >> 2) & 1, quad = warp & 3;
+    const int row = quad * 32 + lane;  // TMEM lane == component row within the tile
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    if (t < ntl && b0 < b1) {
+      const int comp = (tile0 + t) * BN + row;
+      uint32_t k = 0, n_flush = 0;
+      int seg_cur = a.blk_seg[b0];
+      for (int64_t b = b0; b < b1; ++b, ++k) {
+        const uint32_t st = k % NS_S, lb = 2u * (uint32_t)t + (k & 1u);
+        mbar_wait(s_full + st, (k / NS_S) & 1u);   // the stage's lse values (written by the bulk copy) are visible
+        const float* lse = reinterpret_cast<const float*>(sS + (size_t)st * STAGE + FB + TB) + 32 * cq;
+        mbar_wait(l_full + lb, (k >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_log = tmem_base + lane_addr + COL_LOGIT + 64u * lb + 32u * (uint32_t)cq;
+        uint32_t r[32];
+        tc_ld32_issue(t_log, r);
+        tc_ld_wait(r);
+        float gam[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ls = *reinterpret_cast<const float4*>(lse + 4 * q);
+          gam[4 * q + 0] = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
+          gam[4 * q + 1] = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
+          gam[4 * q + 2] = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
+          gam[4 * q + 3] = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
+        }
+        tc_st32(t_log, gam);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(g_full + lb);
+        const int seg_next = (b + 1 < b1) ? a.blk_seg[b + 1] : -2;
+        if (seg_next != seg_cur) {
+          // last step of a segment inside this chunk: wait for its statistics GEMMs, add the accumulator to the outputs
+          mbar_wait(st_done + t, n_flush & 1u);
+          ++n_flush;
+          tc_fence_after();
+          const uint32_t saddr = tmem_base + lane_addr + COL_STAT + (uint32_t)(t * KDb);
+          const int half_cols = KDb >> 1;  // a multiple of 8
+#pragma unroll 1
+          for (int c0 = cq * half_cols; c0 < (cq + 1) * half_cols; c0 += 8) {
+            uint32_t s8[8];
+            tc_ld8(saddr + c0, s8);
+            if (comp < a.K) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int jj = c0 + e;
+                const double v = (double)__uint_as_float(s8[e]);
+                if (jj < D) atomicAdd(a.out_f + ((int64_t)seg_cur * a.K + comp) * D + jj, v);
+                else if (jj < 2 * D) atomicAdd(a.out_s + ((int64_t)seg_cur * a.K + comp) * D + (jj - D), v);
+                else if (jj == 2 * D) atomicAdd(a.out_n + (int64_t)seg_cur * a.K + comp, v);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(drained + t);
+        }
+        seg_cur = seg_next;
+      }
     }
   }
   tc_fence_before();
@@ -695,15 +648,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
 
 }  // namespace em
 
-bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_lo != 0 && L.n_models == 1; }
+bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_bf != 0 && L.n_models == 1; }
 
-int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames) {
-  return stats_tc_supported(L) ? (int64_t)sizeof(float2) * 2 * (L.Kp / em::BN) * total_frames : 0;
+int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames, int64_t n_segs) {
+  return stats_tc_supported(L) ? (int64_t)em::ws_layout(L, total_frames, n_segs).bytes : 0;
 }
 
 int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames, const void* pack,
                     const PackLayout& L, float* frame_lse, double* out_n, double* out_f, double* out_s, double* out_loglik,
-                    void* workspace, cudaStream_t st) {
+                    void* workspace, bool reuse_images, cudaStream_t st) {
   using namespace em;
   SSP_CUDA_OK(cudaMemsetAsync(out_loglik, 0, sizeof(double) * n_segs, st));
   if (total_frames == 0) return SSP_OK;
@@ -713,37 +666,68 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
     SSP_CUDA_OK(cudaGetDevice(&dev));
     SSP_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const Ws w = ws_layout(L, total_frames, n_segs);
+  unsigned char* base = (unsigned char*)workspace;
   Args a;
   a.feats = feats;
   a.seg = seg_offsets;
   a.n_segs = n_segs;
   a.total_frames = total_frames;
-  a.n_tiles = L.Kp / BN;
-  int64_t gx = num_sms / a.n_tiles;
-  if (gx < 1) gx = 1;
-  int64_t chunk = (total_frames + gx - 1) / gx;
-  chunk = (chunk + BM1 - 1) / BM1 * BM1;
-  gx = (total_frames + chunk - 1) / chunk;
-  a.chunk = chunk;
-  a.tiles_hi = (const float*)((const char*)pack + L.off_tile);
-  a.tiles_lo = (const float*)((const char*)pack + L.off_tile_lo);
+  a.blk_start = (int64_t*)(base + w.o_blk_start);
+  a.blk_seg = (int32_t*)(base + w.o_blk_seg);
+  a.blk_t0 = (int64_t*)(base + w.o_blk_t0);
+  a.blk_nt = (int32_t*)(base + w.o_blk_nt);
+  a.lse2 = (float*)(base + w.o_lse2);
+  a.partial = (float2*)(base + w.o_partial);
+  a.fb = base + w.o_fb;
+  a.xt = base + w.o_xt;
+  a.nb_max = w.nb_max;
+  a.P = w.P;
+  a.tiles = (const unsigned char*)pack + L.off_tile_bf;
   a.K = L.K;
   a.D = L.D;
-  a.KD = L.KD;
-  a.partial = (float2*)workspace;
+  a.KDb = w.KDb;
+  a.n_tiles = L.Kp / BN;
   a.frame_lse = frame_lse;
   a.out_n = out_n;
   a.out_f = out_f;
   a.out_s = out_s;
   a.out_loglik = out_loglik;
-  const size_t smem_lse = (size_t)(2 * BN * L.KD + BM1 * MAX_KD / 2) * sizeof(float) + 128;
-  const size_t smem_stats = p3::carve(L.KD).bytes;
-  dim3 grid((unsigned)gx, (unsigned)a.n_tiles);
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lse));
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats));
-  gmm_em_lse_kernel<<<grid, THREADS, smem_lse, st>>>(a);
+  if (!reuse_images) {
+    em_plan_kernel<<<1, 1024, 0, st>>>(a);
+    SSP_LAUNCH_CHECK("em_plan_kernel");
+    em_prep_kernel<<<(unsigned)w.nb_max, 256, 0, st>>>(a);
+    SSP_LAUNCH_CHECK("em_prep_kernel");
+  }
+  const int n_pairs = (a.n_tiles + 1) / 2;
+  // the number of blocks is a device value (segment padding); size the grids from its host-side bounds
+  const int64_t nb_lo = (total_frames + BLK - 1) / BLK;
+  int64_t gx = num_sms / n_pairs;
+  if (gx < 1) gx = 1;
+  const int64_t gx_l = min(gx, (nb_lo + 1) / 2), gx_s = min(gx, nb_lo);
+  const size_t TB = w.img_bytes();
+  const size_t smem_lse = (2 + NS_L) * TB + 16 * sizeof(uint64_t) + 64;
+  const size_t smem_stats = 2 * TB + NS_S * (TB / 2 + TB + 256) + 24 * sizeof(uint64_t) + 64;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("SSP_EM_POLY_PAIRS");  // share of the LSE pass's exponentials on the FMA pipe (pairs of 16)
+    poly = e ? atoi(e) : 4;
+  }
+#define SSP_EM_LSE(pp)                                                                                               \
+  case pp:                                                                                                           \
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel<pp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lse)); \
+    gmm_em_lse_kernel<pp><<<dim3((unsigned)gx_l, (unsigned)n_pairs), THREADS, smem_lse, st>>>(a);                   \
+    break;
+  switch (poly) {
+    SSP_EM_LSE(0) SSP_EM_LSE(2) SSP_EM_LSE(4) SSP_EM_LSE(6) SSP_EM_LSE(8)
+    default: SSP_REQUIRE(false, "SSP_EM_POLY_PAIRS must be 0, 2, 4, 6 or 8 (got %d)", poly);
+  }
+#undef SSP_EM_LSE
   SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
-  gmm_em_stats_kernel<<<grid, THREADS, smem_stats, st>>>(a);
+  em_merge_kernel<<<(unsigned)((w.nb_max + 3) / 4), 256, 0, st>>>(a);
+  SSP_LAUNCH_CHECK("em_merge_kernel");
+  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats));
+  gmm_em_stats_kernel<<<dim3((unsigned)gx_s, (unsigned)n_pairs), THREADS, smem_stats, st>>>(a);
   SSP_LAUNCH_CHECK("gmm_em_stats_kernel");
   return SSP_OK;
 }
