@@ -244,16 +244,21 @@ int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64
  * enrolment):  N[s,c] = sum_t g_tc, F[s,c,:] = sum_t g_tc x_t, S[s,c,:] = sum_t g_tc x_t^2,
  * loglik[s] = sum_t log p(x_t); g = posterior (sklearn _base.py:552-582; M-step inputs of
  * _gaussian_mixture.py:312-313,250-252).  Outputs are ACCUMULATED into (caller zeroes them).
- * frame_lse      device float[total_frames] scratch (written by this call)
+ * frame_lse      device float[total_frames]: per-frame log-likelihood under the model (written by this call)
+ * workspace      device, ssp_gmm_stats_workspace_bytes() bytes, 1024-byte aligned.  The tensor-core path (tcgen05,
+ *                D <= 39) keeps there (a) the tcgen05 operand images of the frames -- [x, x^2, 1, 1] as BF16 hi + lo
+ *                rows and as TF32 hi + lo with the frame index contiguous, segments padded to 64 frames: 12 * roundup(2D+2,
+ *                16) bytes per frame, 960 at D = 39 -- and (b) per-component-tile log-sum-exp partials.  A NULL or short
+ *                workspace is SSP_EINVAL (the FP32 CUDA-core kernels serve D > 39 only, never as a silent fallback).
+ * reuse_images   nonzero: the workspace still holds the images of THIS feats / seg_offsets from an earlier call (the
+ *                frames of an EM run never change, only the model does): the preparation pass is skipped.
  */
 int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs,
                   int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n,
                   double* out_f, double* out_s, double* out_loglik, void* workspace, int64_t workspace_bytes,
-                  void* stream);
-/* Scratch bytes ssp_gmm_stats needs for these dims (0: none).  The tensor-core path (tcgen05, D <= 39) keeps its
- * operand images and per-component-tile log-sum-exp partials there; a NULL or short workspace is SSP_EINVAL (the FP32
- * CUDA-core kernels serve D > 39 only, never as a silent fallback). */
-int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames);
+                  int32_t reuse_images, void* stream);
+/* Scratch bytes ssp_gmm_stats needs for these dims, frames and segments (0: none). */
+int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames, int64_t n_segs);
 
 /*
  * M-step on device (sklearn _gaussian_mixture.py:312-313,250-252,898): from (all-reduced)

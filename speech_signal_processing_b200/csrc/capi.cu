@@ -134,15 +134,16 @@ static bool stats_want_tc(const ssp::PackLayout& L) {
   return impl == 1 && ssp::stats_tc_supported(L);
 }
 
-extern "C" int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames) {
+extern "C" int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames, int64_t n_segs) {
   ssp::PackLayout L;
-  if (!ssp::make_layout(dims, &L) || total_frames < 0) return 0;
-  return ssp::stats_tc_workspace_bytes(L, total_frames);
+  if (!ssp::make_layout(dims, &L) || total_frames < 0 || n_segs < 0) return 0;
+  return ssp::stats_tc_workspace_bytes(L, total_frames, n_segs);
 }
 
 extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
                              const void* pack, const ssp_gmm_dims* dims, float* frame_lse, double* out_n, double* out_f,
-                             double* out_s, double* out_loglik, void* workspace, int64_t workspace_bytes, void* stream) {
+                             double* out_s, double* out_loglik, void* workspace, int64_t workspace_bytes, int32_t reuse_images,
+                             void* stream) {
   ssp::PackLayout L;
   SSP_REQUIRE(ssp::make_layout(dims, &L), "ssp_gmm_stats: unsupported dims");
   SSP_REQUIRE(dims->n_models == 1, "ssp_gmm_stats: statistics are taken under ONE model (got %d)", dims->n_models);
@@ -152,12 +153,12 @@ extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int
   cudaStream_t st = (cudaStream_t)stream;
   if (stats_want_tc(L)) {
     // no silent 10x slower path: a short workspace is the caller's error
-    const int64_t need = ssp::stats_tc_workspace_bytes(L, total_frames);
+    const int64_t need = ssp::stats_tc_workspace_bytes(L, total_frames, n_segs);
     SSP_REQUIRE(need == 0 || (workspace && workspace_bytes >= need),
                 "ssp_gmm_stats: workspace of %lld bytes, the tensor-core path needs %lld (ssp_gmm_stats_workspace_bytes)",
                 (long long)(workspace ? workspace_bytes : 0), (long long)need);
     return ssp::launch_stats_tc(feats, seg_offsets, n_segs, total_frames, pack, L, frame_lse, out_n, out_f, out_s, out_loglik,
-                                workspace, st);
+                                workspace, reuse_images != 0, st);
   }
   // FP32 CUDA-core path (D > 39).  pass 1: per-frame log-likelihood and the per-segment sum of frame log-likelihoods (the EM
   // lower bound numerator, sklearn _base.py:558); pass 2: posteriors and N/F/S

@@ -53,7 +53,8 @@ struct PackLayout {
   int Kp;  // K rounded up to kTileN (padded components have cst = -1e30, zero rows)
   int DP;  // D padded for the CUDA-core kernels: 16, 32, 40, 64 or 80
   int KD;  // contraction length of the tensor kernel: roundup(2D + 2, 8)
-  size_t off_ab, off_cst, off_tile, off_tile_lo, bytes;
+  size_t off_ab, off_cst, off_tile, off_tile_lo, off_tile_bf, bytes;  // off_tile_bf == 0: no BF16 images (n_models > 1)
+  int KDb() const { return (2 * D + 2 + 15) / 16 * 16; }  // contraction length of the BF16 images (multiple of 16)
   size_t tile_floats() const { return (size_t)kTileN * KD; }
 };
 
@@ -108,6 +109,13 @@ inline bool make_layout(const ssp_gmm_dims* dims, PackLayout* L) {
   // residual ("lo") tiles: B = hi + lo to ~2^-22 -- the 3xTF32 EM kernels and the 2- / 3-pass scoring rungs
   L->off_tile_lo = o;
   o = up(o + (size_t)L->n_models * L->Kp * L->KD * sizeof(float));
+  // BF16 hi + lo images of a single model (the UBM) for the EM / MAP statistics kernels:
+  // [Kp/128 tiles][hi | lo][KDb/8][128][8 bf16]; the constant rides as three BF16 pieces (hi: columns 2D, 2D+1; lo: 2D)
+  L->off_tile_bf = 0;
+  if (L->n_models == 1 && 2 * L->D + 2 <= 80) {
+    L->off_tile_bf = o;
+    o = up(o + (size_t)(L->Kp / kTileN) * 512 * L->KDb());
+  }
   L->bytes = o;
   return true;
 }
@@ -162,14 +170,14 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
                     const PackLayout& L, int parts, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
 int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames, const void* pack,
                     const PackLayout& L, float* frame_lse, double* out_n, double* out_f, double* out_s, double* out_loglik,
-                    void* workspace, cudaStream_t st);
+                    void* workspace, bool reuse_images, cudaStream_t st);
 bool stats_tc_supported(const PackLayout& L);
 int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, void* pack, cudaStream_t st);
 int64_t score_sv_workspace_bytes(const SvLayout& L);
 int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
                     const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* workspace,
                     cudaStream_t st);
-int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames);
+int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames, int64_t n_segs);
 int launch_stats_simt(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
                       const void* pack, const PackLayout& L, const float* frame_lse, double* out_n, double* out_f,
                       double* out_s, cudaStream_t st);

@@ -66,9 +66,10 @@ static Ws ws_layout(const PackLayout& L, int64_t total_frames, int64_t n_segs) {
   w.o_blk_t0 = o;    o = up(o + sizeof(int64_t) * w.nb_max);
   w.o_blk_nt = o;    o = up(o + sizeof(int32_t) * w.nb_max);
   w.o_lse2 = o;      o = up(o + sizeof(float) * w.P);
-  w.o_partial = o;   o = up(o + sizeof(float2) * 2 * (L.Kp / BN) * w.P);
   w.o_fb = o;        o = up(o + w.img_bytes() * (w.nb_max / 2));
   w.o_xt = o;        o = up(o + w.xt_bytes() * w.nb_max);
+  // last: the only section whose size depends on K, so that the images stay valid for a model of another size
+  w.o_partial = o;   o = up(o + sizeof(float2) * 2 * (L.Kp / BN) * w.P);
   w.bytes = o;
   return w;
 }
@@ -211,7 +212,7 @@ __device__ __forceinline__ float feat_col(const float* xr, int j, int D) {
 // one CTA per block: block table entry + the block's half of an Fb image + its Xt image
 __global__ void __launch_bounds__(256) em_prep_kernel(const Args a) {
   __shared__ float sx[BLK * (MAX_KD / 2)];
-  __shared__ int s_seg, s_nt;
+  __shared__ int s_nt;
   __shared__ int64_t s_t0;
   const int64_t b = blockIdx.x;
   const int64_t nb = a.blk_start[a.n_segs];
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256) em_prep_kernel(const Args a) {
       t0 = a.seg[seg] + (b - a.blk_start[seg]) * BLK;
       nt = (int)min((int64_t)BLK, a.seg[seg + 1] - t0);
     }
-    s_seg = seg; s_nt = nt; s_t0 = t0;
+    s_nt = nt; s_t0 = t0;
     a.blk_seg[b] = seg;
     a.blk_t0[b] = t0;
     a.blk_nt[b] = nt;

@@ -1,5 +1,7 @@
 // Model packing, M-step and MAP adaptation: small double-precision kernels that keep the whole
 // EM / enrolment loop resident in HBM (no host round trip of parameters between iterations).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ssp {
@@ -16,7 +18,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __restrict__ mu,
                                 const double* __restrict__ var, int n_models, int K, int Kp, int D, int DP, int KD,
                                 float2* __restrict__ ab, float* __restrict__ cst, float* __restrict__ tiles,
-                                float* __restrict__ tiles_lo) {
+                                float* __restrict__ tiles_lo, __nv_bfloat16* __restrict__ tiles_bf, int KDb) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_models * Kp) return;
   int m = (int)(idx / Kp), c = (int)(idx % Kp);
@@ -28,8 +30,21 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   // residual image (same layout): B = hi + lo to ~2^-22, used by the 3xTF32 EM kernels
   float* tlo = tiles_lo ? tiles_lo + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KD : nullptr;
   auto lo_at = [&](int j) -> float& { return tlo[((j >> 2) * kTileN + n) * 4 + (j & 3)]; };
+  // BF16 image of the tile (EM kernels): [hi | lo][KDb/8][128][8], element (part, j, n) at ((part*KDb/8 + j/8)*128 + n)*8 + j%8
+  __nv_bfloat16* tbf = tiles_bf ? tiles_bf + (int64_t)(c / kTileN) * 2 * kTileN * KDb : nullptr;
+  auto bf_at = [&](int part, int j) -> __nv_bfloat16& {
+    return tbf[(((int64_t)part * (KDb >> 3) + (j >> 3)) * kTileN + n) * 8 + (j & 7)];
+  };
+  auto bf_split = [&](int j, double v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn((float)v);
+    bf_at(0, j) = h;
+    bf_at(1, j) = __float2bfloat16_rn((float)(v - (double)__bfloat162float(h)));
+  };
+  if (tbf)
+    for (int j = 0; j < KDb; ++j) { bf_at(0, j) = __float2bfloat16_rn(0.f); bf_at(1, j) = __float2bfloat16_rn(0.f); }
   const double LOG2E = 1.4426950408889634074;
   if (c >= K) {
+    if (tbf) bf_at(0, 2 * D) = __float2bfloat16_rn(-1e30f);
     for (int d = 0; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
     cst[idx] = -1e30f;
     for (int j = 0; j < KD; ++j) tile_at(j) = 0.f;
@@ -54,6 +69,10 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
       lo_at(d) = to_tf32((float)(a1 * LOG2E - (double)h1));
       lo_at(D + d) = to_tf32((float)(a2 * LOG2E - (double)h2));
     }
+    if (tbf) {
+      bf_split(d, a1 * LOG2E);
+      bf_split(D + d, a2 * LOG2E);
+    }
   }
   for (int d = D; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
   double cc = log(w[(int64_t)m * K + c]) - 0.5 * (D * 1.8378770664093454836 + quad) + 0.5 * logdet;
@@ -70,6 +89,14 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
     lo_at(2 * D) = to_tf32((float)(c2 - (double)hi - (double)lo));  // third piece of the constant
     for (int j = 2 * D + 1; j < KD; ++j) lo_at(j) = 0.f;
   }
+  if (tbf) {  // three BF16 pieces of the constant (24 bits) against the two "one" columns of the frame operand
+    const __nv_bfloat16 p1 = __float2bfloat16_rn((float)c2);
+    const double r1 = c2 - (double)__bfloat162float(p1);
+    const __nv_bfloat16 p2 = __float2bfloat16_rn((float)r1);
+    bf_at(0, 2 * D) = p1;
+    bf_at(0, 2 * D + 1) = p2;
+    bf_at(1, 2 * D) = __float2bfloat16_rn((float)(r1 - (double)__bfloat162float(p2)));
+  }
 }
 
 int launch_pack(const double* w, const double* mu, const double* var, const PackLayout& L, void* pack, cudaStream_t st) {
@@ -80,7 +107,8 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
   gmm_pack_kernel<<<(unsigned)blocks, threads, 0, st>>>(w, mu, var, L.n_models, L.K, L.Kp, L.D, L.DP, L.KD,
                                                        (float2*)(base + L.off_ab), (float*)(base + L.off_cst),
                                                        (float*)(base + L.off_tile),
-                                                       L.off_tile_lo ? (float*)(base + L.off_tile_lo) : nullptr);
+                                                       L.off_tile_lo ? (float*)(base + L.off_tile_lo) : nullptr,
+                                                       L.off_tile_bf ? (__nv_bfloat16*)(base + L.off_tile_bf) : nullptr, L.KDb());
   SSP_LAUNCH_CHECK("gmm_pack_kernel");
   return SSP_OK;
 }

@@ -118,8 +118,12 @@ class ModelSet:
         return scores, lse
 
     @_lib.on_device
-    def stats(self, feats, seg_offsets):
-        """N (S,K), F (S,K,D), S2 (S,K,D), loglik (S,) float64 cuda, under this (single) model."""
+    def stats(self, feats, seg_offsets, workspace=None, reuse_images=False):
+        """N (S,K), F (S,K,D), S2 (S,K,D), loglik (S,) float64 cuda, under this (single) model.
+
+        ``workspace``: a :class:`StatsWorkspace` shared between calls (and model sets) on the SAME ``feats`` /
+        ``seg_offsets``; ``reuse_images=True`` then skips the preparation pass that turns the frames into tensor-core
+        operand images (EM iterations: the frames never change).  Default: a workspace owned by this model set."""
         torch = _lib.require_cuda()
         if self.n_models != 1:
             raise ValueError("statistics are taken under one model (the UBM)")
@@ -132,16 +136,37 @@ class ModelSet:
         ll = torch.zeros(n_segs, dtype=torch.float64, device=self.device)
         lse = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
         d_off = torch.as_tensor(seg_offsets, device=self.device)
-        ws_bytes = int(self.lib.ssp_gmm_stats_workspace_bytes(C.byref(self.dims), total))
-        ws = getattr(self, "_ws", None)
-        if ws_bytes and (ws is None or ws.numel() < ws_bytes):
-            ws = self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        ws_bytes = int(self.lib.ssp_gmm_stats_workspace_bytes(C.byref(self.dims), total, n_segs))
+        if workspace is None:
+            workspace = getattr(self, "_ws", None)
+            if workspace is None:
+                workspace = self._ws = StatsWorkspace(self.device)
+            reuse_images = False
+        buf = workspace.reserve(ws_bytes)
         rc = self.lib.ssp_gmm_stats(_lib.ptr(feats), _lib.ptr(d_off), n_segs, total, _lib.ptr(self.pack),
                                     C.byref(self.dims), _lib.ptr(lse), _lib.ptr(n), _lib.ptr(f), _lib.ptr(s), _lib.ptr(ll),
-                                    _lib.ptr(ws) if ws_bytes else None, ws_bytes, _lib.stream_ptr())
+                                    _lib.ptr(buf) if ws_bytes else None, ws_bytes, int(bool(reuse_images) and workspace.valid),
+                                    _lib.stream_ptr())
         _lib.check(rc, "ssp_gmm_stats")
+        workspace.valid = True
         self._keep = (d_off, lse)
         return n, f, s, ll
+
+
+class StatsWorkspace:
+    """Scratch of ``ssp_gmm_stats`` (operand images of the frames + log-sum-exp partials).  ``valid`` says that it holds
+    the images of the frames it was last used with; growing it invalidates them."""
+
+    def __init__(self, device):
+        self.device, self.buf, self.valid = device, None, False
+
+    def reserve(self, nbytes: int):
+        torch = _lib.require_cuda()
+        if nbytes and (self.buf is None or self.buf.numel() < nbytes):
+            self.buf = None  # release before growing: the images of a large run are tens of GB
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.valid = False
+        return self.buf
 
 
 class SharedModelSet:
@@ -300,11 +325,11 @@ class GaussianMixture:
         self.precisions_ = self.precisions_cholesky_ ** 2
 
     # ------------------------------------------------------------------ EM
-    def _em_iteration(self, ms, feats, seg, n_total, nk_eps, w, mu, var):
+    def _em_iteration(self, ms, feats, seg, n_total, nk_eps, w, mu, var, workspace=None):
         """One E+M step on device.  Returns the lower bound (mean frame log-likelihood under the
         parameters the E-step used)."""
         torch = _lib.require_cuda()
-        n, f, s, ll = ms.stats(feats, seg)
+        n, f, s, ll = ms.stats(feats, seg, workspace=workspace, reuse_images=True)
         if self.comm is not None and self.comm.world_size > 1:
             k, d = ms.n_comp, ms.n_feat
             cnt = torch.tensor([float(feats.shape[0])], dtype=torch.float64, device=feats.device)
@@ -323,7 +348,7 @@ class GaussianMixture:
         _lib.check(rc, "ssp_gmm_mstep")
         return float(ll.item()) / n_total, n
 
-    def _kmeans_init(self, feats, seg, rs, w, mu, var, nk_eps, iters=10):
+    def _kmeans_init(self, feats, seg, rs, w, mu, var, nk_eps, iters=10, workspace=None):
         """Lloyd iterations as hard EM: equal weights, one small shared variance, so posteriors are
         (numerically) one-hot; empty clusters are re-seeded from random frames.  Ends with sklearn's
         ``_initialize(X, resp)`` M-step from those assignments."""
@@ -371,7 +396,7 @@ class GaussianMixture:
         ms = ModelSet(w, mu, sharp, device=feats.device)
         for it in range(iters + 1):
             ms.repack(w, mu, sharp)
-            n, f, s, _ = ms.stats(feats, seg)
+            n, f, s, _ = ms.stats(feats, seg, workspace=workspace, reuse_images=True)
             if comm is not None:
                 flat = reduced(torch.cat([n.reshape(-1), f.reshape(-1), s.reshape(-1)]))
                 n, f, s = flat[:k].reshape(1, k), flat[k : k + k * d].reshape(1, k, d), flat[k + k * d :].reshape(1, k, d)
@@ -414,6 +439,7 @@ class GaussianMixture:
 
         do_init = not (self.warm_start and hasattr(self, "converged_"))
         best = None
+        workspace = StatsWorkspace(dev)  # the frames' operand images are built by the first statistics call and reused
         for _init in range(self.n_init if do_init else 1):
             w = torch.empty((1, k), dtype=torch.float64, device=dev)
             mu = torch.empty((1, k, d), dtype=torch.float64, device=dev)
@@ -427,7 +453,7 @@ class GaussianMixture:
                     if self.init_params not in ("kmeans", "k-means++", "random_from_data", "random"):
                         raise ValueError(f"Invalid value for 'init_params': {self.init_params}")
                     self._kmeans_init(feats, seg, rs, w, mu, var, nk_eps,
-                                      iters=10 if self.init_params in ("kmeans", "k-means++") else 0)
+                                      iters=10 if self.init_params in ("kmeans", "k-means++") else 0, workspace=workspace)
                 if self.weights_init is not None:
                     w.copy_(torch.as_tensor(np.asarray(self.weights_init, dtype=np.float64))[None])
                 if self.means_init is not None:
@@ -439,7 +465,7 @@ class GaussianMixture:
             for n_iter in range(1, self.max_iter + 1):
                 prev = lower
                 ms.repack(w, mu, var)
-                lower, _ = self._em_iteration(ms, feats, seg, float(n_frames), nk_eps, w, mu, var)
+                lower, _ = self._em_iteration(ms, feats, seg, float(n_frames), nk_eps, w, mu, var, workspace)
                 bounds.append(lower)
                 if abs(lower - prev) < self.tol:
                     converged = True

@@ -21,7 +21,7 @@ REL = {"fp32": 2e-6, "tf32": 5e-4, "tf32x2": 5e-4, "tf32x3": 2e-6}
 # LLR within 1e-3 absolute, per-utterance score within 1e-4 relative
 LLR_ATOL, SCORE_RTOL = 1e-3, 1e-4
 # the kernels that must serve ssp_gmm_stats for D <= 39 (tcgen05), and the FP32 CUDA-core pair for wider features
-EM_TENSOR_KERNELS = {"gmm_em_lse_kernel", "gmm_em_stats_kernel"}
+EM_TENSOR_KERNELS = {"em_plan_kernel", "em_prep_kernel", "gmm_em_lse_kernel", "em_merge_kernel", "gmm_em_stats_kernel"}
 EM_SIMT_KERNELS = {"gmm_score_simt_kernel", "gmm_stats_simt_kernel"}
 
 
