@@ -44,7 +44,6 @@ constexpr int EPI = 512;       // 16 epilogue warps
 constexpr int THREADS = 64 + EPI;
 constexpr int MAX_KD = 80;
 constexpr int NS_L = 3;        // Fb stages of the LSE pass
-constexpr int NS_S = 2;        // (Fb half, Xt, lse) stages of the STATS pass
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct Ws {
@@ -435,9 +434,13 @@ __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
 }
 
 // ================================================================================================ pass STATS
-// grid = (block chunks, tile pairs).  Shared memory: the pair's model tiles + NS_S stages of (Fb half image, Xt image,
-// 64 lse values); tensor memory: logits / gamma [tile][buffer] 64 columns each, statistics [tile] KDb columns.
+// grid = (block chunks, tile pairs).  Shared memory: the pair's model tiles, a ring of NF (Fb half image + 64 lse values)
+// stages for the logit GEMM and a ring of NX Xt images for the statistics GEMM; tensor memory: logits / gamma
+// [tile][buffer] 64 columns each, statistics [tile] KDb columns.  Tensor-pipe order per step k: GEMM1(k) (logits),
+// GEMM2(k - 1) (statistics); both rings are released by the completion of GEMM2(k), so the loads of step k + 1 are
+// issued two GEMMs before they are needed.
 namespace p3 {
+constexpr int NF = 3, NX = 2;
 constexpr uint32_t COL_LOGIT = 0;    // + 64 * (2 * tile + buffer)
 constexpr uint32_t COL_STAT = 256;   // + KDb * tile
 }
@@ -448,14 +451,17 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
   const int KDb = a.KDb, D = a.D;
   const uint32_t TB = 512u * (uint32_t)KDb;     // model tile image; also one Xt image
   const uint32_t FB = TB >> 1;                  // the 64-row half of an Fb image (hi + lo)
-  const uint32_t STAGE = FB + TB + 256u;        // + 64 lse values
+  const uint32_t FST = FB + 256u;               // F stage: + 64 lse values
   unsigned char* sB = smem;                     // [2][TB]
-  unsigned char* sS = smem + 2 * (size_t)TB;    // [NS_S][STAGE]: F half | Xt | lse
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)NS_S * STAGE);
+  unsigned char* sF = smem + 2 * (size_t)TB;    // [NF][FST]
+  unsigned char* sX = sF + (size_t)NF * FST;    // [NX][TB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)NX * TB);
   uint64_t* b_full = bars;           // model tiles landed
-  uint64_t* s_full = bars + 1;       // [NS_S]
-  uint64_t* s_empty = s_full + NS_S; // [NS_S] statistics GEMMs of the step are complete
-  uint64_t* l_full = s_empty + NS_S; // [4] logits of (tile, buffer) are in TMEM
+  uint64_t* f_full = bars + 1;       // [NF]
+  uint64_t* f_empty = f_full + NF;   // [NF] the statistics GEMMs of the step are complete (its lse values are dead too)
+  uint64_t* x_full = f_empty + NF;   // [NX]
+  uint64_t* x_empty = x_full + NX;   // [NX]
+  uint64_t* l_full = x_empty + NX;   // [4] logits of (tile, buffer) are in TMEM
   uint64_t* g_full = l_full + 4;     // [4] gamma of (tile, buffer) is in TMEM
   uint64_t* st_done = g_full + 4;    // [2] per tile: every statistics GEMM issued so far is complete
   uint64_t* drained = st_done + 2;   // [2] per tile: the accumulator has been read out after a segment end
@@ -466,7 +472,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
   const int ntl = min(2, a.n_tiles - tile0);
   if (tid == 0) {
     mbar_init(b_full, 1);
-    for (int i = 0; i < NS_S; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 1); }
+    for (int i = 0; i < NF; ++i) { mbar_init(f_full + i, 1); mbar_init(f_empty + i, 1); }
+    for (int i = 0; i < NX; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(l_full + i, 1); mbar_init(g_full + i, EPI / 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(st_done + i, 1); mbar_init(drained + i, EPI / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -494,16 +501,19 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
       const int n_pieces = 2 * (KDb >> 3);  // (hi | lo) x chunk: 1 KB each, 64 rows x 16 B out of a 128-row chunk
       uint32_t k = 0;
       for (int64_t b = b0; b < b1; ++b, ++k) {
-        const uint32_t st = k % NS_S, ph = (k / NS_S) & 1u;
-        mbar_wait(s_empty + st, ph ^ 1u);
-        unsigned char* dst = sS + (size_t)st * STAGE;
-        if (lane == 0) mbar_arrive_expect_tx(s_full + st, STAGE);
+        const uint32_t fs = k % NF, xs = k % NX;
+        mbar_wait(f_empty + fs, ((k / NF) & 1u) ^ 1u);
+        unsigned char* dst = sF + (size_t)fs * FST;
+        if (lane == 0) mbar_arrive_expect_tx(f_full + fs, FST);
         __syncwarp();
         const unsigned char* img = a.fb + (size_t)(b >> 1) * TB + (size_t)(b & 1) * (BLK * 16);
-        for (int pc = lane; pc < n_pieces; pc += 32) bulk_g2s(dst + (size_t)pc * 1024, img + (size_t)pc * 2048, 1024u, s_full + st);
-        if (lane == 31) {
-          bulk_g2s(dst + FB, a.xt + (size_t)b * TB, TB, s_full + st);
-          bulk_g2s(dst + FB + TB, a.lse2 + b * BLK, 256u, s_full + st);
+        for (int pc = lane; pc < n_pieces; pc += 32) bulk_g2s(dst + (size_t)pc * 1024, img + (size_t)pc * 2048, 1024u, f_full + fs);
+        if (lane == 31) bulk_g2s(dst + FB, a.lse2 + b * BLK, 256u, f_full + fs);
+        __syncwarp();
+        mbar_wait(x_empty + xs, ((k / NX) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(x_full + xs, TB);
+          bulk_g2s(sX + (size_t)xs * TB, a.xt + (size_t)b * TB, TB, x_full + xs);
         }
         __syncwarp();
       }
@@ -518,14 +528,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
       const uint32_t idesc1 = make_idesc_bf16(BN, BLK);
       const uint32_t idesc2 = make_idesc_tf32(BN, KDb, 0, 0);
       const int ksteps = KDb >> 4;
-      const uint32_t sB_u = smem_u32(sB), sS_u = smem_u32(sS);
+      const uint32_t sB_u = smem_u32(sB), sF_u = smem_u32(sF), sX_u = smem_u32(sX);
       mbar_wait(b_full, 0);
       bool pending_drain[2] = {false, false};
       uint32_t n_drains[2] = {0u, 0u};
-      // statistics GEMM of step p: stats[tile] += gamma (TMEM, in the logit columns of (tile, p & 1)) . Xt (stage p % NS_S)
+      // statistics GEMM of step p: stats[tile] += gamma (TMEM, in the logit columns of (tile, p & 1)) . Xt (stage p % NX)
       auto gemm2 = [&](uint32_t p, bool first, bool flush) {
-        const uint32_t st = p % NS_S;
-        const uint32_t xb = sS_u + st * STAGE + FB;
+        const uint32_t xs = p % NX;
+        mbar_wait(x_full + xs, (p / NX) & 1u);
+        const uint32_t xb = sX_u + xs * TB;
         const uint64_t xhi = make_desc(xb, lbo_x, sbo), xlo = make_desc(xb + (TB >> 1), lbo_x, sbo);
         for (int t = 0; t < ntl; ++t) {
           const uint32_t lb = 2u * (uint32_t)t + (p & 1u);
@@ -541,7 +552,10 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
             for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
             for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
             if (flush) tc_commit(st_done + t);
-            if (t == ntl - 1) tc_commit(s_empty + st);
+            if (t == ntl - 1) {
+              tc_commit(f_empty + p % NF);
+              tc_commit(x_empty + xs);
+            }
           }
           __syncwarp();
           if (flush) pending_drain[t] = true;
@@ -552,10 +566,11 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
       int seg_cur = a.blk_seg[b0];
       bool first_in_seg = true;
       for (int64_t b = b0; b < b1; ++b, ++k) {
-        const uint32_t st = k % NS_S;
-        mbar_wait(s_full + st, (k / NS_S) & 1u);
+        const int seg_next = (b + 1 < b1) ? __ldg(a.blk_seg + b + 1) : -2;  // issued early, used at the bottom
+        const uint32_t fs = k % NF;
+        mbar_wait(f_full + fs, (k / NF) & 1u);
         tc_fence_after();
-        const uint32_t fb_u = sS_u + st * STAGE;
+        const uint32_t fb_u = sF_u + fs * FST;
         const uint64_t fh = make_desc(fb_u, lbo_f, sbo), fl = make_desc(fb_u + (FB >> 1), lbo_f, sbo);
         for (int t = 0; t < ntl; ++t) {
           // the logit buffer (t, k & 1) was last read by the statistics GEMM of step k - 2, issued before this one
@@ -571,7 +586,6 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
           __syncwarp();
         }
         if (k > 0) gemm2(k - 1, prev_first, prev_flush);
-        const int seg_next = (b + 1 < b1) ? a.blk_seg[b + 1] : -2;
         prev_first = first_in_seg;
         prev_flush = seg_next != seg_cur;
         first_in_seg = prev_flush;
@@ -590,9 +604,13 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
       uint32_t k = 0, n_flush = 0;
       int seg_cur = a.blk_seg[b0];
       for (int64_t b = b0; b < b1; ++b, ++k) {
-        const uint32_t st = k % NS_S, lb = 2u * (uint32_t)t + (k & 1u);
-        mbar_wait(s_full + st, (k / NS_S) & 1u);   // the stage's lse values (written by the bulk copy) are visible
-        const float* lse = reinterpret_cast<const float*>(sS + (size_t)st * STAGE + FB + TB) + 32 * cq;
+        const int seg_next = (b + 1 < b1) ? __ldg(a.blk_seg + b + 1) : -2;  // issued early, used at the bottom
+        const uint32_t fs = k % NF, lb = 2u * (uint32_t)t + (k & 1u);
+        mbar_wait(f_full + fs, (k / NF) & 1u);   // the stage's lse values (written by the bulk copy) are visible
+        const float* lse = reinterpret_cast<const float*>(sF + (size_t)fs * FST + FB) + 32 * cq;
+        float4 ls[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ls[q] = *reinterpret_cast<const float4*>(lse + 4 * q);
         mbar_wait(l_full + lb, (k >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_log = tmem_base + lane_addr + COL_LOGIT + 64u * lb + 32u * (uint32_t)cq;
@@ -602,17 +620,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         float gam[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 ls = *reinterpret_cast<const float4*>(lse + 4 * q);
-          gam[4 * q + 0] = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls.x));
-          gam[4 * q + 1] = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls.y));
-          gam[4 * q + 2] = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls.z));
-          gam[4 * q + 3] = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls.w));
+          gam[4 * q + 0] = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls[q].x));
+          gam[4 * q + 1] = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls[q].y));
+          gam[4 * q + 2] = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls[q].z));
+          gam[4 * q + 3] = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls[q].w));
         }
         tc_st32(t_log, gam);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(g_full + lb);
-        const int seg_next = (b + 1 < b1) ? a.blk_seg[b + 1] : -2;
         if (seg_next != seg_cur) {
           // last step of a segment inside this chunk: wait for its statistics GEMMs, add the accumulator to the outputs
           mbar_wait(st_done + t, n_flush & 1u);
@@ -708,7 +724,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   const int64_t gx_l = min(gx, (nb_lo + 1) / 2), gx_s = min(gx, nb_lo);
   const size_t TB = w.img_bytes();
   const size_t smem_lse = (2 + NS_L) * TB + 16 * sizeof(uint64_t) + 64;
-  const size_t smem_stats = 2 * TB + NS_S * (TB / 2 + TB + 256) + 24 * sizeof(uint64_t) + 64;
+  const size_t smem_stats = 2 * TB + p3::NF * (TB / 2 + 256) + p3::NX * TB + 24 * sizeof(uint64_t) + 64;
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SSP_EM_POLY_PAIRS");  // share of the LSE pass's exponentials on the FMA pipe (pairs of 16)
