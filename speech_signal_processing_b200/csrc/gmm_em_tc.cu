@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
       uint32_t k = 0;
       for (int64_t i = i0; i < i1; ++i, ++k) {
         const uint32_t st = k % NS_L, ph = (k / NS_L) & 1u;
-        mbar_wait(f_empty + st, ph ^ 1u);
+        mbar_wait_relaxed(f_empty + st, ph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(f_full + st, TB);
           bulk_g2s(sF + (size_t)st * TB, a.fb + (size_t)i * TB, TB, f_full + st);
@@ -345,16 +345,16 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
       const int ksteps = KDb >> 4;
       const uint32_t half_units = (TB >> 1) >> 4;      // hi -> lo inside an image, in descriptor units
       const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo, sbo), f_desc0 = make_desc(smem_u32(sF), lbo, sbo);
-      mbar_wait(b_full, 0);
+      mbar_wait_relaxed(b_full, 0);
       uint32_t k = 0;
       for (int64_t i = i0; i < i1; ++i, ++k) {
         const uint32_t st = k % NS_L, ph = (k / NS_L) & 1u;
-        mbar_wait(f_full + st, ph);
+        mbar_wait_relaxed(f_full + st, ph);
         tc_fence_after();
         const uint64_t fh = f_desc0 + (uint64_t)(st * (TB >> 4)), fl = fh + half_units;
         for (int t = 0; t < ntl; ++t) {
           const uint32_t slot = 2u * (k & 1u) + (uint32_t)t;
-          mbar_wait(t_empty + slot, ((k >> 1) & 1u) ^ 1u);
+          mbar_wait_relaxed(t_empty + slot, ((k >> 1) & 1u) ^ 1u);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d = tmem_base + slot * BN;
@@ -406,7 +406,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-// partials -> lse2 per padded frame, frame_lse per frame, log-likelihood per segment.  4 blocks per CTA.
+// partials -> lse2 per padded frame, frame_lse per frame, log-likelihood per segment.  4 blocks per CTA; the partials of
+// a frame are loaded in one batch (independent loads in flight) and merged from registers.
 __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
   const int64_t nb = a.blk_start[a.n_segs];
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
@@ -417,12 +418,18 @@ __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
   float lse2 = 3.0e38f, ll = 0.f;  // dead rows: gamma = 2^(x - huge) = 0
   if (r < nt) {
     const int n_part = 2 * a.n_tiles;
-    float m = -3.0e38f;
-    for (int y = 0; y < n_part; ++y) m = fmaxf(m, a.partial[(size_t)y * a.P + p].x);
-    float s = 0.f;
-    for (int y = 0; y < n_part; ++y) {
-      const float2 q = a.partial[(size_t)y * a.P + p];
-      s += q.y * ex2(q.x - m);
+    float m = -3.0e38f, s = 0.f;
+    for (int y0 = 0; y0 < n_part; y0 += 8) {
+      float2 q[8];
+#pragma unroll
+      for (int y = 0; y < 8; ++y) q[y] = y0 + y < n_part ? __ldg(a.partial + (size_t)(y0 + y) * a.P + p) : make_float2(-3.0e38f, 0.f);
+      float mg = m;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) mg = fmaxf(mg, q[y].x);
+      s *= ex2(m - mg);
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += q[y].y * ex2(q[y].x - mg);
+      m = mg;
     }
     lse2 = m + lg2(s);
     ll = lse2 * 0.69314718055994530942f;
@@ -443,18 +450,23 @@ namespace p3 {
 constexpr int NF = 3, NX = 2;
 constexpr uint32_t COL_LOGIT = 0;    // + 64 * (2 * tile + buffer)
 constexpr uint32_t COL_STAT = 256;   // + KDb * tile
+constexpr int CTRL = 96;             // warp 0: producer; warps 1, 2: MMA issuers of tile 0 / tile 1 (a step's MMAs are 32-40
+                                     // tensor cycles each: one issuing lane cannot keep up with two tiles)
+constexpr int THREADS_S = CTRL + EPI;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) {
+template <int KSTEPS>
+__global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Args a) {
   using namespace p3;
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int KDb = a.KDb, D = a.D;
-  const uint32_t TB = 512u * (uint32_t)KDb;     // model tile image; also one Xt image
-  const uint32_t FB = TB >> 1;                  // the 64-row half of an Fb image (hi + lo)
-  const uint32_t FST = FB + 256u;               // F stage: + 64 lse values
-  unsigned char* sB = smem;                     // [2][TB]
-  unsigned char* sF = smem + 2 * (size_t)TB;    // [NF][FST]
-  unsigned char* sX = sF + (size_t)NF * FST;    // [NX][TB]
+  constexpr int KDb = KSTEPS * 16;
+  const int D = a.D;
+  constexpr uint32_t TB = 512u * (uint32_t)KDb;  // model tile image; also one Xt image
+  constexpr uint32_t FB = TB >> 1;               // the 64-row half of an Fb image (hi + lo)
+  constexpr uint32_t FST = FB + 256u;            // F stage: + 64 lse values
+  unsigned char* sB = smem;                      // [2][TB]
+  unsigned char* sF = smem + 2 * (size_t)TB;     // [NF][FST]
+  unsigned char* sX = sF + (size_t)NF * FST;     // [NX][TB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)NX * TB);
   uint64_t* b_full = bars;           // model tiles landed
   uint64_t* f_full = bars + 1;       // [NF]
@@ -472,8 +484,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
   const int ntl = min(2, a.n_tiles - tile0);
   if (tid == 0) {
     mbar_init(b_full, 1);
-    for (int i = 0; i < NF; ++i) { mbar_init(f_full + i, 1); mbar_init(f_empty + i, 1); }
-    for (int i = 0; i < NX; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+    for (int i = 0; i < NF; ++i) { mbar_init(f_full + i, 1); mbar_init(f_empty + i, (uint32_t)ntl); }
+    for (int i = 0; i < NX; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, (uint32_t)ntl); }
     for (int i = 0; i < 4; ++i) { mbar_init(l_full + i, 1); mbar_init(g_full + i, EPI / 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(st_done + i, 1); mbar_init(drained + i, EPI / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -498,11 +510,11 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, a.tiles + (size_t)(tile0 + t) * TB, TB, b_full);
       }
       __syncwarp();
-      const int n_pieces = 2 * (KDb >> 3);  // (hi | lo) x chunk: 1 KB each, 64 rows x 16 B out of a 128-row chunk
+      constexpr int n_pieces = 2 * (KDb >> 3);  // (hi | lo) x chunk: 1 KB each, 64 rows x 16 B out of a 128-row chunk
       uint32_t k = 0;
       for (int64_t b = b0; b < b1; ++b, ++k) {
         const uint32_t fs = k % NF, xs = k % NX;
-        mbar_wait(f_empty + fs, ((k / NF) & 1u) ^ 1u);
+        mbar_wait_relaxed(f_empty + fs, ((k / NF) & 1u) ^ 1u);
         unsigned char* dst = sF + (size_t)fs * FST;
         if (lane == 0) mbar_arrive_expect_tx(f_full + fs, FST);
         __syncwarp();
@@ -510,7 +522,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         for (int pc = lane; pc < n_pieces; pc += 32) bulk_g2s(dst + (size_t)pc * 1024, img + (size_t)pc * 2048, 1024u, f_full + fs);
         if (lane == 31) bulk_g2s(dst + FB, a.lse2 + b * BLK, 256u, f_full + fs);
         __syncwarp();
-        mbar_wait(x_empty + xs, ((k / NX) & 1u) ^ 1u);
+        mbar_wait_relaxed(x_empty + xs, ((k / NX) & 1u) ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(x_full + xs, TB);
           bulk_g2s(sX + (size_t)xs * TB, a.xt + (size_t)b * TB, TB, x_full + xs);
@@ -518,48 +530,45 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (b0 < b1) {
+  } else if (warp < CTRL / 32) {
+    // ===================== MMA issuer of tile t =====================
+    const int t = warp - 1;
+    if (t < ntl && b0 < b1) {
       constexpr uint32_t sbo = 128u;
-      constexpr uint32_t lbo_b = BN * 16u, lbo_f = BLK * 16u;
-      constexpr uint32_t ks_b = (2u * lbo_b) >> 4, ks_f = (2u * lbo_f) >> 4;
-      const uint32_t lbo_x = (uint32_t)KDb * 16u, ks_x = (2u * lbo_x) >> 4;
-      const uint32_t idesc1 = make_idesc_bf16(BN, BLK);
-      const uint32_t idesc2 = make_idesc_tf32(BN, KDb, 0, 0);
-      const int ksteps = KDb >> 4;
-      const uint32_t sB_u = smem_u32(sB), sF_u = smem_u32(sF), sX_u = smem_u32(sX);
-      mbar_wait(b_full, 0);
-      bool pending_drain[2] = {false, false};
-      uint32_t n_drains[2] = {0u, 0u};
-      // statistics GEMM of step p: stats[tile] += gamma (TMEM, in the logit columns of (tile, p & 1)) . Xt (stage p % NX)
+      constexpr uint32_t lbo_b = BN * 16u, lbo_f = BLK * 16u, lbo_x = (uint32_t)KDb * 16u;
+      constexpr uint32_t ks_b = (2u * lbo_b) >> 4, ks_f = (2u * lbo_f) >> 4, ks_x = (2u * lbo_x) >> 4;
+      constexpr uint32_t idesc1 = make_idesc_bf16(BN, BLK);
+      constexpr uint32_t idesc2 = make_idesc_tf32(BN, KDb, 0, 0);
+      const uint32_t sF_u = smem_u32(sF), sX_u = smem_u32(sX);
+      const uint64_t bh = make_desc(smem_u32(sB) + (uint32_t)t * TB, lbo_b, sbo), bl = bh + (uint64_t)((TB >> 1) >> 4);
+      const uint32_t t_stat = tmem_base + COL_STAT + (uint32_t)(t * KDb);
+      mbar_wait_relaxed(b_full, 0);
+      bool pending_drain = false;
+      uint32_t n_drains = 0;
+      // statistics GEMM of step p: stats += gamma (TMEM, in the logit columns of buffer p & 1) . Xt (stage p % NX)
       auto gemm2 = [&](uint32_t p, bool first, bool flush) {
-        const uint32_t xs = p % NX;
-        mbar_wait(x_full + xs, (p / NX) & 1u);
-        const uint32_t xb = sX_u + xs * TB;
-        const uint64_t xhi = make_desc(xb, lbo_x, sbo), xlo = make_desc(xb + (TB >> 1), lbo_x, sbo);
-        for (int t = 0; t < ntl; ++t) {
-          const uint32_t lb = 2u * (uint32_t)t + (p & 1u);
-          mbar_wait(g_full + lb, (p >> 1) & 1u);
-          if (pending_drain[t]) {
-            mbar_wait(drained + t, n_drains[t] & 1u);
-            ++n_drains[t];
-            pending_drain[t] = false;
-          }
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t t_gam = tmem_base + COL_LOGIT + 64u * lb, t_stat = tmem_base + COL_STAT + (uint32_t)(t * KDb);
-            for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
-            for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
-            if (flush) tc_commit(st_done + t);
-            if (t == ntl - 1) {
-              tc_commit(f_empty + p % NF);
-              tc_commit(x_empty + xs);
-            }
-          }
-          __syncwarp();
-          if (flush) pending_drain[t] = true;
+        const uint32_t xs = p % NX, lb = 2u * (uint32_t)t + (p & 1u);
+        mbar_wait_relaxed(x_full + xs, (p / NX) & 1u);
+        mbar_wait_relaxed(g_full + lb, (p >> 1) & 1u);
+        if (pending_drain) {
+          mbar_wait_relaxed(drained + t, n_drains & 1u);
+          ++n_drains;
+          pending_drain = false;
         }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t xhi = make_desc(sX_u + xs * TB, lbo_x, sbo), xlo = xhi + (uint64_t)((TB >> 1) >> 4);
+          const uint32_t t_gam = tmem_base + COL_LOGIT + 64u * lb;
+#pragma unroll
+          for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
+#pragma unroll
+          for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
+          if (flush) tc_commit(st_done + t);
+          tc_commit(f_empty + p % NF);
+          tc_commit(x_empty + xs);
+        }
+        __syncwarp();
+        pending_drain = flush;
       };
       uint32_t k = 0;
       bool prev_first = true, prev_flush = false;
@@ -567,24 +576,22 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
       bool first_in_seg = true;
       for (int64_t b = b0; b < b1; ++b, ++k) {
         const int seg_next = (b + 1 < b1) ? __ldg(a.blk_seg + b + 1) : -2;  // issued early, used at the bottom
-        const uint32_t fs = k % NF;
-        mbar_wait(f_full + fs, (k / NF) & 1u);
+        const uint32_t fs = k % NF, lb = 2u * (uint32_t)t + (k & 1u);
+        mbar_wait_relaxed(f_full + fs, (k / NF) & 1u);
         tc_fence_after();
-        const uint32_t fb_u = sF_u + fs * FST;
-        const uint64_t fh = make_desc(fb_u, lbo_f, sbo), fl = make_desc(fb_u + (FB >> 1), lbo_f, sbo);
-        for (int t = 0; t < ntl; ++t) {
-          // the logit buffer (t, k & 1) was last read by the statistics GEMM of step k - 2, issued before this one
-          if (elect_one()) {
-            const uint32_t lb = 2u * (uint32_t)t + (k & 1u);
-            const uint32_t d = tmem_base + COL_LOGIT + 64u * lb;
-            const uint64_t bh = make_desc(sB_u + (uint32_t)t * TB, lbo_b, sbo), bl = make_desc(sB_u + (uint32_t)t * TB + (TB >> 1), lbo_b, sbo);
-            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, bh + (uint64_t)(q * ks_b), fh + (uint64_t)(q * ks_f), idesc1, q > 0 ? 1u : 0u);
-            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, bh + (uint64_t)(q * ks_b), fl + (uint64_t)(q * ks_f), idesc1, 1u);
-            for (int q = 0; q < ksteps; ++q) mma_bf16_ss(d, bl + (uint64_t)(q * ks_b), fh + (uint64_t)(q * ks_f), idesc1, 1u);
-            tc_commit(l_full + lb);
-          }
-          __syncwarp();
+        // the logit buffer (t, k & 1) was last read by the statistics GEMM of step k - 2, issued before this one
+        if (elect_one()) {
+          const uint64_t fh = make_desc(sF_u + fs * FST, lbo_f, sbo), fl = fh + (uint64_t)((FB >> 1) >> 4);
+          const uint32_t d = tmem_base + COL_LOGIT + 64u * lb;
+#pragma unroll
+          for (int q = 0; q < KSTEPS; ++q) mma_bf16_ss(d, bh + (uint64_t)(q * ks_b), fh + (uint64_t)(q * ks_f), idesc1, q > 0 ? 1u : 0u);
+#pragma unroll
+          for (int q = 0; q < KSTEPS; ++q) mma_bf16_ss(d, bh + (uint64_t)(q * ks_b), fl + (uint64_t)(q * ks_f), idesc1, 1u);
+#pragma unroll
+          for (int q = 0; q < KSTEPS; ++q) mma_bf16_ss(d, bl + (uint64_t)(q * ks_b), fh + (uint64_t)(q * ks_f), idesc1, 1u);
+          tc_commit(l_full + lb);
         }
+        __syncwarp();
         if (k > 0) gemm2(k - 1, prev_first, prev_flush);
         prev_first = first_in_seg;
         prev_flush = seg_next != seg_cur;
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
     }
   } else {
     // ===================== epilogue: thread == (component row, 32 of a step's 64 frames) =====================
-    const int ew = warp - 2;
+    const int ew = warp - CTRL / 32;
     const int t = ew >> 3, cq = (ew >> 2) & 1, quad = warp & 3;
     const int row = quad * 32 + lane;  // TMEM lane == component row within the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_stats_kernel(const Args a) 
           ++n_flush;
           tc_fence_after();
           const uint32_t saddr = tmem_base + lane_addr + COL_STAT + (uint32_t)(t * KDb);
-          const int half_cols = KDb >> 1;  // a multiple of 8
+          constexpr int half_cols = KDb >> 1;  // a multiple of 8
 #pragma unroll 1
           for (int c0 = cq * half_cols; c0 < (cq + 1) * half_cols; c0 += 8) {
             uint32_t s8[8];
@@ -728,7 +735,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SSP_EM_POLY_PAIRS");  // share of the LSE pass's exponentials on the FMA pipe (pairs of 16)
-    poly = e ? atoi(e) : 4;
+    poly = e ? atoi(e) : 6;  // measured at config 3 (36 M frames, K = 512): 2 / 4 / 6 / 8 pairs -> 30.0 / 27.8 / 26.3 / 27.3 ms per call
   }
 #define SSP_EM_LSE(pp)                                                                                               \
   case pp:                                                                                                           \
@@ -743,8 +750,16 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
   em_merge_kernel<<<(unsigned)((w.nb_max + 3) / 4), 256, 0, st>>>(a);
   SSP_LAUNCH_CHECK("em_merge_kernel");
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats));
-  gmm_em_stats_kernel<<<dim3((unsigned)gx_s, (unsigned)n_pairs), THREADS, smem_stats, st>>>(a);
+#define SSP_EM_STATS(ks)                                                                                                  \
+  case ks:                                                                                                                \
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel<ks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats)); \
+    gmm_em_stats_kernel<ks><<<dim3((unsigned)gx_s, (unsigned)n_pairs), p3::THREADS_S, smem_stats, st>>>(a);             \
+    break;
+  switch (w.KDb >> 4) {
+    SSP_EM_STATS(1) SSP_EM_STATS(2) SSP_EM_STATS(3) SSP_EM_STATS(4) SSP_EM_STATS(5)
+    default: SSP_REQUIRE(false, "ssp_gmm_stats: contraction length %d", w.KDb);
+  }
+#undef SSP_EM_STATS
   SSP_LAUNCH_CHECK("gmm_em_stats_kernel");
   return SSP_OK;
 }

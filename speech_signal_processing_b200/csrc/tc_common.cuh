@@ -29,14 +29,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap, not hang the GPU (2^32 SM cycles ~ 2-3 s).
+// Bounded waits: a protocol bug must trap, not hang the GPU.  The bound is a poll COUNTER (one integer add per failed
+// poll; round 1 read clock64() in every iteration of every spin loop, 5 % of all executed instructions of the scoring
+// kernel and half of those of the EM kernels).  mbarrier.try_wait itself blocks for a hardware-defined time slice,
+// so 2^26 failed polls are seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 32)) {
-      printf("ssp gmm_score_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+    if (++polls > (1u << 26)) {
+      printf("ssp: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x,
              smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+// The control warps' version: a failed poll parks the warp in hardware for up to ~1 us (it still wakes when the phase
+// completes) instead of re-issuing the wait loop, which would steal issue slots from the epilogue warps that share
+// the sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t polls = 0;; ++polls) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(1000u)
+        : "memory");
+    if (ok) return;
+    if (polls > (1u << 22)) {
+      printf("ssp: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, addr, parity);
       __trap();
     }
   }
