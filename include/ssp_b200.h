@@ -226,13 +226,14 @@ int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, int64_t n_ut
  * dims->n_models = number of mean sets S; weights double[K], variances double[K*D], means double[S*K*D] (device).
  * ref_model      index of the mean set whose per-frame maximum logit stabilises the exponentials (the UBM's own
  *                means if they are part of the set, else any member).
- * workspace      device, ssp_gmm_score_shared_workspace_bytes() bytes; may be NULL when that is 0 (this build keeps
- *                its partial sums in shared memory and needs none).
+ * workspace      device, ssp_gmm_score_shared_workspace_bytes() bytes; may be NULL when that is 0.  Large model sets
+ *                are scored in groups whose tile images stay resident in L2 while all frames pass by; the per-frame
+ *                exponent stabilisers found while the first group is scored live here (4 bytes per frame).
  */
 int64_t ssp_gmm_shared_pack_bytes(const ssp_gmm_dims* dims);
 int ssp_gmm_pack_shared(const double* weights, const double* variances, const double* means,
                         const ssp_gmm_dims* dims, void* out_pack, void* stream);
-int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims);
+int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames);
 int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64_t n_utts,
                          int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, int32_t ref_model,
                          double* out_scores, float* out_frame_lse, void* workspace, int64_t workspace_bytes,

@@ -100,10 +100,10 @@ extern "C" int ssp_gmm_pack_shared(const double* weights, const double* variance
   return ssp::launch_pack_sv(weights, variances, means, L, out_pack, (cudaStream_t)stream);
 }
 
-extern "C" int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims) {
+extern "C" int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames) {
   ssp::SvLayout L;
-  if (!ssp::make_sv_layout(dims, &L)) return 0;
-  return ssp::score_sv_workspace_bytes(L);
+  if (!ssp::make_sv_layout(dims, &L) || total_frames < 0) return 0;
+  return ssp::score_sv_workspace_bytes(L, total_frames);
 }
 
 extern "C" int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64_t n_utts, int64_t total_frames,
@@ -112,12 +112,12 @@ extern "C" int ssp_gmm_score_shared(const float* feats, const int64_t* frame_off
   ssp::SvLayout L;
   SSP_REQUIRE(ssp::make_sv_layout(dims, &L), "ssp_gmm_score_shared: unsupported dims");
   SSP_REQUIRE(frame_offsets && pack && out_scores && (feats || total_frames == 0), "ssp_gmm_score_shared: null pointer");
-  SSP_REQUIRE(workspace || ssp::score_sv_workspace_bytes(L) == 0, "ssp_gmm_score_shared: null workspace");
+  SSP_REQUIRE(workspace || ssp::score_sv_workspace_bytes(L, total_frames) == 0, "ssp_gmm_score_shared: null workspace");
   SSP_REQUIRE(n_utts >= 0 && total_frames >= 0, "ssp_gmm_score_shared: negative size");
   SSP_REQUIRE(ref_model >= 0 && ref_model < L.n_models, "ssp_gmm_score_shared: ref_model %d outside [0, %d)", ref_model,
               L.n_models);
-  SSP_REQUIRE(workspace_bytes >= ssp::score_sv_workspace_bytes(L), "ssp_gmm_score_shared: workspace of %lld bytes, need %lld",
-              (long long)workspace_bytes, (long long)ssp::score_sv_workspace_bytes(L));
+  SSP_REQUIRE(workspace_bytes >= ssp::score_sv_workspace_bytes(L, total_frames), "ssp_gmm_score_shared: workspace of %lld bytes, need %lld",
+              (long long)workspace_bytes, (long long)ssp::score_sv_workspace_bytes(L, total_frames));
   if (n_utts == 0) return SSP_OK;
   return ssp::launch_score_sv(feats, frame_offsets, n_utts, total_frames, pack, L, ref_model, true, out_scores, out_frame_lse,
                               workspace, (cudaStream_t)stream);

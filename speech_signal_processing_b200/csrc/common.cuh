@@ -173,7 +173,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
                     void* workspace, bool reuse_images, cudaStream_t st);
 bool stats_tc_supported(const PackLayout& L);
 int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, void* pack, cudaStream_t st);
-int64_t score_sv_workspace_bytes(const SvLayout& L);
+int64_t score_sv_workspace_bytes(const SvLayout& L, int64_t total_frames);
 int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
                     const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* workspace,
                     cudaStream_t st);

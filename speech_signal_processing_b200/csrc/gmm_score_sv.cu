@@ -57,10 +57,16 @@ struct Args {
   const float* feats;
   const int64_t* offsets;
   int64_t n_utts, total_frames;
-  const float* tiles;  // [n_tiles][1 + n_models][KS/4][BN] float4 images; image 0 of a tile is the common q part
-  int n_models, n_tiles, D, KS, ref_model, normalize;
-  double* scores;
-  float* frame_lse;
+  const float* tiles;  // [n_tiles][1 + S][KS/4][BN] float4 images of the WHOLE set (S models); image 0 of a tile is the common q part
+  // One launch scores the models [model0, model0 + n_models) of the set -- an L2-resident group (see launch_score_sv):
+  const float* tiles_group;  // == tiles + model0 images: image 1 + m of a tile is model model0 + m
+  int n_models;              // models of this launch
+  int set_images;            // 1 + S: images per tile
+  int set_models;            // S: row stride of the score matrix
+  int n_tiles, D, KS, ref_model, normalize;
+  float* stab;         // [total_frames] per-frame exponent stabiliser: written by the first launch (kFirst), read by the others
+  double* scores;      // + model0
+  float* frame_lse;    // + model0 * total_frames
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -78,21 +84,42 @@ __device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// spin on an mbarrier phase; a protocol bug must trap (after ~1 s), not hang the GPU.  No printf here: a call would
-// cost the control warps more registers than setmaxnreg leaves them.
+// spin on an mbarrier phase; a protocol bug must trap (after seconds), not hang the GPU.  The bound is a poll counter:
+// reading clock64() in every iteration was 5 % of the kernel's executed instructions (profiles/r1d_sass_opcode_mix).
+// No printf here: a call would cost the control warps more registers than setmaxnreg leaves them.
+// Watchdog of the spin loops: clock64() (default) or a poll counter (SSP_SV_CLOCK_WATCHDOG=0).  The clock reads are 5 % of
+// the kernel's executed instructions, but removing them makes it SLOWER: measured on one box, config 4, ms per call
+// (benchmarks/sv_ab.sh, profiles/r2e_sv_ab.txt): clock64 706 / 708, poll counter 718 / 727, counter + nanosleep(20 / 60)
+// 712 / 713 -- a waiting epilogue warp that polls faster takes issue slots and mbarrier bandwidth from the three working
+// warps of its sub-partition; the clock read is the cheapest throttle found.
+#ifndef SSP_SV_CLOCK_WATCHDOG
+#define SSP_SV_CLOCK_WATCHDOG 1
+#endif
 __device__ __forceinline__ void bar_spin(uint32_t bar, uint32_t parity) {
   if (bar_try_wait(bar, parity)) return;
+#if SSP_SV_CLOCK_WATCHDOG
   const long long t0 = clock64();
   while (!bar_try_wait(bar, parity)) {
     if (clock64() - t0 > (1ll << 31)) __trap();
   }
+#else
+  uint32_t polls = 0;
+  while (!bar_try_wait(bar, parity)) {
+#ifdef SSP_SV_POLL_SLEEP_NS
+    __nanosleep(SSP_SV_POLL_SLEEP_NS);
+#endif
+    if (++polls > (1u << 26)) __trap();
+  }
+#endif
 }
 // the control warps' version: a failed poll parks the warp in hardware for up to ~1 us instead of re-issuing the wait
 // loop, which would steal issue slots from the four epilogue warps that share the sub-partition
 __device__ __forceinline__ void bar_spin_relaxed(uint32_t bar, uint32_t parity) {
   if (bar_try_wait(bar, parity)) return;
+#if SSP_SV_CLOCK_WATCHDOG
   const long long t0 = clock64();
-  for (;;) {
+#endif
+  for (uint32_t polls = 0;; ++polls) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -102,7 +129,11 @@ __device__ __forceinline__ void bar_spin_relaxed(uint32_t bar, uint32_t parity) 
         : "r"(bar), "r"(parity), "r"(1000u)
         : "memory");
     if (ok) return;
+#if SSP_SV_CLOCK_WATCHDOG
     if (clock64() - t0 > (1ll << 31)) __trap();
+#else
+    if (polls > (1u << 22)) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void bar_arrive(uint32_t bar) {
@@ -198,7 +229,10 @@ __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float 
   return tot.x + tot.y;
 }
 
-template <int kPoly, int kDeg, int KSTEPS>
+// kFirst: this launch finds the stabilisers (pre-pass over the reference model) and, if a.stab is set, leaves them for
+// the launches of the other model groups; !kFirst: reads them.  A template flag, so that the control warps (32
+// registers after setmaxnreg) compile exactly as for a single launch.
+template <int kPoly, int kDeg, int KSTEPS, bool kFirst>
 __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int KS = KSTEPS * 8;
@@ -258,18 +292,19 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       __syncwarp();
       if (++stage == NSTAGE) { stage = 0; ph ^= 1u; }
     };
+    const size_t tile_stride = (size_t)a.set_images * tile_floats;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-      for (int j = 0; j < NT; ++j) {
-        const float* tj = a.tiles + (size_t)j * (S + 1) * tile_floats;
-        load(tj);
-        load(tj + (size_t)(1 + a.ref_model) * tile_floats);
-      }
+      if (kFirst)
+        for (int j = 0; j < NT; ++j) {
+          const float* tj = a.tiles + (size_t)j * tile_stride;
+          load(tj);
+          load(tj + (size_t)(1 + a.ref_model) * tile_floats);
+        }
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
-          const float* tj = a.tiles + (size_t)j * (S + 1) * tile_floats;
-          load(tj);
-          const float* src = tj + (size_t)(1 + m0) * tile_floats;
+          load(a.tiles + (size_t)j * tile_stride);
+          const float* src = a.tiles_group + (size_t)j * tile_stride + (size_t)(1 + m0) * tile_floats;
           for (int m = 0; m < nm; ++m, src += tile_floats) load(src);
         }
       }
@@ -335,7 +370,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
       bar_spin_relaxed(a_full, unit_idx & 1u);
       tc_fence_after();
-      for (int j = 0; j < NT; ++j) job_q(true);   // pre-pass: full logits of the reference model
+      if (kFirst)
+        for (int j = 0; j < NT; ++j) job_q(true);   // pre-pass: full logits of the reference model
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
@@ -432,19 +468,25 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       float fwgt = 1.f;
       if (futt >= 0 && a.normalize) fwgt = 1.f / (float)(a.offsets[futt + 1] - a.offsets[futt]);
 
-      // ---- pre-pass: per-frame maximum logit of the reference model -> stabiliser
-      float rmax = -3.0e38f;
-      for (int j = 0; j < NT; ++j) {
-        uint32_t r[32];
-        fetch(r);
-        float cm = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+      // ---- per-frame stabiliser: round(maximum logit of the reference model), from a pre-pass in the first launch
+      float m_t;
+      if (kFirst) {
+        float rmax = -3.0e38f;
+        for (int j = 0; j < NT; ++j) {
+          uint32_t r[32];
+          fetch(r);
+          float cm = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
 #pragma unroll
-        for (int i = 3; i < 31; i += 2) cm = max3(cm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        rmax = max3(rmax, cm, __uint_as_float(r[31]));
+          for (int i = 3; i < 31; i += 2) cm = max3(cm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          rmax = max3(rmax, cm, __uint_as_float(r[31]));
+        }
+        mx[half * UNIT + urow] = rmax;
+        named_bar_sync(1 + g, 2 * BM);
+        m_t = rintf(fmaxf(mx[urow], mx[UNIT + urow]));
+        if (half == 0 && a.stab && frame0 + urow < a.total_frames) a.stab[frame0 + urow] = m_t;
+      } else {
+        m_t = frame0 + urow < a.total_frames ? a.stab[frame0 + urow] : 0.f;
       }
-      mx[half * UNIT + urow] = rmax;
-      named_bar_sync(1 + g, 2 * BM);
-      const float m_t = rintf(fmaxf(mx[urow], mx[UNIT + urow]));
       if (half == 0) mstab[urow] = m_t;
 
       // ---- main pass, a chunk of models at a time
@@ -499,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
             float lse = (mf + lg2(v)) * LN2;
             if (!(v > 7.9e-31f && v < 1.2e30f)) lse = __int_as_float(0x7fc00000);  // outside [2^-100, 2^100]: sv_fixup_kernel
             if (flive && a.frame_lse) a.frame_lse[(int64_t)(m0 + m) * a.total_frames + ff] = lse;
-            warp_segmented_atomic_add(a.scores, futt, S, m0 + m, lse * fwgt, lane);
+            warp_segmented_atomic_add(a.scores, futt, a.set_models, m0 + m, lse * fwgt, lane);
           }
         }
         named_bar_sync(3, EPI);
@@ -518,7 +560,7 @@ __global__ void __launch_bounds__(256) sv_fixup_kernel(const Args a, int64_t n_p
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int S = a.n_models, KS = a.KS, D = a.D;
+  const int S = a.set_models, KS = a.KS, D = a.D;   // launched once over the whole set
   const size_t tile_floats = (size_t)BN * KS;
   const float LN2 = 0.69314718055994530942f;
   for (int64_t p = warp0; p < n_pairs; p += n_warps) {
@@ -567,25 +609,30 @@ static int num_sms() {
 }
 
 template <int kPoly, int kDeg, int KSTEPS>
-static int launch_one(const Args& a, unsigned grid, cudaStream_t st) {
+static int launch_one(const Args& a, unsigned grid, bool first, cudaStream_t st) {
   constexpr size_t tile_bytes = (size_t)BN * KSTEPS * 8 * 4, aq_bytes = (size_t)UNIT * KSTEPS * 8 * 4;
   constexpr size_t smem = aq_bytes + NSTAGE * tile_bytes + (size_t)2 * CHUNK * UNIT * sizeof(float) +
                           (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 + 3 * UNIT * sizeof(float);
-  SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_sv_kernel<kPoly, kDeg, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gmm_score_sv_kernel<kPoly, kDeg, KSTEPS><<<grid, THREADS, smem, st>>>(a);
+  if (first) {
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, true><<<grid, THREADS, smem, st>>>(a);
+  } else {
+    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, false><<<grid, THREADS, smem, st>>>(a);
+  }
   return SSP_OK;
 }
 template <int kPoly, int kDeg>
-static int launch_ks(const Args& a, unsigned grid, cudaStream_t st) {
+static int launch_ks(const Args& a, unsigned grid, bool first, cudaStream_t st) {
   switch (a.KS) {
-    case 8: return launch_one<kPoly, kDeg, 1>(a, grid, st);
-    case 16: return launch_one<kPoly, kDeg, 2>(a, grid, st);
-    case 24: return launch_one<kPoly, kDeg, 3>(a, grid, st);
-    case 32: return launch_one<kPoly, kDeg, 4>(a, grid, st);
-    case 40: return launch_one<kPoly, kDeg, 5>(a, grid, st);
-    case 48: return launch_one<kPoly, kDeg, 6>(a, grid, st);
-    case 56: return launch_one<kPoly, kDeg, 7>(a, grid, st);
-    case 64: return launch_one<kPoly, kDeg, 8>(a, grid, st);
+    case 8: return launch_one<kPoly, kDeg, 1>(a, grid, first, st);
+    case 16: return launch_one<kPoly, kDeg, 2>(a, grid, first, st);
+    case 24: return launch_one<kPoly, kDeg, 3>(a, grid, first, st);
+    case 32: return launch_one<kPoly, kDeg, 4>(a, grid, first, st);
+    case 40: return launch_one<kPoly, kDeg, 5>(a, grid, first, st);
+    case 48: return launch_one<kPoly, kDeg, 6>(a, grid, first, st);
+    case 56: return launch_one<kPoly, kDeg, 7>(a, grid, first, st);
+    case 64: return launch_one<kPoly, kDeg, 8>(a, grid, first, st);
   }
   set_error("ssp_gmm_score_shared: contraction length %d is not a multiple of 8 in [8, 64]", a.KS);
   return SSP_EINVAL;
@@ -593,28 +640,48 @@ static int launch_ks(const Args& a, unsigned grid, cudaStream_t st) {
 
 }  // namespace sv
 
-int64_t score_sv_workspace_bytes(const SvLayout&) { return 0; }
+// Large model sets are scored in GROUPS whose tile images stay resident in L2 while all frames pass by: one launch per
+// group over the same frames, the per-frame stabilisers of the first launch kept in the workspace.  (Round 1 streamed the
+// whole set -- 197 MB at config 4 -- once per 256-frame unit: 36 GB of DRAM reads per call, 48x the algorithmic bytes.)
+// SSP_SV_GROUP_MB sets the group's footprint (default 24 MB; 0 = one launch over the whole set).
+static int sv_group_models(const SvLayout& L) {
+  static double mb = -1.0;
+  if (mb < 0.0) {
+    const char* e = getenv("SSP_SV_GROUP_MB");
+    mb = e ? atof(e) : 24.0;
+  }
+  if (mb <= 0.0) return L.n_models;
+  const double per_model = (double)L.Kp * L.KS * sizeof(float);
+  int g = (int)(mb * 1048576.0 / per_model) / sv::CHUNK * sv::CHUNK;
+  if (g < sv::CHUNK) g = sv::CHUNK;
+  return g >= L.n_models ? L.n_models : g;
+}
+
+int64_t score_sv_workspace_bytes(const SvLayout& L, int64_t total_frames) {
+  return sv_group_models(L) < L.n_models ? (int64_t)sizeof(float) * total_frames : 0;
+}
 
 int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
-                    const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* /*workspace*/,
+                    const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* workspace,
                     cudaStream_t st) {
   using namespace sv;
   SSP_CUDA_OK(cudaMemsetAsync(scores, 0, sizeof(double) * n_utts * L.n_models, st));
   if (total_frames == 0) return SSP_OK;
+  const int group = sv_group_models(L);
   Args a;
   a.feats = feats;
   a.offsets = offsets;
   a.n_utts = n_utts;
   a.total_frames = total_frames;
   a.tiles = (const float*)pack;
-  a.n_models = L.n_models;
+  a.set_images = L.n_models + 1;
+  a.set_models = L.n_models;
   a.n_tiles = L.Kp / BN;
   a.D = L.D;
   a.KS = L.KS;
   a.ref_model = ref_model;
   a.normalize = normalize ? 1 : 0;
-  a.scores = scores;
-  a.frame_lse = frame_lse;
+  a.stab = group < L.n_models ? (float*)workspace : nullptr;
   const int64_t n_units = (total_frames + UNIT - 1) / UNIT;
   const unsigned grid = (unsigned)(n_units < num_sms() ? n_units : num_sms());
   static int poly = -1, deg = -1;
@@ -624,17 +691,29 @@ int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, 
     e = getenv("SSP_SV_POLY_DEG");
     deg = e ? atoi(e) : kDefaultPolyDeg;
   }
-  int rc = SSP_EINVAL;
-  if (deg == 4 && poly == 0) rc = launch_ks<0, 4>(a, grid, st);
-  else if (deg == 4 && poly == 2) rc = launch_ks<2, 4>(a, grid, st);
-  else if (deg == 4 && poly == 4) rc = launch_ks<4, 4>(a, grid, st);
-  else if (deg == 4 && poly == 6) rc = launch_ks<6, 4>(a, grid, st);
-  else if (deg == 4 && poly == 8) rc = launch_ks<8, 4>(a, grid, st);
-  else if (deg == 3 && poly == 6) rc = launch_ks<6, 3>(a, grid, st);
-  else if (deg == 3 && poly == 8) rc = launch_ks<8, 3>(a, grid, st);
-  else set_error("SSP_SV_POLY_PAIRS / SSP_SV_POLY_DEG: unsupported combination (%d, %d)", poly, deg);
-  if (rc != SSP_OK) return rc;
-  SSP_LAUNCH_CHECK("gmm_score_sv_kernel");
+  for (int m0 = 0; m0 < L.n_models; m0 += group) {
+    a.n_models = L.n_models - m0 < group ? L.n_models - m0 : group;
+    a.tiles_group = a.tiles + (size_t)m0 * BN * L.KS;
+    a.scores = scores + m0;
+    a.frame_lse = frame_lse ? frame_lse + (size_t)m0 * total_frames : nullptr;
+    const bool first = m0 == 0;
+    int rc = SSP_EINVAL;
+    if (deg == 4 && poly == 0) rc = launch_ks<0, 4>(a, grid, first, st);
+    else if (deg == 4 && poly == 2) rc = launch_ks<2, 4>(a, grid, first, st);
+    else if (deg == 4 && poly == 4) rc = launch_ks<4, 4>(a, grid, first, st);
+    else if (deg == 4 && poly == 6) rc = launch_ks<6, 4>(a, grid, first, st);
+    else if (deg == 4 && poly == 8) rc = launch_ks<8, 4>(a, grid, first, st);
+    else if (deg == 3 && poly == 6) rc = launch_ks<6, 3>(a, grid, first, st);
+    else if (deg == 3 && poly == 8) rc = launch_ks<8, 3>(a, grid, first, st);
+    else set_error("SSP_SV_POLY_PAIRS / SSP_SV_POLY_DEG: unsupported combination (%d, %d)", poly, deg);
+    if (rc != SSP_OK) return rc;
+    SSP_LAUNCH_CHECK("gmm_score_sv_kernel");
+  }
+  // the fix-up pass sees the whole set
+  a.n_models = L.n_models;
+  a.tiles_group = a.tiles;
+  a.scores = scores;
+  a.frame_lse = frame_lse;
   const int64_t n_pairs = n_utts * L.n_models;
   const int64_t want = (n_pairs + 7) / 8, cap = 4 * (int64_t)num_sms();
   sv_fixup_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a, n_pairs);

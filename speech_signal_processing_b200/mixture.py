@@ -202,8 +202,7 @@ class SharedModelSet:
             _lib.check(self.lib.ssp_gmm_pack_shared(_lib.ptr(w), _lib.ptr(var), _lib.ptr(mu), C.byref(self.dims),
                                                     _lib.ptr(self.pack), _lib.stream_ptr()), "ssp_gmm_pack_shared")
         self._params = (w, var, mu)
-        self._ws = torch.empty(int(self.lib.ssp_gmm_score_shared_workspace_bytes(C.byref(self.dims))), dtype=torch.uint8,
-                               device=self.device)
+        self._ws = None
 
     @staticmethod
     def shares_base(weights, variances) -> bool:
@@ -228,9 +227,12 @@ class SharedModelSet:
         d_off = torch.as_tensor(frame_offsets, device=self.device)
         scores = torch.empty((n_utts, self.n_models), dtype=torch.float64, device=self.device)
         lse = torch.empty((self.n_models, total), dtype=torch.float32, device=self.device) if want_frame_lse else None
+        ws_bytes = int(self.lib.ssp_gmm_score_shared_workspace_bytes(C.byref(self.dims), total))
+        if ws_bytes and (self._ws is None or self._ws.numel() < ws_bytes):
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         rc = self.lib.ssp_gmm_score_shared(_lib.ptr(feats), _lib.ptr(d_off), n_utts, total, _lib.ptr(self.pack),
                                            C.byref(self.dims), self.ref_model, _lib.ptr(scores), _lib.ptr(lse),
-                                           _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr())
+                                           _lib.ptr(self._ws) if ws_bytes else None, ws_bytes, _lib.stream_ptr())
         _lib.check(rc, "ssp_gmm_score_shared")
         self._keep = d_off
         return scores, lse

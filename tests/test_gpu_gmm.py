@@ -1,10 +1,13 @@
 """Parity of the GMM kernels (through the C ABI) with sklearn fixtures and the oracle."""
+import os
 import pickle
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 import speech_signal_processing_b200 as ssp  # noqa: E402
 from oracle import gmm as ogmm  # noqa: E402
@@ -666,3 +669,45 @@ def test_install_runs_the_reference_call_pattern(tmp_path, monkeypatch):
     # the same numbers as the batched entry point
     ref, _ = ssp.identify(feats, gmms, ubm, precision="fp32")
     np.testing.assert_allclose(pred, ref, rtol=0, atol=1e-4)
+
+
+def test_shared_variance_model_groups_in_l2(tmp_path):
+    """Large speaker sets are scored in L2-resident model groups (the per-frame stabilisers of the first group are kept in
+    the workspace for the later ones).  Forced here with a tiny group footprint (SSP_SV_GROUP_MB is read once per process):
+    70 models in 3 groups over 5 frame units give the scores of the single-group order and of the FP32 kernel."""
+    import subprocess
+    import sys
+
+    script = tmp_path / "groups.py"
+    script.write_text(r"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+import speech_signal_processing_b200 as ssp
+from speech_signal_processing_b200 import synth
+k, d, n_spk = 64, 39, 69
+w, mu, var = synth.synth_ubm(k, d, seed=31)
+spk_mu = np.concatenate([synth.synth_speaker_means(mu, n_spk, seed=32, shift=0.25), mu[None]])
+lens = [298, 1, 300, 255, 257, 129]
+utts = [synth.sample_gmm(w, spk_mu[i %% n_spk], var, n, seed=5 + i) for i, n in enumerate(lens)]
+sms = ssp.SharedModelSet(w, var, spk_mu, ref_model=n_spk)
+feats, offs = ssp.mixture.concat_utterances(utts, sms.device)
+got, lse = sms.score(feats, offs, want_frame_lse=True)
+assert (sms._ws is not None) == (os.environ["SSP_SV_GROUP_MB"] != "0"), "workspace <=> more than one group"
+ref = sms.expand().score(feats, offs, precision="fp32", want_frame_lse=True)
+np.save(sys.argv[1], np.stack([got.cpu().numpy(), ref[0].cpu().numpy()]))
+assert float((lse - ref[1]).abs().max() / ref[1].abs().max()) < 3e-3
+""" % ROOT)
+    out = {}
+    for mb in ("0.4", "0"):
+        path = str(tmp_path / f"scores_{mb}.npy")
+        r = subprocess.run([sys.executable, str(script), path], env=dict(os.environ, SSP_SV_GROUP_MB=mb), capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[mb] = np.load(path)
+    grouped, fp32 = out["0.4"]
+    single = out["0"][0]
+    long_enough = np.array([298, 1, 300, 255, 257, 129]) >= 31
+    np.testing.assert_allclose(grouped[long_enough], fp32[long_enough], rtol=REL["tf32"], atol=0)
+    # same stabilisers, same tiles, same order of the partial sums within a model: the grouping changes nothing
+    np.testing.assert_array_equal(grouped, single)
