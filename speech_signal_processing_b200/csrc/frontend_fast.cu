@@ -14,6 +14,11 @@
 //   * int16 PCM is staged with 16-byte loads (8 samples) when the utterance starts on a 16-byte boundary;
 //   * delta and delta-delta are materialised once in shared memory when the utterance is short enough,
 //     and the CMVN statistics / output passes read them instead of re-deriving 16 taps per element.
+//   * kSk = true is the instantiation for the reference's own setting (sidekit recipe at 16 kHz: 400-sample frames, hop
+//     160, per-frame pre-emphasis, power spectrum, 24 filters, natural log, 13 cepstra, every frame complete): frame
+//     geometry and conventions are compile-time constants, the window, the real-FFT twiddles and the DCT rows live in
+//     registers, samples are read as aligned 8-byte pairs (round 1: 4-byte loads at stride 2 floats, the bulk of the
+//     26 % bank-conflict wavefronts), the DCT runs two lanes per cepstrum, and log is lg2.approx * ln 2 (|error| ~1e-6).
 #include <cstdlib>
 
 #include "frontend_common.cuh"
@@ -66,16 +71,20 @@ __host__ __device__ inline size_t carve_floats(const ssp_frontend_cfg& c, int ma
   if (per_warp_out) *per_warp_out = per_warp;
   if (stg_out) *stg_out = stg;
   size_t f = 2 * (NH + 2) + FLp + ((c.n_ceps * (c.n_filt | 1) + 3) & ~3) + 8 * MAXSEG + 2 * MAXSEG + (MAXF + 4) + 4 + 256 + 64 + 64 +
-             stg + (size_t)W * per_warp;
+             2 * (stg + 12) + (size_t)W * per_warp;
   f += (size_t)max_frames * c.n_ceps * (mat ? (1 + c.delta_order) : 1);
   return f;
 }
 
-template <typename PcmT>
-__global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, const int materialize) {
+// the configuration the kSk instantiation is compiled for (sidekit recipe at 16 kHz, GMM_UBM.py:89)
+constexpr int SK_FL = 400, SK_SH = 160, SK_NF = 24, SK_NC = 13;
+
+template <typename PcmT, bool kSk>
+__global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, const int materialize, const int64_t n_utts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ssp_frontend_cfg& cfg = a.cfg;
-  const int NC = cfg.n_ceps, NF = cfg.n_filt, FL = cfg.frame_len, SH = cfg.frame_shift;
+  const int NC = kSk ? SK_NC : cfg.n_ceps, NF = kSk ? SK_NF : cfg.n_filt, FL = kSk ? SK_FL : cfg.frame_len,
+            SH = kSk ? SK_SH : cfg.frame_shift;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int OD = NC * (1 + cfg.delta_order);
   // ---- carve-up (mirrors carve_floats)
@@ -94,7 +103,10 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   float* red = p; p += 256;
   float* mean = p; p += 64;
   float* istd = p; p += 64;
-  float* stage = p; p += stg;
+  // two staging buffers (batch b in buffer b & 1: one CTA barrier per batch instead of two); "+ 3": sample 0 of a batch sits
+  // at a 16-byte boundary (stage[1]), so 8 samples are staged with two 16-byte stores and frames read aligned pairs
+  float* stage0 = p + 3; p += 2 * (stg + 12);
+  const int stage_stride = stg + 12;
   float* wb = p + (size_t)warp * per_warp; p += (size_t)W * per_warp;
   float* ceps = p;
   float2* ex = reinterpret_cast<float2*>(wb);
@@ -102,14 +114,7 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   float* segsum = pw + PWN;
   float* mel = segsum + MAXSEG;
 
-  const int u = blockIdx.x;
-  const int64_t s_begin = a.sample_offsets[u];
-  const int64_t n_samp = a.sample_offsets[u + 1] - s_begin;
-  const int64_t f_begin = a.frame_offsets[u];
-  const int T = (int)(a.frame_offsets[u + 1] - f_begin);
-  if (T <= 0) return;
-
-  // ---- per-CTA tables
+  // ---- per-CTA tables (built once: a CTA walks utterances blockIdx.x, + gridDim.x, ...)
   for (int k = tid; k <= NH; k += 256) {
     float s, c;
     sincospif(-(float)k / 256.0f, &s, &c);  // e^{-2 pi i k / 512}
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   for (int i = tid; i < NC * NF; i += 256) dct[(i / NF) * DS + (i % NF)] = a.dct[i];
   // filterbank CSR (3 x NF ints) is pulled in cooperatively; every triangle is cut into 8-bin segments that start
   // on a multiple of 4 bins
-  int* csr = reinterpret_cast<int*>(stage);  // stage is free until the first batch
+  int* csr = reinterpret_cast<int*>(stage0);  // the staging buffers are free until the first batch
   for (int i = tid; i < NF; i += 256) {
     csr[i] = a.fb_len[i];
     csr[MAXF + i] = a.fb_start[i];
@@ -165,9 +170,36 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   }
   __syncthreads();
 
+  // real-FFT twiddles of the bins this lane splits (k = 1 + lane + 32 j), constant across frames
+  float2 twr[4];
+#pragma unroll
+  for (int jx = 0; jx < 4; ++jx) {
+    float sn, cs;
+    sincospif(-(float)(1 + lane + 32 * jx) / 256.0f, &sn, &cs);
+    twr[jx] = make_float2(cs, sn);
+  }
+  // kSk: window taps of this lane's samples (i = 64 j + 2 lane, + 1) and its half DCT row (lane = 2 cepstrum + half)
+  float2 wreg[7];
+  float dreg[SK_NF / 2];
+  if (kSk) {
+#pragma unroll
+    for (int jx = 0; jx < 7; ++jx) {
+      const int i = 64 * jx + 2 * lane;
+      wreg[jx] = i < SK_FL ? make_float2(a.window[i], a.window[i + 1]) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < SK_NF / 2; ++i) dreg[i] = lane < 2 * SK_NC ? a.dct[(lane >> 1) * SK_NF + (lane & 1) * (SK_NF / 2) + i] : 0.f;
+  }
   const float pre = cfg.preemph;
-  const int pmode = cfg.preemph_mode;
+  const int pmode = kSk ? 1 : cfg.preemph_mode;
   const float LOG10_E = 0.43429448190325176f;
+
+  for (int64_t u = blockIdx.x; u < n_utts; u += gridDim.x) {
+  const int64_t s_begin = a.sample_offsets[u];
+  const int64_t n_samp = a.sample_offsets[u + 1] - s_begin;
+  const int64_t f_begin = a.frame_offsets[u];
+  const int T = (int)(a.frame_offsets[u + 1] - f_begin);
+  if (T <= 0) continue;
   const int n_batches = (T + W - 1) / W;
 
   // The staging loads of batch b+1 are issued before batch b is processed and only written to shared memory
@@ -210,16 +242,19 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   };
   prefetch(0);
   for (int b = 0; b < n_batches; ++b) {
-    __syncthreads();
+    float* stage = stage0 + (b & 1) * stage_stride;
     if (vec) {
       if (8 * tid < stg - 1) {
+        float smp[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t wd = __float_as_uint(pf[e]);
-          const int i = 1 + 8 * tid + 2 * e;
-          if (i < stg) stage[i] = (float)(int16_t)(wd & 0xffffu);
-          if (i + 1 < stg) stage[i + 1] = (float)(int16_t)(wd >> 16);
+          smp[2 * e] = (float)(int16_t)(wd & 0xffffu);
+          smp[2 * e + 1] = (float)(int16_t)(wd >> 16);
         }
+        float4* dst = reinterpret_cast<float4*>(stage + 1 + 8 * tid);   // 16-byte aligned; the buffer has slack for whole stores
+        dst[0] = make_float4(smp[0], smp[1], smp[2], smp[3]);
+        dst[1] = make_float4(smp[4], smp[5], smp[6], smp[7]);
       }
       if (tid == 255) stage[0] = pf[4];
     } else {
@@ -229,7 +264,7 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
         if (i < stg) stage[i] = pf[r];
       }
     }
-    __syncthreads();
+    __syncthreads();  // batch b is staged; buffer (b + 1) & 1 was last read in batch b - 1, which every warp has left
     if (b + 1 < n_batches) prefetch(b + 1);
     const int f = b * W + warp;
     if (f >= T) continue;
@@ -240,23 +275,41 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     // ---- load + pre-emphasis + energy + window, packed z[n] = (x[2n], x[2n+1]); lane holds z[32 j + lane]
     float2 v[8];
     float energy = 0.f;
+    if (kSk) {
+      // every frame is complete (framing 0): no tail handling; samples as aligned pairs, window taps from registers
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = 64 * j + 2 * lane;
-      float y0 = 0.f, y1 = 0.f;
-      if (i < n_valid) {
-        const float x0 = s[i];
-        float xm1 = s[i - 1];
-        if (i == 0 && pmode == 1) xm1 = x0;
-        y0 = pmode ? fmaf(-pre, xm1, x0) : x0;
-        if (i + 1 < n_valid) {
-          const float x1 = s[i + 1];
-          y1 = pmode ? fmaf(-pre, x0, x1) : x1;
+      for (int j = 0; j < 7; ++j) {
+        const int i = 64 * j + 2 * lane;
+        float2 x = make_float2(0.f, 0.f);
+        float xm1 = 0.f;
+        if (j < 6 || i < SK_FL) {
+          x = *reinterpret_cast<const float2*>(s + i);
+          xm1 = (j == 0 && lane == 0) ? x.x : s[i - 1];
         }
+        const float y0 = fmaf(-pre, xm1, x.x), y1 = fmaf(-pre, x.x, x.y);
+        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+        v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
       }
-      energy = fmaf(y0, y0, fmaf(y1, y1, energy));
-      const float w0 = i < FL ? win[i] : 0.f, w1 = i + 1 < FL ? win[i + 1] : 0.f;
-      v[j] = make_float2(y0 * w0, y1 * w1);
+      v[7] = make_float2(0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = 64 * j + 2 * lane;
+        float y0 = 0.f, y1 = 0.f;
+        if (i < n_valid) {
+          const float x0 = s[i];
+          float xm1 = s[i - 1];
+          if (i == 0 && pmode == 1) xm1 = x0;
+          y0 = pmode ? fmaf(-pre, xm1, x0) : x0;
+          if (i + 1 < n_valid) {
+            const float x1 = s[i + 1];
+            y1 = pmode ? fmaf(-pre, x0, x1) : x1;
+          }
+        }
+        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+        const float w0 = i < FL ? win[i] : 0.f, w1 = i + 1 < FL ? win[i + 1] : 0.f;
+        v[j] = make_float2(y0 * w0, y1 * w1);
+      }
     }
     energy = warp_sum(energy);
 
@@ -299,7 +352,7 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     for (int j = 0; j < 4; ++j) {
       const int k = 1 + lane + 32 * j, km = NH - k;  // k in 1..128
       const float2 zk = ex[k + 4 * (k >> 6)], zm = ex[km + 4 * (km >> 6)];
-      const float2 t = tw_real[k];
+      const float2 t = twr[j];
       const float2 xe = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
       const float2 xo = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
       const float2 x = cmul(t, xo);
@@ -307,9 +360,11 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
       const float re = xe.x + x.x, im = xe.y + x.y;
       const float re2 = xe.x - x.x, im2 = xe.y - x.y;
       float p1 = fmaf(re, re, im * im), p2 = fmaf(re2, re2, im2 * im2);
-      if (cfg.spec_type == 1) { p1 = sqrtf(p1); p2 = sqrtf(p2); }
-      p1 *= cfg.spec_scale;
-      p2 *= cfg.spec_scale;
+      if (!kSk) {
+        if (cfg.spec_type == 1) { p1 = sqrtf(p1); p2 = sqrtf(p2); }
+        p1 *= cfg.spec_scale;
+        p2 *= cfg.spec_scale;
+      }
       pw[k] = p1;
       if (km != k) { pw[km] = p2; etot += p2; }
       etot += p1;
@@ -317,14 +372,16 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     if (lane == 0) {
       const float2 z0 = ex[0];
       float p0 = (z0.x + z0.y) * (z0.x + z0.y), pn = (z0.x - z0.y) * (z0.x - z0.y);
-      if (cfg.spec_type == 1) { p0 = sqrtf(p0); pn = sqrtf(pn); }
-      p0 *= cfg.spec_scale;
-      pn *= cfg.spec_scale;
+      if (!kSk) {
+        if (cfg.spec_type == 1) { p0 = sqrtf(p0); pn = sqrtf(pn); }
+        p0 *= cfg.spec_scale;
+        pn *= cfg.spec_scale;
+      }
       pw[0] = p0;
       pw[NH] = pn;
       etot += p0 + pn;
     }
-    if (cfg.energy_mode == 2) etot = warp_sum(etot);
+    if (!kSk && cfg.energy_mode == 2) etot = warp_sum(etot);
     __syncwarp();
 
     // ---- filterbank: bounded-width segments spread over the lanes, then a fixed-order sum per filter
@@ -352,12 +409,31 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
         const float* q = pw + a.fb_start[m];
         for (int i = 0; i < a.fb_len[m]; ++i) acc = fmaf(w[i], q[i], acc);
       }
-      if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
-      acc += cfg.log_add;
-      mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
+      if (kSk) {
+        mel[m] = __logf(acc);
+      } else {
+        if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
+        acc += cfg.log_add;
+        mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
+      }
     }
     __syncwarp();
     // ---- DCT
+    if (kSk) {
+      // two lanes per cepstrum, 12 filters each, coefficients in registers
+      const float4* mh = reinterpret_cast<const float4*>(mel + (lane & 1) * (SK_NF / 2));
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < SK_NF / 8; ++q) {
+        const float4 mv = mh[q];
+        acc = fmaf(dreg[4 * q + 0], mv.x, acc);
+        acc = fmaf(dreg[4 * q + 1], mv.y, acc);
+        acc = fmaf(dreg[4 * q + 2], mv.z, acc);
+        acc = fmaf(dreg[4 * q + 3], mv.w, acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (lane < 2 * SK_NC && (lane & 1) == 0) ceps[f * SK_NC + (lane >> 1)] = acc;
+    } else {
     for (int j = lane; j < NC; j += 32) {
       const float* row = dct + j * DS;
       float acc0 = 0.f, acc1 = 0.f;
@@ -375,7 +451,8 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
       }
       ceps[f * NC + j] = acc;
     }
-    if (lane == 0 && a.out_log_energy && cfg.energy_mode == 1) a.out_log_energy[f_begin + f] = logf(energy);
+    }
+    if (lane == 0 && a.out_log_energy && cfg.energy_mode == 1) a.out_log_energy[f_begin + f] = kSk ? __logf(energy) : logf(energy);
   }
   __syncthreads();
 
@@ -442,6 +519,8 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
       if (jc >= OD) { jc -= OD; ++t; }
     }
   }
+  __syncthreads();  // the cepstra / statistics of this utterance are dead: the next one may overwrite them
+  }  // utterances
 }
 
 }  // namespace ff
@@ -468,13 +547,35 @@ int launch_frontend_fast(const FrontendArgs& a, int64_t n_utts, size_t* smem_out
   if (force >= 0) mat = force != 0 && a.cfg.delta_order > 0 && with <= 220 * 1024;
   const size_t smem = mat ? with : frontend_fast_smem(a.cfg, a.max_frames, false);
   if (smem_out) *smem_out = smem;
-  if (a.cfg.pcm_dtype == 0) {
-    SSP_CUDA_OK(cudaFuncSetAttribute(ff::frontend512_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ff::frontend512_kernel<int16_t><<<(unsigned)n_utts, 256, smem, st>>>(a, mat ? 1 : 0);
-  } else {
-    SSP_CUDA_OK(cudaFuncSetAttribute(ff::frontend512_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ff::frontend512_kernel<float><<<(unsigned)n_utts, 256, smem, st>>>(a, mat ? 1 : 0);
+  // persistent CTAs: the per-CTA tables (twiddles, filterbank segments) are built once and amortised over the utterances
+  // a CTA walks; 16 CTAs per SM slot keep the block scheduler's dynamic balancing for ragged batches
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    SSP_CUDA_OK(cudaGetDevice(&dev));
+    SSP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const unsigned grid = (unsigned)(n_utts < 16 * (int64_t)sms ? n_utts : 16 * (int64_t)sms);
+  const ssp_frontend_cfg& c = a.cfg;
+  static int no_sk = -1;
+  if (no_sk < 0) {
+    const char* e = getenv("SSP_FE_GENERIC");  // A/B knob: 1 = never take the compile-time specialisation
+    no_sk = e ? atoi(e) : 0;
+  }
+  const bool sk = !no_sk && c.frame_len == ff::SK_FL && c.frame_shift == ff::SK_SH && c.n_filt == ff::SK_NF && c.n_ceps == ff::SK_NC &&
+                  c.framing == 0 && c.preemph_mode == 1 && c.spec_type == 0 && c.spec_scale == 1.0f && c.log_type == 0 &&
+                  c.log_add == 0.0f && c.log_zero_floor == 0.0f && c.energy_mode <= 1;
+#define SSP_FE_LAUNCH(T, SK)                                                                                              \
+  do {                                                                                                                    \
+    SSP_CUDA_OK(cudaFuncSetAttribute(ff::frontend512_kernel<T, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ff::frontend512_kernel<T, SK><<<grid, 256, smem, st>>>(a, mat ? 1 : 0, n_utts);                                      \
+  } while (0)
+  if (c.pcm_dtype == 0) {
+    if (sk) SSP_FE_LAUNCH(int16_t, true); else SSP_FE_LAUNCH(int16_t, false);
+  } else {
+    if (sk) SSP_FE_LAUNCH(float, true); else SSP_FE_LAUNCH(float, false);
+  }
+#undef SSP_FE_LAUNCH
   SSP_LAUNCH_CHECK("frontend512_kernel");
   return SSP_OK;
 }
