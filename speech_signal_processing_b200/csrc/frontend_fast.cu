@@ -190,6 +190,13 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
 #pragma unroll
     for (int i = 0; i < SK_NF / 2; ++i) dreg[i] = lane < 2 * SK_NC ? a.dct[(lane >> 1) * SK_NF + (lane & 1) * (SK_NF / 2) + i] : 0.f;
   }
+  // kSk: this lane's filterbank bookkeeping in registers (first bin of its <= 4 segments, segment range of its filter)
+  int sgs[4] = {0, 0, 0, 0}, fs0 = 0, fs1 = 0;
+  if (kSk) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sgs[q] = (lane + 32 * q < n_seg && n_seg <= MAXSEG) ? seg_start[lane + 32 * q] : -1;
+    if (lane < SK_NF) { fs0 = filt_seg0[lane]; fs1 = filt_seg0[lane + 1]; }
+  }
   const float pre = cfg.preemph;
   const int pmode = kSk ? 1 : cfg.preemph_mode;
   const float LOG10_E = 0.43429448190325176f;
@@ -385,6 +392,45 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     __syncwarp();
 
     // ---- filterbank: bounded-width segments spread over the lanes, then a fixed-order sum per filter
+    if (kSk) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (sgs[q] >= 0) {
+          const int sg = lane + 32 * q;
+          const float4* q4 = reinterpret_cast<const float4*>(pw + sgs[q]);
+          const float4 w0 = reinterpret_cast<const float4*>(segw)[sg], w1 = reinterpret_cast<const float4*>(segw)[MAXSEG + sg];
+          const float4 q0 = q4[0], q1 = q4[1];
+          float acc = w0.x * q0.x;
+          acc = fmaf(w0.y, q0.y, acc);
+          acc = fmaf(w0.z, q0.z, acc);
+          acc = fmaf(w0.w, q0.w, acc);
+          acc = fmaf(w1.x, q1.x, acc);
+          acc = fmaf(w1.y, q1.y, acc);
+          acc = fmaf(w1.z, q1.z, acc);
+          acc = fmaf(w1.w, q1.w, acc);
+          segsum[sg] = acc;
+        }
+      }
+      __syncwarp();
+      if (lane < SK_NF) {
+        // the loads of up to 8 segments are independent (issued back to back); wider filters finish in the loop
+        float part[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) part[q] = fs0 + q < fs1 ? segsum[fs0 + q] : 0.f;
+        float acc = part[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) acc += part[q];   // same order as the sequential sum (zeros pad the tail)
+        for (int sg = fs0 + 8; sg < fs1; ++sg) acc += segsum[sg];
+        if (n_seg > MAXSEG) {  // (24 filters wider than the segment table holds: plain dot products, as in the generic path)
+          acc = 0.f;
+          const float* w = a.fb_weights + a.fb_offset[lane];
+          const float* q = pw + a.fb_start[lane];
+          for (int i = 0; i < a.fb_len[lane]; ++i) acc = fmaf(w[i], q[i], acc);
+        }
+        mel[lane] = __logf(acc);
+      }
+      __syncwarp();
+    } else {
     for (int sg = lane; sg < n_seg && n_seg <= MAXSEG; sg += 32) {
       const float4* q4 = reinterpret_cast<const float4*>(pw + seg_start[sg]);
       const float4 w0 = reinterpret_cast<const float4*>(segw)[sg], w1 = reinterpret_cast<const float4*>(segw)[MAXSEG + sg];
@@ -409,15 +455,12 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
         const float* q = pw + a.fb_start[m];
         for (int i = 0; i < a.fb_len[m]; ++i) acc = fmaf(w[i], q[i], acc);
       }
-      if (kSk) {
-        mel[m] = __logf(acc);
-      } else {
-        if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
-        acc += cfg.log_add;
-        mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
-      }
+      if (cfg.log_zero_floor > 0.f && acc == 0.f) acc = cfg.log_zero_floor;
+      acc += cfg.log_add;
+      mel[m] = cfg.log_type == 2 ? acc : (cfg.log_type == 1 ? logf(acc) * LOG10_E : logf(acc));
     }
     __syncwarp();
+    }
     // ---- DCT
     if (kSk) {
       // two lanes per cepstrum, 12 filters each, coefficients in registers
