@@ -240,11 +240,14 @@ int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64
                          void* stream);
 
 /*
- * Posterior-weighted sufficient statistics of ONE model (dims->n_models must be 1) over
- * segments of frames (one segment = all frames for UBM EM; one segment per speaker for MAP
- * enrolment):  N[s,c] = sum_t g_tc, F[s,c,:] = sum_t g_tc x_t, S[s,c,:] = sum_t g_tc x_t^2,
- * loglik[s] = sum_t log p(x_t); g = posterior (sklearn _base.py:552-582; M-step inputs of
- * _gaussian_mixture.py:312-313,250-252).  Outputs are ACCUMULATED into (caller zeroes them).
+ * Posterior-weighted sufficient statistics over segments of frames:
+ *   N[s,c] = sum_t g_tc, F[s,c,:] = sum_t g_tc x_t, S[s,c,:] = sum_t g_tc x_t^2, loglik[s] = sum_t log p(x_t);
+ *   g = posterior (sklearn _base.py:552-582; M-step inputs of _gaussian_mixture.py:312-313,250-252).
+ * dims->n_models == 1: every segment under the ONE model (all frames = one segment for UBM EM; one segment per speaker
+ *   for MAP enrolment).
+ * dims->n_models == n_segs > 1: segment s under model s -- S models trained together, the per-speaker loop of
+ *   GMM_UBM.py:154-165 as one call per EM iteration (D <= 39, n_models <= 1024).
+ * Outputs are ACCUMULATED into (caller zeroes them).
  * frame_lse      device float[total_frames]: per-frame log-likelihood under the model (written by this call)
  * workspace      device, ssp_gmm_stats_workspace_bytes() bytes, 1024-byte aligned.  The tensor-core path (tcgen05,
  *                D <= 39) keeps there (a) the tcgen05 operand images of the frames -- [x, x^2, 1, 1] as BF16 hi + lo
@@ -263,10 +266,10 @@ int64_t ssp_gmm_stats_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_fr
 
 /*
  * M-step on device (sklearn _gaussian_mixture.py:312-313,250-252,898): from (all-reduced)
- * statistics to weights/means/variances, double precision.
+ * statistics to weights/means/variances, double precision, for n_models models at once (arrays [n_models][K](xD)).
  * nk = N + 10*eps_of(stat_dtype); mu = F/nk; var = S/nk - mu^2 + reg_covar; w = nk/sum(nk).
  */
-int ssp_gmm_mstep(const double* n, const double* f, const double* s, int32_t n_comp, int32_t n_feat,
+int ssp_gmm_mstep(const double* n, const double* f, const double* s, int32_t n_models, int32_t n_comp, int32_t n_feat,
                   double reg_covar, double nk_eps, double* out_weights, double* out_means,
                   double* out_variances, void* stream);
 

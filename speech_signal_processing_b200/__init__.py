@@ -10,10 +10,10 @@ from . import vad  # noqa: F401  (reference VAD.py entry points)
 from .frontend import (FrontEnd, MFCC, MFCC_lib, MelDbFrontEnd, PlpFrontEnd, Recipe, delta, extract_feature,  # noqa: F401
                        librosa_mfcc, librosa_recipe, mfcc, mfccInitFilterBanks, plp, plp_recipe, preprocessing, processing_recipe, psf_recipe,
                        scale, sidekit_recipe)
-from .mixture import GaussianMixture, ModelSet, SharedModelSet, score_matrix  # noqa: F401
+from .mixture import GaussianMixture, ModelSet, SharedModelSet, fit_batch, score_matrix  # noqa: F401
 from .ubm import GMM, chunk_features, chunk_identify, identify, identify_pcm, install, load_data, load_extract, main, map_adapt, map_enrol  # noqa: F401
 
 __all__ = ["FrontEnd", "Recipe", "sidekit_recipe", "psf_recipe", "processing_recipe", "mfcc", "plp", "plp_recipe", "PlpFrontEnd", "MFCC", "MFCC_lib", "mfccInitFilterBanks",
            "librosa_mfcc", "librosa_recipe", "MelDbFrontEnd", "delta", "scale",
-           "preprocessing", "extract_feature", "GaussianMixture", "ModelSet", "SharedModelSet", "score_matrix", "GMM", "identify", "identify_pcm", "chunk_features", "chunk_identify",
+           "preprocessing", "extract_feature", "GaussianMixture", "ModelSet", "SharedModelSet", "score_matrix", "fit_batch", "GMM", "identify", "identify_pcm", "chunk_features", "chunk_identify",
            "map_adapt", "map_enrol", "install", "load_data", "load_extract", "main", "synth", "vad"]

@@ -146,7 +146,9 @@ extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int
                              void* stream) {
   ssp::PackLayout L;
   SSP_REQUIRE(ssp::make_layout(dims, &L), "ssp_gmm_stats: unsupported dims");
-  SSP_REQUIRE(dims->n_models == 1, "ssp_gmm_stats: statistics are taken under ONE model (got %d)", dims->n_models);
+  SSP_REQUIRE(dims->n_models == 1 || dims->n_models == n_segs,
+              "ssp_gmm_stats: %d models for %lld segments (one model for all segments, or one per segment)", dims->n_models,
+              (long long)n_segs);
   SSP_REQUIRE(seg_offsets && pack && frame_lse && out_n && out_f && out_s && out_loglik, "ssp_gmm_stats: null pointer");
   SSP_REQUIRE(n_segs >= 0 && total_frames >= 0, "ssp_gmm_stats: negative size");
   if (n_segs == 0) return SSP_OK;
@@ -159,6 +161,10 @@ extern "C" int ssp_gmm_stats(const float* feats, const int64_t* seg_offsets, int
                 (long long)(workspace ? workspace_bytes : 0), (long long)need);
     return ssp::launch_stats_tc(feats, seg_offsets, n_segs, total_frames, pack, L, frame_lse, out_n, out_f, out_s, out_loglik,
                                 workspace, reuse_images != 0, st);
+  }
+  if (dims->n_models != 1) {
+    ssp::set_error("ssp_gmm_stats: per-segment models need the tensor-core path (D <= 39, n_models <= %d)", ssp::kMaxTrainModels);
+    return SSP_EUNSUP;
   }
   // FP32 CUDA-core path (D > 39).  pass 1: per-frame log-likelihood and the per-segment sum of frame log-likelihoods (the EM
   // lower bound numerator, sklearn _base.py:558); pass 2: posteriors and N/F/S

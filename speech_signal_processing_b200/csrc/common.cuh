@@ -47,6 +47,7 @@ void count_launch(const char* kernel_name);
 //                                 TF32-rounded, log2(e)-scaled rows [mu/var, -1/(2var), c_hi, c_lo, 0..]
 constexpr int kTileN = 128;  // components per tensor tile / padding granule of K
 constexpr int kMaxFeat = 80;
+constexpr int kMaxTrainModels = 1024;  // model sets up to this size carry the BF16 images ssp_gmm_stats needs
 
 struct PackLayout {
   int n_models, K, D;
@@ -109,12 +110,13 @@ inline bool make_layout(const ssp_gmm_dims* dims, PackLayout* L) {
   // residual ("lo") tiles: B = hi + lo to ~2^-22 -- the 3xTF32 EM kernels and the 2- / 3-pass scoring rungs
   L->off_tile_lo = o;
   o = up(o + (size_t)L->n_models * L->Kp * L->KD * sizeof(float));
-  // BF16 hi + lo images of a single model (the UBM) for the EM / MAP statistics kernels:
-  // [Kp/128 tiles][hi | lo][KDb/8][128][8 bf16]; the constant rides as three BF16 pieces (hi: columns 2D, 2D+1; lo: 2D)
+  // BF16 hi + lo images for the EM / MAP statistics kernels (the UBM, or a small set of models trained together --
+  // one per segment): [model][Kp/128 tiles][hi | lo][KDb/8][128][8 bf16]; the constant rides as three BF16 pieces
+  // (hi: columns 2D, 2D+1; lo: 2D)
   L->off_tile_bf = 0;
-  if (L->n_models == 1 && 2 * L->D + 2 <= 80) {
+  if (L->n_models <= kMaxTrainModels && 2 * L->D + 2 <= 80) {
     L->off_tile_bf = o;
-    o = up(o + (size_t)(L->Kp / kTileN) * 512 * L->KDb());
+    o = up(o + (size_t)L->n_models * (L->Kp / kTileN) * 512 * L->KDb());
   }
   L->bytes = o;
   return true;

@@ -56,7 +56,7 @@ struct Ws {
 static Ws ws_layout(const PackLayout& L, int64_t total_frames, int64_t n_segs) {
   Ws w;
   w.KDb = (2 * L.D + 2 + 15) / 16 * 16;
-  w.nb_max = (total_frames / BLK + n_segs + 2) & ~(int64_t)1;
+  w.nb_max = (total_frames / BLK + 2 * n_segs + 2) & ~(int64_t)1;  // per-segment models pad segments to whole 128-frame images
   w.P = w.nb_max * BLK;
   auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
   size_t o = 0;
@@ -88,8 +88,9 @@ struct Args {
   const unsigned char* xt;  // [nb_max] images:     [hi | lo][16][KDb rows][4 fp32]
   int64_t nb_max, P;
   // model
-  const unsigned char* tiles;  // [n_tiles] images [hi | lo][KDb/8][128 comps][8 bf16]
+  const unsigned char* tiles;  // [model][n_tiles] images [hi | lo][KDb/8][128 comps][8 bf16]
   int K, D, KDb, n_tiles;
+  int per_seg_model;           // 1: segment s is scored under model s (grid z = segment; segments padded to whole Fb images)
   // outputs
   float* frame_lse;
   double* out_n;
@@ -185,8 +186,13 @@ __global__ void __launch_bounds__(1024) em_plan_kernel(const Args a) {
   const int tid = threadIdx.x;
   const int64_t per = (a.n_segs + 1023) / 1024;
   const int64_t s0 = min((int64_t)tid * per, a.n_segs), s1 = min(s0 + per, a.n_segs);
+  // blocks of a segment; with per-segment models an even number, so that no Fb image straddles two models
+  auto n_blk = [&](int64_t s) {
+    const int64_t nbk = (a.seg[s + 1] - a.seg[s] + BLK - 1) / BLK;
+    return a.per_seg_model ? (nbk + 1) & ~(int64_t)1 : nbk;
+  };
   int64_t sum = 0;
-  for (int64_t s = s0; s < s1; ++s) sum += (a.seg[s + 1] - a.seg[s] + BLK - 1) / BLK;
+  for (int64_t s = s0; s < s1; ++s) sum += n_blk(s);
   part[tid] = sum;
   __syncthreads();
   if (tid == 0) {
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(1024) em_plan_kernel(const Args a) {
   int64_t run = part[tid];
   for (int64_t s = s0; s < s1; ++s) {
     a.blk_start[s] = run;
-    run += (a.seg[s + 1] - a.seg[s] + BLK - 1) / BLK;
+    run += n_blk(s);
   }
 }
 
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(256) em_prep_kernel(const Args a) {
     if (b < nb) {
       seg = find_segment(a.blk_start, a.n_segs, b);
       t0 = a.seg[seg] + (b - a.blk_start[seg]) * BLK;
-      nt = (int)min((int64_t)BLK, a.seg[seg + 1] - t0);
+      nt = (int)max((int64_t)0, min((int64_t)BLK, a.seg[seg + 1] - t0));  // 0: the padding block of an odd-sized segment
     }
     s_nt = nt; s_t0 = t0;
     a.blk_seg[b] = seg;
@@ -312,17 +318,23 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int64_t nb = a.blk_start[a.n_segs];
-  const int64_t n_img = (nb + 1) >> 1;
-  const int64_t per = (n_img + gridDim.x - 1) / gridDim.x;
-  const int64_t i0 = (int64_t)blockIdx.x * per, i1 = min(i0 + per, n_img);
+  // images of this CTA: a chunk of all images, or (per-segment models) a chunk of the images of segment blockIdx.z
+  int64_t img_lo = 0, img_hi = (a.blk_start[a.n_segs] + 1) >> 1;
+  const unsigned char* tiles = a.tiles;
+  if (a.per_seg_model) {
+    img_lo = a.blk_start[blockIdx.z] >> 1;
+    img_hi = a.blk_start[blockIdx.z + 1] >> 1;
+    tiles += (size_t)blockIdx.z * a.n_tiles * TB;
+  }
+  const int64_t per = (img_hi - img_lo + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = img_lo + (int64_t)blockIdx.x * per, i1 = min(i0 + per, img_hi);
 
   if (warp == 0) {
     // ===================== producer =====================
     if (i0 < i1) {
       if (elect_one()) {
         mbar_arrive_expect_tx(b_full, (uint32_t)ntl * TB);
-        for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, a.tiles + (size_t)(tile0 + t) * TB, TB, b_full);
+        for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, tiles + (size_t)(tile0 + t) * TB, TB, b_full);
       }
       __syncwarp();
       uint32_t k = 0;
@@ -498,16 +510,23 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int64_t nb = a.blk_start[a.n_segs];
-  const int64_t per = (nb + gridDim.x - 1) / gridDim.x;
-  const int64_t b0 = (int64_t)blockIdx.x * per, b1 = min(b0 + per, nb);
+  // blocks of this CTA: a chunk of all blocks, or (per-segment models) a chunk of the blocks of segment blockIdx.z
+  int64_t blk_lo = 0, blk_hi = a.blk_start[a.n_segs];
+  const unsigned char* tiles = a.tiles;
+  if (a.per_seg_model) {
+    blk_lo = a.blk_start[blockIdx.z];
+    blk_hi = a.blk_start[blockIdx.z + 1];
+    tiles += (size_t)blockIdx.z * a.n_tiles * TB;
+  }
+  const int64_t per = (blk_hi - blk_lo + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = blk_lo + (int64_t)blockIdx.x * per, b1 = min(b0 + per, blk_hi);
 
   if (warp == 0) {
     // ===================== producer =====================
     if (b0 < b1) {
       if (elect_one()) {
         mbar_arrive_expect_tx(b_full, (uint32_t)ntl * TB);
-        for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, a.tiles + (size_t)(tile0 + t) * TB, TB, b_full);
+        for (int t = 0; t < ntl; ++t) bulk_g2s(sB + (size_t)t * TB, tiles + (size_t)(tile0 + t) * TB, TB, b_full);
       }
       __syncwarp();
       constexpr int n_pieces = 2 * (KDb >> 3);  // (hi | lo) x chunk: 1 KB each, 64 rows x 16 B out of a 128-row chunk
@@ -672,7 +691,7 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
 
 }  // namespace em
 
-bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_bf != 0 && L.n_models == 1; }
+bool stats_tc_supported(const PackLayout& L) { return L.KD <= em::MAX_KD && L.off_tile_bf != 0; }
 
 int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames, int64_t n_segs) {
   return stats_tc_supported(L) ? (int64_t)em::ws_layout(L, total_frames, n_segs).bytes : 0;
@@ -712,6 +731,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   a.D = L.D;
   a.KDb = w.KDb;
   a.n_tiles = L.Kp / BN;
+  a.per_seg_model = L.n_models > 1 ? 1 : 0;
   a.frame_lse = frame_lse;
   a.out_n = out_n;
   a.out_f = out_f;
@@ -726,7 +746,9 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   const int n_pairs = (a.n_tiles + 1) / 2;
   // the number of blocks is a device value (segment padding); size the grids from its host-side bounds
   const int64_t nb_lo = (total_frames + BLK - 1) / BLK;
-  int64_t gx = num_sms / n_pairs;
+  const unsigned gz = a.per_seg_model ? (unsigned)n_segs : 1u;
+  SSP_REQUIRE(gz <= 65535u, "ssp_gmm_stats: %lld per-segment models (at most 65535)", (long long)n_segs);
+  int64_t gx = num_sms / ((int64_t)n_pairs * gz);
   if (gx < 1) gx = 1;
   const int64_t gx_l = min(gx, (nb_lo + 1) / 2), gx_s = min(gx, nb_lo);
   const size_t TB = w.img_bytes();
@@ -740,7 +762,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
 #define SSP_EM_LSE(pp)                                                                                               \
   case pp:                                                                                                           \
     SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_lse_kernel<pp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lse)); \
-    gmm_em_lse_kernel<pp><<<dim3((unsigned)gx_l, (unsigned)n_pairs), THREADS, smem_lse, st>>>(a);                   \
+    gmm_em_lse_kernel<pp><<<dim3((unsigned)gx_l, (unsigned)n_pairs, gz), THREADS, smem_lse, st>>>(a);               \
     break;
   switch (poly) {
     SSP_EM_LSE(0) SSP_EM_LSE(2) SSP_EM_LSE(4) SSP_EM_LSE(6) SSP_EM_LSE(8)
@@ -753,7 +775,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
 #define SSP_EM_STATS(ks)                                                                                                  \
   case ks:                                                                                                                \
     SSP_CUDA_OK(cudaFuncSetAttribute(gmm_em_stats_kernel<ks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats)); \
-    gmm_em_stats_kernel<ks><<<dim3((unsigned)gx_s, (unsigned)n_pairs), p3::THREADS_S, smem_stats, st>>>(a);             \
+    gmm_em_stats_kernel<ks><<<dim3((unsigned)gx_s, (unsigned)n_pairs, gz), p3::THREADS_S, smem_stats, st>>>(a);         \
     break;
   switch (w.KDb >> 4) {
     SSP_EM_STATS(1) SSP_EM_STATS(2) SSP_EM_STATS(3) SSP_EM_STATS(4) SSP_EM_STATS(5)

@@ -31,7 +31,7 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   float* tlo = tiles_lo ? tiles_lo + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KD : nullptr;
   auto lo_at = [&](int j) -> float& { return tlo[((j >> 2) * kTileN + n) * 4 + (j & 3)]; };
   // BF16 image of the tile (EM kernels): [hi | lo][KDb/8][128][8], element (part, j, n) at ((part*KDb/8 + j/8)*128 + n)*8 + j%8
-  __nv_bfloat16* tbf = tiles_bf ? tiles_bf + (int64_t)(c / kTileN) * 2 * kTileN * KDb : nullptr;
+  __nv_bfloat16* tbf = tiles_bf ? tiles_bf + ((int64_t)m * (Kp / kTileN) + c / kTileN) * 2 * kTileN * KDb : nullptr;
   auto bf_at = [&](int part, int j) -> __nv_bfloat16& {
     return tbf[(((int64_t)part * (KDb >> 3) + (j >> 3)) * kTileN + n) * 8 + (j & 7)];
   };
@@ -172,6 +172,10 @@ __global__ void gmm_mstep_kernel(const double* __restrict__ n, const double* __r
                                  double* __restrict__ omu, double* __restrict__ ovar) {
   __shared__ double red[32];
   __shared__ double total_s;
+  // one block per model (statistics and parameters of model m at offset m * K (* D))
+  n += (int64_t)blockIdx.x * K; ow += (int64_t)blockIdx.x * K;
+  f += (int64_t)blockIdx.x * K * D; s += (int64_t)blockIdx.x * K * D;
+  omu += (int64_t)blockIdx.x * K * D; ovar += (int64_t)blockIdx.x * K * D;
   double part = 0.0;
   for (int c = threadIdx.x; c < K; c += blockDim.x) part += n[c] + nk_eps;
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -244,13 +248,13 @@ __global__ void gmm_map_kernel(const double* __restrict__ n, const double* __res
 
 }  // namespace ssp
 
-extern "C" int ssp_gmm_mstep(const double* n, const double* f, const double* s, int32_t n_comp, int32_t n_feat,
+extern "C" int ssp_gmm_mstep(const double* n, const double* f, const double* s, int32_t n_models, int32_t n_comp, int32_t n_feat,
                              double reg_covar, double nk_eps, double* out_weights, double* out_means,
                              double* out_variances, void* stream) {
   SSP_REQUIRE(n && f && s && out_weights && out_means && out_variances, "ssp_gmm_mstep: null pointer");
-  SSP_REQUIRE(n_comp > 0 && n_feat > 0, "ssp_gmm_mstep: bad dims");
-  ssp::gmm_mstep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, f, s, n_comp, n_feat, reg_covar, nk_eps, out_weights,
-                                                             out_means, out_variances);
+  SSP_REQUIRE(n_models > 0 && n_comp > 0 && n_feat > 0, "ssp_gmm_mstep: bad dims");
+  ssp::gmm_mstep_kernel<<<(unsigned)n_models, 1024, 0, (cudaStream_t)stream>>>(n, f, s, n_comp, n_feat, reg_covar, nk_eps,
+                                                                              out_weights, out_means, out_variances);
   SSP_LAUNCH_CHECK("gmm_mstep_kernel");
   return SSP_OK;
 }

@@ -119,16 +119,18 @@ class ModelSet:
 
     @_lib.on_device
     def stats(self, feats, seg_offsets, workspace=None, reuse_images=False):
-        """N (S,K), F (S,K,D), S2 (S,K,D), loglik (S,) float64 cuda, under this (single) model.
+        """N (S,K), F (S,K,D), S2 (S,K,D), loglik (S,) float64 cuda: every segment under this set's single model, or
+        -- if the set holds one model per segment -- segment s under model s (models trained together, :func:`fit_batch`).
 
         ``workspace``: a :class:`StatsWorkspace` shared between calls (and model sets) on the SAME ``feats`` /
         ``seg_offsets``; ``reuse_images=True`` then skips the preparation pass that turns the frames into tensor-core
         operand images (EM iterations: the frames never change).  Default: a workspace owned by this model set."""
         torch = _lib.require_cuda()
-        if self.n_models != 1:
-            raise ValueError("statistics are taken under one model (the UBM)")
         seg_offsets = np.asarray(seg_offsets, dtype=np.int64)
         n_segs, total = len(seg_offsets) - 1, int(seg_offsets[-1])
+        if self.n_models != 1 and self.n_models != n_segs:
+            raise ValueError("statistics are taken under one model for all segments (the UBM), or under one model per "
+                             f"segment (got {self.n_models} models for {n_segs} segments)")
         k, d = self.n_comp, self.n_feat
         n = torch.zeros((n_segs, k), dtype=torch.float64, device=self.device)
         f = torch.zeros((n_segs, k, d), dtype=torch.float64, device=self.device)
@@ -345,7 +347,7 @@ class GaussianMixture:
                 timing[-1][1].record()
             n, f, s = flat[:k].reshape(1, k), flat[k : k + k * d].reshape(1, k, d), flat[k + k * d : k + 2 * k * d].reshape(1, k, d)
             ll, n_total = flat[k + 2 * k * d : k + 2 * k * d + 1], float(flat[-1].item())
-        rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), ms.n_comp, ms.n_feat, float(self.reg_covar),
+        rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), 1, ms.n_comp, ms.n_feat, float(self.reg_covar),
                                   float(nk_eps), _lib.ptr(w), _lib.ptr(mu), _lib.ptr(var), _lib.stream_ptr())
         _lib.check(rc, "ssp_gmm_mstep")
         return float(ll.item()) / n_total, n
@@ -402,7 +404,7 @@ class GaussianMixture:
             if comm is not None:
                 flat = reduced(torch.cat([n.reshape(-1), f.reshape(-1), s.reshape(-1)]))
                 n, f, s = flat[:k].reshape(1, k), flat[k : k + k * d].reshape(1, k, d), flat[k + k * d :].reshape(1, k, d)
-            rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), k, d, float(self.reg_covar), float(nk_eps),
+            rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), 1, k, d, float(self.reg_covar), float(nk_eps),
                                       _lib.ptr(w), _lib.ptr(mu), _lib.ptr(var), _lib.stream_ptr())
             _lib.check(rc, "ssp_gmm_mstep")
             empty = (n[0] < 0.5).nonzero().flatten()
@@ -418,6 +420,32 @@ class GaussianMixture:
             w.fill_(1.0 / k)
             if empty.numel():
                 mu[0, empty] = seed_rows(int(empty.numel()), avoid=mu[0])
+
+    def _initial_parameters(self, feats, seg, rs, nk_eps, do_init=True, workspace=None):
+        """(w (1,K), mu (1,K,D), var (1,K,D)) float64 on the device: warm start, k-means / random initialisation
+        (sklearn/mixture/_base.py:120-129) and the user's ``*_init`` overrides."""
+        torch = _lib.require_cuda()
+        dev, (k, d) = feats.device, (self.n_components, feats.shape[1])
+        w = torch.empty((1, k), dtype=torch.float64, device=dev)
+        mu = torch.empty((1, k, d), dtype=torch.float64, device=dev)
+        var = torch.empty((1, k, d), dtype=torch.float64, device=dev)
+        if not do_init:
+            w.copy_(torch.as_tensor(self.weights_)[None]); mu.copy_(torch.as_tensor(self.means_)[None])
+            var.copy_(torch.as_tensor(self.covariances_)[None])
+            return w, mu, var
+        have_all = self.weights_init is not None and self.means_init is not None and self.precisions_init is not None
+        if not have_all:
+            if self.init_params not in ("kmeans", "k-means++", "random_from_data", "random"):
+                raise ValueError(f"Invalid value for 'init_params': {self.init_params}")
+            self._kmeans_init(feats, seg, rs, w, mu, var, nk_eps,
+                              iters=10 if self.init_params in ("kmeans", "k-means++") else 0, workspace=workspace)
+        if self.weights_init is not None:
+            w.copy_(torch.as_tensor(np.asarray(self.weights_init, dtype=np.float64))[None])
+        if self.means_init is not None:
+            mu.copy_(torch.as_tensor(np.asarray(self.means_init, dtype=np.float64))[None])
+        if self.precisions_init is not None:
+            var.copy_(1.0 / torch.as_tensor(np.asarray(self.precisions_init, dtype=np.float64))[None])
+        return w, mu, var
 
     def fit(self, X, y=None):
         """Estimate parameters with EM (sklearn/mixture/_base.py:203-312)."""
@@ -443,25 +471,7 @@ class GaussianMixture:
         best = None
         workspace = StatsWorkspace(dev)  # the frames' operand images are built by the first statistics call and reused
         for _init in range(self.n_init if do_init else 1):
-            w = torch.empty((1, k), dtype=torch.float64, device=dev)
-            mu = torch.empty((1, k, d), dtype=torch.float64, device=dev)
-            var = torch.empty((1, k, d), dtype=torch.float64, device=dev)
-            if not do_init:
-                w.copy_(torch.as_tensor(self.weights_)[None]); mu.copy_(torch.as_tensor(self.means_)[None])
-                var.copy_(torch.as_tensor(self.covariances_)[None])
-            else:
-                have_all = self.weights_init is not None and self.means_init is not None and self.precisions_init is not None
-                if not have_all:
-                    if self.init_params not in ("kmeans", "k-means++", "random_from_data", "random"):
-                        raise ValueError(f"Invalid value for 'init_params': {self.init_params}")
-                    self._kmeans_init(feats, seg, rs, w, mu, var, nk_eps,
-                                      iters=10 if self.init_params in ("kmeans", "k-means++") else 0, workspace=workspace)
-                if self.weights_init is not None:
-                    w.copy_(torch.as_tensor(np.asarray(self.weights_init, dtype=np.float64))[None])
-                if self.means_init is not None:
-                    mu.copy_(torch.as_tensor(np.asarray(self.means_init, dtype=np.float64))[None])
-                if self.precisions_init is not None:
-                    var.copy_(1.0 / torch.as_tensor(np.asarray(self.precisions_init, dtype=np.float64))[None])
+            w, mu, var = self._initial_parameters(feats, seg, rs, nk_eps, do_init, workspace)
             ms = ModelSet(w, mu, var, device=dev)
             lower, bounds, converged, n_iter = -np.inf, [], False, 0
             for n_iter in range(1, self.max_iter + 1):
@@ -534,3 +544,100 @@ class GaussianMixture:
         sk.converged_, sk.n_iter_, sk.lower_bound_ = self.converged_, self.n_iter_, self.lower_bound_
         sk.n_features_in_ = self.means_.shape[1]
         return sk
+
+
+def fit_batch(X_list, n_components=1, **kwargs):
+    """``[GaussianMixture(n_components, **kwargs).fit(X) for X in X_list]`` -- the per-speaker training loop of
+    GMM_UBM.py:154-165 -- with the EM iterations of ALL models batched: one ``ssp_gmm_stats`` call per iteration scores
+    segment s (speaker s's frames) under model s, one ``ssp_gmm_mstep`` launch updates every model, and ONE host
+    read-back per iteration carries all lower bounds.  A model that has converged (sklearn's ``abs(change) < tol`` rule,
+    per model) keeps the parameters of its converging iteration while the others go on, so every model ends with the
+    ``n_iter_`` / parameters its own loop would have produced.  Initialisation (k-means or the ``*_init`` arguments,
+    which may be per-model lists) runs per model, exactly as in :meth:`GaussianMixture.fit`.
+
+    Returns the list of fitted :class:`GaussianMixture`.  ``n_init > 1``, ``warm_start`` and ``comm`` fall back to the
+    plain loop."""
+    torch = _lib.require_cuda()
+    n_models = len(X_list)
+    per_model = {key: kwargs.pop(key) for key in ("weights_init", "means_init", "precisions_init") if key in kwargs}
+
+    def ctor_kwargs(i):
+        out = dict(kwargs)
+        for key, val in per_model.items():
+            out[key] = None if val is None else (val[i] if isinstance(val, (list, tuple)) or np.ndim(val) == (3 if key != "weights_init" else 2) else val)
+        return out
+
+    gms = [GaussianMixture(n_components=n_components, **ctor_kwargs(i)) for i in range(n_models)]
+    if n_models == 0:
+        return gms
+    g0 = gms[0]
+    g0._check()
+    if g0.n_init != 1 or g0.warm_start or g0.comm is not None or n_models > 1024:
+        return [gm.fit(x) for gm, x in zip(gms, X_list)]
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    feats, seg = concat_utterances([np.asarray(x) if not isinstance(x, torch.Tensor) else x.cpu().numpy() for x in X_list], dev)
+    d, k = feats.shape[1], n_components
+    if 2 * d + 2 > 80:  # per-segment models need the tensor-core statistics kernels
+        return [gm.fit(x) for gm, x in zip(gms, X_list)]
+    counts = np.diff(seg)
+    for cnt in counts:
+        if cnt < 2:
+            raise ValueError(f"Found array with {cnt} sample(s) while a minimum of 2 is required.")
+        if cnt < k:
+            raise ValueError(f"Expected n_samples >= n_components but got n_components = {k}, n_samples = {cnt}")
+    x_dtypes = [np.float32 if (isinstance(x, torch.Tensor) and x.dtype == torch.float32) or
+                (isinstance(x, np.ndarray) and x.dtype == np.float32) else np.float64 for x in X_list]
+    nk_eps = 10.0 * float(np.finfo(x_dtypes[0]).eps)
+    # ---- initial parameters, per model (same code and RNG use as fit())
+    w = torch.empty((n_models, k), dtype=torch.float64, device=dev)
+    mu = torch.empty((n_models, k, d), dtype=torch.float64, device=dev)
+    var = torch.empty((n_models, k, d), dtype=torch.float64, device=dev)
+    for i, gm in enumerate(gms):
+        rs = gm.random_state if isinstance(gm.random_state, np.random.RandomState) else np.random.RandomState(gm.random_state)
+        fi = feats[int(seg[i]) : int(seg[i + 1])]
+        wi, mi, vi = gm._initial_parameters(fi, np.array([0, fi.shape[0]], dtype=np.int64), rs, nk_eps, True, StatsWorkspace(dev))
+        w[i], mu[i], var[i] = wi[0], mi[0], vi[0]
+    # ---- batched EM
+    ms = ModelSet(w, mu, var, device=dev)
+    workspace = StatsWorkspace(dev)
+    t_counts = torch.as_tensor(counts.astype(np.float64), device=dev)
+    w_new, mu_new, var_new = torch.empty_like(w), torch.empty_like(mu), torch.empty_like(var)
+    lower = np.full(n_models, -np.inf)
+    bounds = [[] for _ in range(n_models)]
+    converged = np.zeros(n_models, dtype=bool)
+    n_iter = np.zeros(n_models, dtype=np.int64)
+    for it in range(1, g0.max_iter + 1):
+        active = ~converged
+        if not active.any():
+            break
+        ms.repack(w, mu, var)
+        n, f, s, ll = ms.stats(feats, seg, workspace=workspace, reuse_images=True)
+        rc = ms.lib.ssp_gmm_mstep(_lib.ptr(n), _lib.ptr(f), _lib.ptr(s), n_models, k, d, float(g0.reg_covar), float(nk_eps),
+                                  _lib.ptr(w_new), _lib.ptr(mu_new), _lib.ptr(var_new), _lib.stream_ptr())
+        _lib.check(rc, "ssp_gmm_mstep")
+        now = (ll / t_counts).cpu().numpy()          # the one host synchronisation of the iteration
+        keep = torch.as_tensor(active, device=dev)
+        w = torch.where(keep[:, None], w_new, w)
+        mu = torch.where(keep[:, None, None], mu_new, mu)
+        var = torch.where(keep[:, None, None], var_new, var)
+        for i in np.nonzero(active)[0]:
+            bounds[i].append(float(now[i]))
+            n_iter[i] = it
+            if abs(now[i] - lower[i]) < g0.tol:
+                converged[i] = True
+            lower[i] = now[i]
+    hw, hmu, hvar = w.cpu().numpy(), mu.cpu().numpy(), var.cpu().numpy()
+    for i, gm in enumerate(gms):
+        if not converged[i] and gm.max_iter > 0:
+            warnings.warn("Best performing initialization did not converge. Try different init parameters, or "
+                          "increase max_iter, tol, or check for degenerate data.", UserWarning)
+        gm.weights_, gm.means_, gm.covariances_ = hw[i], hmu[i], hvar[i]
+        gm.precisions_cholesky_ = 1.0 / np.sqrt(gm.covariances_)
+        gm.precisions_ = gm.precisions_cholesky_ ** 2
+        if not np.all(np.isfinite(gm.covariances_)) or np.any(gm.covariances_ <= 0):
+            raise ValueError("Fitting the mixture model failed because some components have ill-defined empirical "
+                             "covariance (for instance caused by singleton or collapsed samples). Try to decrease the "
+                             "number of components, increase reg_covar, or scale the input data.")
+        gm.converged_, gm.n_iter_, gm.lower_bound_, gm.lower_bounds_ = bool(converged[i]), int(n_iter[i]), float(lower[i]), bounds[i]
+        gm._ms = None
+    return gms

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from . import frontend as fe
-from .mixture import (SINGLE_PASS_MIN_COMPONENTS, GaussianMixture, ModelSet, SharedModelSet, concat_utterances,
+from .mixture import (SINGLE_PASS_MIN_COMPONENTS, GaussianMixture, ModelSet, SharedModelSet, concat_utterances, fit_batch,
                       resolve_precision)
 
 
@@ -351,9 +351,9 @@ def GMM(train, x_train, y_train, x_test, y_test, n_components=16, model=False, l
             ubm = GaussianMixture.from_sklearn(u) if not isinstance(u, GaussianMixture) else u
     else:
         print("Train GMM!")
-        gmms = []
-        for spk in speakers:
-            gmms.append(GaussianMixture(n_components=n_components, covariance_type="diag", random_state=random_state).fit(train[spk]))
+        # the per-speaker loop of GMM_UBM.py:154-160 as ONE batched EM: a statistics call per iteration for all speakers
+        gmms = fit_batch([train[spk] for spk in speakers], n_components=n_components, covariance_type="diag",
+                         random_state=random_state)
         print("Train UBM!")
         ubm_train = np.vstack([train[spk] for spk in speakers])
         ubm = GaussianMixture(n_components=n_components, covariance_type="diag", random_state=random_state).fit(ubm_train)

@@ -632,7 +632,7 @@ def test_config3_512_component_statistics_match_oracle():
     rw, rmu, rvar = ogmm.m_step(*(np.asarray(t, dtype=np.float64) for t in tot))
     gw, gmu, gvar = (torch.empty(sh, dtype=torch.float64, device="cuda") for sh in ((k,), (k, d), (k, d)))
     tn, tf_, ts = (torch.as_tensor(t, device="cuda") for t in tot)
-    _lib.check(_lib.load().ssp_gmm_mstep(_lib.ptr(tn), _lib.ptr(tf_), _lib.ptr(ts), k, d, 1e-6, 10 * np.finfo(np.float64).eps,
+    _lib.check(_lib.load().ssp_gmm_mstep(_lib.ptr(tn), _lib.ptr(tf_), _lib.ptr(ts), 1, k, d, 1e-6, 10 * np.finfo(np.float64).eps,
                                          _lib.ptr(gw), _lib.ptr(gmu), _lib.ptr(gvar), _lib.stream_ptr()), "ssp_gmm_mstep")
     np.testing.assert_allclose(gw.cpu().numpy(), rw, rtol=1e-12)
     np.testing.assert_allclose(gmu.cpu().numpy(), rmu, rtol=1e-10, atol=1e-12)
@@ -711,3 +711,59 @@ assert float((lse - ref[1]).abs().max() / ref[1].abs().max()) < 3e-3
     np.testing.assert_allclose(grouped[long_enough], fp32[long_enough], rtol=REL["tf32"], atol=0)
     # same stabilisers, same tiles, same order of the partial sums within a model: the grouping changes nothing
     np.testing.assert_array_equal(grouped, single)
+
+
+def test_fit_batch_equals_the_per_speaker_loop():
+    """GMM_UBM.py:154-165 trains one GMM per speaker in a Python loop; fit_batch runs the EM iterations of all of them
+    as one segmented call per iteration (segment s under model s).  Same initial parameters in => per-model n_iter_,
+    convergence flags, lower bounds and parameters of the looped fits out -- also when the models need different numbers
+    of iterations -- with O(iterations) statistics launches instead of O(speakers x iterations)."""
+    import warnings
+
+    from speech_signal_processing_b200 import _lib
+
+    k, d, n_spk = 16, 26, 5
+    xs, inits = [], []
+    for i in range(n_spk):
+        w, mu, var = synth.synth_ubm(k, d, seed=90 + i, spread=1.0 + 0.3 * i)
+        xs.append(synth.sample_gmm(w, mu, var, 1500 + 211 * i, seed=95 + i))       # ragged: 1500 .. 2344 frames (odd block counts)
+        w0, mu0, var0 = synth.synth_ubm(k, d, seed=190 + i, spread=1.0)
+        inits.append((w0, mu0 + 0.2, np.ones_like(var0)))
+    kw = dict(covariance_type="diag", max_iter=40, tol=1e-3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        looped = [ssp.GaussianMixture(n_components=k, weights_init=a, means_init=b, precisions_init=1.0 / c, **kw).fit(x)
+                  for x, (a, b, c) in zip(xs, inits)]
+        _lib.load().ssp_reset_launch_count()
+        batched = ssp.fit_batch(xs, n_components=k, weights_init=[a for a, _, _ in inits], means_init=[b for _, b, _ in inits],
+                                precisions_init=[1.0 / c for _, _, c in inits], **kw)
+    log = _lib.launch_log()
+    iters = max(g.n_iter_ for g in batched)
+    assert log["gmm_em_stats_kernel"] == iters and log["gmm_mstep_kernel"] == iters   # not n_spk x iterations
+    assert len({g.n_iter_ for g in looped}) > 1, "the case should exercise per-model convergence"
+    for a, b in zip(looped, batched):
+        assert (a.n_iter_, a.converged_) == (b.n_iter_, b.converged_)
+        # The two runs chunk the frames differently (FP32 accumulation in TMEM per chunk) and add the float64 partial
+        # statistics in a different order; over dozens of iterations that moves the trajectory by ~1e-5 relative.
+        assert abs(a.lower_bound_ - b.lower_bound_) <= 2e-5 * abs(a.lower_bound_)
+        np.testing.assert_allclose(b.weights_, a.weights_, rtol=2e-3, atol=1e-6)
+        np.testing.assert_allclose(b.means_, a.means_, rtol=0, atol=2e-3)
+        np.testing.assert_allclose(b.covariances_, a.covariances_, rtol=1e-2, atol=1e-5)
+    # ... while ONE iteration from the same parameters is the same arithmetic up to the summation order
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        one_l = [ssp.GaussianMixture(n_components=k, weights_init=a, means_init=b, precisions_init=1.0 / c, covariance_type="diag",
+                                     max_iter=1).fit(x) for x, (a, b, c) in zip(xs, inits)]
+        one_b = ssp.fit_batch(xs, n_components=k, weights_init=[a for a, _, _ in inits], means_init=[b for _, b, _ in inits],
+                              precisions_init=[1.0 / c for _, _, c in inits], covariance_type="diag", max_iter=1)
+    for a, b in zip(one_l, one_b):
+        assert abs(a.lower_bound_ - b.lower_bound_) <= 1e-7 * abs(a.lower_bound_)
+        np.testing.assert_allclose(b.weights_, a.weights_, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(b.means_, a.means_, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(b.covariances_, a.covariances_, rtol=1e-5, atol=1e-8)
+    # default initialisation (k-means per model, then batched EM) trains usable models
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        auto = ssp.fit_batch(xs, n_components=k, covariance_type="diag", random_state=0)
+    for i, g in enumerate(auto):
+        assert g.score(xs[i]) > max(g.score(xs[j]) for j in range(n_spk) if j != i)
