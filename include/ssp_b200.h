@@ -219,25 +219,27 @@ int ssp_gmm_score(const float* feats, const int64_t* frame_offsets, int64_t n_ut
  * Scoring of model sets that SHARE weights and variances and differ in their means only -- what mean-only
  * relevance-MAP enrolment from a UBM produces (ssp_gmm_map_adapt with flags == 1), i.e. the speaker models of
  * GMM_UBM.py:182-197 when they are adapted instead of trained from scratch.  The log-likelihood splits into a part
- * common to all models ([x^2, 1] . [-1/(2 var), const]) computed once per frame block and a per-model part linear
- * in the frame ([x, 1] . [mu/var, const]), so the per-model tensor-core contraction is D + 2 long instead of
- * 2D + 2.  Same results as ssp_gmm_score(SSP_PREC_TF32) on the expanded set, to TF32 rounding.
+ * common to all models -- the full logit of a REFERENCE member of the set, [x^2, x, 1] . [-1/(2 var), mu_ref/var,
+ * const], computed once per frame block with the model operand split in two TF32 pieces -- and a per-model part
+ * linear in the frame, [x, 1] . [(mu - mu_ref)/var, const], so the per-model tensor-core contraction is D + 2 long
+ * instead of 2D + 2 and TF32 rounding acts on the DIFFERENCE from the reference only: scores agree with
+ * ssp_gmm_score(SSP_PREC_TF32) on the expanded set to TF32 rounding or better, and log-likelihood ratios against the
+ * reference member are an order of magnitude tighter for MAP-adapted speakers.
  *
  * dims->n_models = number of mean sets S; weights double[K], variances double[K*D], means double[S*K*D] (device).
- * ref_model      index of the mean set whose per-frame maximum logit stabilises the exponentials (the UBM's own
- *                means if they are part of the set, else any member).
+ * ref_model      (at pack time) index of the reference member: the UBM's own means if they are part of the set,
+ *                else any member.  Its per-frame maximum logit also stabilises the exponentials.
  * workspace      device, ssp_gmm_score_shared_workspace_bytes() bytes; may be NULL when that is 0.  Large model sets
  *                are scored in groups whose tile images stay resident in L2 while all frames pass by; the per-frame
  *                exponent stabilisers found while the first group is scored live here (4 bytes per frame).
  */
 int64_t ssp_gmm_shared_pack_bytes(const ssp_gmm_dims* dims);
 int ssp_gmm_pack_shared(const double* weights, const double* variances, const double* means,
-                        const ssp_gmm_dims* dims, void* out_pack, void* stream);
+                        const ssp_gmm_dims* dims, int32_t ref_model, void* out_pack, void* stream);
 int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames);
 int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64_t n_utts,
-                         int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, int32_t ref_model,
-                         double* out_scores, float* out_frame_lse, void* workspace, int64_t workspace_bytes,
-                         void* stream);
+                         int64_t total_frames, const void* pack, const ssp_gmm_dims* dims, double* out_scores,
+                         float* out_frame_lse, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Posterior-weighted sufficient statistics over segments of frames:

@@ -66,9 +66,9 @@ PROTOTYPES = {
     "ssp_gmm_pack_models": (C.c_int, [_P, _P, _P, C.POINTER(GmmDims), _P, _P]),
     "ssp_gmm_score": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(GmmDims), _I32, _P, _P, _P]),
     "ssp_gmm_shared_pack_bytes": (_I64, [C.POINTER(GmmDims)]),
-    "ssp_gmm_pack_shared": (C.c_int, [_P, _P, _P, C.POINTER(GmmDims), _P, _P]),
+    "ssp_gmm_pack_shared": (C.c_int, [_P, _P, _P, C.POINTER(GmmDims), _I32, _P, _P]),
     "ssp_gmm_score_shared_workspace_bytes": (_I64, [C.POINTER(GmmDims), _I64]),
-    "ssp_gmm_score_shared": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(GmmDims), _I32, _P, _P, _P, _I64, _P]),
+    "ssp_gmm_score_shared": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(GmmDims), _P, _P, _P, _I64, _P]),
     "ssp_gmm_stats": (C.c_int, [_P, _P, _I64, _I64, _P, C.POINTER(GmmDims), _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "ssp_gmm_stats_workspace_bytes": (_I64, [C.POINTER(GmmDims), _I64, _I64]),
     "ssp_gmm_mstep": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, C.c_double, C.c_double, _P, _P, _P, _P]),

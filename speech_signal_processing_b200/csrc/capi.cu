@@ -92,12 +92,14 @@ extern "C" int64_t ssp_gmm_shared_pack_bytes(const ssp_gmm_dims* dims) {
 }
 
 extern "C" int ssp_gmm_pack_shared(const double* weights, const double* variances, const double* means,
-                                   const ssp_gmm_dims* dims, void* out_pack, void* stream) {
+                                   const ssp_gmm_dims* dims, int32_t ref_model, void* out_pack, void* stream) {
   ssp::SvLayout L;
-  SSP_REQUIRE(ssp::make_sv_layout(dims, &L), "ssp_gmm_pack_shared: unsupported dims (need 1 <= D <= %d)", ssp::kSvMaxKS - 2);
+  SSP_REQUIRE(ssp::make_sv_layout(dims, &L), "ssp_gmm_pack_shared: unsupported dims (need 1 <= D <= %d)", ssp::kSvMaxFeat);
   SSP_REQUIRE(weights && variances && means && out_pack, "ssp_gmm_pack_shared: null pointer");
   SSP_REQUIRE(((uintptr_t)out_pack & 127) == 0, "ssp_gmm_pack_shared: out_pack must be 128-byte aligned");
-  return ssp::launch_pack_sv(weights, variances, means, L, out_pack, (cudaStream_t)stream);
+  SSP_REQUIRE(ref_model >= 0 && ref_model < L.n_models, "ssp_gmm_pack_shared: ref_model %d outside [0, %d)", ref_model,
+              L.n_models);
+  return ssp::launch_pack_sv(weights, variances, means, L, ref_model, out_pack, (cudaStream_t)stream);
 }
 
 extern "C" int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims, int64_t total_frames) {
@@ -107,20 +109,18 @@ extern "C" int64_t ssp_gmm_score_shared_workspace_bytes(const ssp_gmm_dims* dims
 }
 
 extern "C" int ssp_gmm_score_shared(const float* feats, const int64_t* frame_offsets, int64_t n_utts, int64_t total_frames,
-                                    const void* pack, const ssp_gmm_dims* dims, int32_t ref_model, double* out_scores,
-                                    float* out_frame_lse, void* workspace, int64_t workspace_bytes, void* stream) {
+                                    const void* pack, const ssp_gmm_dims* dims, double* out_scores, float* out_frame_lse,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
   ssp::SvLayout L;
   SSP_REQUIRE(ssp::make_sv_layout(dims, &L), "ssp_gmm_score_shared: unsupported dims");
   SSP_REQUIRE(frame_offsets && pack && out_scores && (feats || total_frames == 0), "ssp_gmm_score_shared: null pointer");
   SSP_REQUIRE(workspace || ssp::score_sv_workspace_bytes(L, total_frames) == 0, "ssp_gmm_score_shared: null workspace");
   SSP_REQUIRE(n_utts >= 0 && total_frames >= 0, "ssp_gmm_score_shared: negative size");
-  SSP_REQUIRE(ref_model >= 0 && ref_model < L.n_models, "ssp_gmm_score_shared: ref_model %d outside [0, %d)", ref_model,
-              L.n_models);
   SSP_REQUIRE(workspace_bytes >= ssp::score_sv_workspace_bytes(L, total_frames), "ssp_gmm_score_shared: workspace of %lld bytes, need %lld",
               (long long)workspace_bytes, (long long)ssp::score_sv_workspace_bytes(L, total_frames));
   if (n_utts == 0) return SSP_OK;
-  return ssp::launch_score_sv(feats, frame_offsets, n_utts, total_frames, pack, L, ref_model, true, out_scores, out_frame_lse,
-                              workspace, (cudaStream_t)stream);
+  return ssp::launch_score_sv(feats, frame_offsets, n_utts, total_frames, pack, L, true, out_scores, out_frame_lse, workspace,
+                              (cudaStream_t)stream);
 }
 
 // The tensor-core kernels serve every feature width they support (D <= 39); the FP32 CUDA-core kernels are the

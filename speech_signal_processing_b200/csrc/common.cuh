@@ -60,17 +60,34 @@ struct PackLayout {
 };
 
 // Shared-variance model sets (gmm_score_sv.cu): every model has the base model's weights and variances and its own
-// means.  One buffer of tcgen05 shared-memory images, [Kp/64 tiles][1 + n_models][KS/4][64] float4:
-//   image 0      = common part   log2(e) [-1/(2 var), cq_hi, cq_lo, 0..],  cq = log w - D/2 log 2pi - 1/2 sum log var
-//   image 1 + s  = model s       log2(e) [mu_s/var,   ck_hi, ck_lo, 0..],  ck = -1/2 sum mu_s^2 / var
+// means.  One buffer of tcgen05 shared-memory images, [Kp/64 tiles][kSvBaseImages + n_models][KS/4][64] float4, all
+// scaled by log2(e); "hi" / "lo" are the two TF32 pieces of a value (hi + lo exact to ~2^-22):
+//   images 0, 1  = common part, hi / lo     [-1/(2 var), cq pieces, 0..],  cq = log w - D/2 log 2pi - 1/2 sum log var
+//   images 2, 3  = reference model, hi / lo [mu_ref/var, ck pieces, 0..],  ck = -1/2 sum mu_ref^2 / var
+//   image 4      = BF16 image [KL/8][64][8] of [-1/(2 var) | mu_ref/var | 0..], KL = roundup(2D, 16): multiplies the
+//                  frames' TF32 rounding residuals [x^2 - tf32(x^2) | x - tf32(x)]
+//   image 5 + s  = model s MINUS the reference  [(mu_s - mu_ref)/var, (ck_s - ck_ref) hi, lo, 0..]
 constexpr int kSvTileN = 64;
 constexpr int kSvMaxKS = 64;
+constexpr int kSvBaseImages = 5;
+// shape of gmm_score_sv_kernel (here because it bounds the feature width the layout accepts)
+#ifndef SSP_SV_STAGES
+#define SSP_SV_STAGES 6
+#endif
+constexpr int kSvStages = SSP_SV_STAGES, kSvSlots = 6, kSvChunk = 32, kSvUnit = 256;
+constexpr size_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
+constexpr int kSvMaxFeat = 40;          // widest feature vector whose operands fit (sv_smem_bytes)
 struct SvLayout {
   int n_models, K, D;
   int Kp;  // K rounded up to kSvTileN
   int KS;  // contraction length: roundup(D + 2, 8)
   size_t bytes;
 };
+inline int sv_residual_len(int D) { return (2 * D + 15) / 16 * 16; }
+inline size_t sv_smem_bytes(int KS, int KL) {
+  return (size_t)kSvUnit * KS * 4 + (size_t)kSvUnit * KL * 2 + (size_t)kSvStages * kSvTileN * KS * 4 +
+         (size_t)2 * kSvChunk * kSvUnit * 4 + (2 * kSvStages + 2 * kSvSlots + 2) * 8 + 16 + kSvUnit * 4;
+}
 inline bool make_sv_layout(const ssp_gmm_dims* dims, SvLayout* L) {
   if (!dims || dims->n_models < 1 || dims->n_comp < 1 || dims->n_feat < 1) return false;
   L->n_models = dims->n_models;
@@ -78,8 +95,8 @@ inline bool make_sv_layout(const ssp_gmm_dims* dims, SvLayout* L) {
   L->D = dims->n_feat;
   L->Kp = (L->K + kSvTileN - 1) / kSvTileN * kSvTileN;
   L->KS = (L->D + 2 + 7) / 8 * 8;
-  if (L->KS > kSvMaxKS) return false;
-  L->bytes = (size_t)(L->Kp / kSvTileN) * (size_t)(L->n_models + 1) * kSvTileN * L->KS * sizeof(float);
+  if (L->KS > kSvMaxKS || sv_smem_bytes(L->KS, sv_residual_len(L->D)) > kMaxDynSmem) return false;  // D <= kSvMaxFeat
+  L->bytes = (size_t)(L->Kp / kSvTileN) * (size_t)(L->n_models + kSvBaseImages) * kSvTileN * L->KS * sizeof(float);
   return true;
 }
 
@@ -174,11 +191,11 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
                     const PackLayout& L, float* frame_lse, double* out_n, double* out_f, double* out_s, double* out_loglik,
                     void* workspace, bool reuse_images, cudaStream_t st);
 bool stats_tc_supported(const PackLayout& L);
-int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, void* pack, cudaStream_t st);
+int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, int ref_model, void* pack,
+                   cudaStream_t st);
 int64_t score_sv_workspace_bytes(const SvLayout& L, int64_t total_frames);
 int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
-                    const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* workspace,
-                    cudaStream_t st);
+                    const SvLayout& L, bool normalize, double* scores, float* frame_lse, void* workspace, cudaStream_t st);
 int64_t stats_tc_workspace_bytes(const PackLayout& L, int64_t total_frames, int64_t n_segs);
 int launch_stats_simt(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames,
                       const void* pack, const PackLayout& L, const float* frame_lse, double* out_n, double* out_f,

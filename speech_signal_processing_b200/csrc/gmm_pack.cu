@@ -113,53 +113,90 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
   return SSP_OK;
 }
 
-// Shared-variance pack (SvLayout): one thread per (image, padded component).
+// Shared-variance pack (SvLayout): one thread per (image, padded component).  Images 0..3 are the part common to all
+// models INCLUDING the reference model's means, as hi + lo TF32 pieces (split-B: model-side rounding of the common part
+// drops to ~2^-22); image kSvBaseImages + s holds model s as its DIFFERENCE from the reference, so TF32 rounding acts
+// on (mu_s - mu_ref) / var -- an order of magnitude smaller than mu_s / var for MAP-adapted speakers -- and the
+// reference model's own image is exactly zero: a log-likelihood RATIO against it carries the rounding of the
+// differences only.
 __global__ void gmm_pack_sv_kernel(const double* __restrict__ w, const double* __restrict__ var, const double* __restrict__ mu,
-                                   int S, int K, int Kp, int D, int KS, float* __restrict__ tiles) {
+                                   int S, int K, int Kp, int D, int KS, int ref, float* __restrict__ tiles) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)(S + 1) * Kp) return;
+  const int n_images = S + kSvBaseImages;
+  if (idx >= (int64_t)n_images * Kp) return;
   const int image = (int)(idx / Kp), c = (int)(idx % Kp);
   const int n = c % kSvTileN;
-  float* tile = tiles + ((int64_t)(c / kSvTileN) * (S + 1) + image) * (int64_t)kSvTileN * KS;
+  float* tile = tiles + ((int64_t)(c / kSvTileN) * n_images + image) * (int64_t)kSvTileN * KS;
   auto tile_at = [&](int j) -> float& { return tile[((j >> 2) * kSvTileN + n) * 4 + (j & 3)]; };
-  for (int j = 0; j < KS; ++j) tile_at(j) = 0.f;
   const double LOG2E = 1.4426950408889634074;
+  const double* var_r = var + (int64_t)c * D;
+  const double* ref_r = mu + ((int64_t)ref * K + c) * D;
+  if (image == 4) {  // BF16 [KL/8][64][8] in the same slot (KL <= 2 KS): what the frames' rounding residuals multiply
+    __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(tile);
+    for (int j = 0; j < 2 * KS; ++j) {
+      double v = 0.0;
+      if (c < K && j < 2 * D) v = (j < D ? -0.5 : ref_r[j - D]) / var_r[j < D ? j : j - D] * LOG2E;
+      tb[((j >> 3) * kSvTileN + n) * 8 + (j & 7)] = __float2bfloat16_rn((float)v);
+    }
+    return;
+  }
+  for (int j = 0; j < KS; ++j) tile_at(j) = 0.f;
   if (c >= K) {
     if (image == 0) tile_at(D) = to_tf32(-1e30f);  // padded components never contribute
     return;
   }
-  const double* var_r = var + (int64_t)c * D;
+  const bool lo_image = image == 1 || image == 3;
+  auto hi_of = [](double v) { return to_tf32((float)v); };
+  auto piece = [&](double v) {  // the hi or the lo TF32 piece of v, by image
+    const float h = hi_of(v);
+    return lo_image ? to_tf32((float)(v - (double)h)) : h;
+  };
   double cc;
-  if (image == 0) {
+  if (image < 2) {          // [x^2, 1, 1] . log2(e) [-1/(2 var), cq ...],  cq = log w - D/2 log 2pi - 1/2 sum log var
     double logdet = 0.0;
     for (int d = 0; d < D; ++d) {
       const double p = 1.0 / var_r[d];
       logdet += log(p);
-      tile_at(d) = to_tf32((float)(-0.5 * p * LOG2E));
+      tile_at(d) = piece(-0.5 * p * LOG2E);
     }
     cc = log(w[c]) - 0.5 * D * 1.8378770664093454836 + 0.5 * logdet;
     if (!(cc > -1e30)) cc = -1e30;  // w == 0
-  } else {
-    const double* mu_r = mu + ((int64_t)(image - 1) * K + c) * D;
+  } else if (image < kSvBaseImages) {  // [x, 1, 1] . log2(e) [mu_ref / var, ck ...],  ck = -1/2 sum mu_ref^2 / var
     double quad = 0.0;
     for (int d = 0; d < D; ++d) {
       const double p = 1.0 / var_r[d];
-      quad += mu_r[d] * mu_r[d] * p;
-      tile_at(d) = to_tf32((float)(mu_r[d] * p * LOG2E));
+      quad += ref_r[d] * ref_r[d] * p;
+      tile_at(d) = piece(ref_r[d] * p * LOG2E);
     }
     cc = -0.5 * quad;
+  } else {                   // [x, 1, 1] . log2(e) [(mu_s - mu_ref) / var, ck_s - ck_ref ...]
+    const double* mu_r = mu + ((int64_t)(image - kSvBaseImages) * K + c) * D;
+    double dquad = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double p = 1.0 / var_r[d], dm = mu_r[d] - ref_r[d];
+      dquad += dm * (mu_r[d] + ref_r[d]) * p;
+      tile_at(d) = hi_of(dm * p * LOG2E);
+    }
+    cc = -0.5 * dquad;
   }
+  // the constant as exactly representable TF32 pieces against the frame operand's two columns of 1.0: two in a hi (or
+  // difference) image, the third in the lo image
   const double c2 = cc * LOG2E;
-  const float hi = to_tf32((float)c2);
-  tile_at(D) = hi;
-  tile_at(D + 1) = to_tf32((float)(c2 - (double)hi));
+  const float hi = hi_of(c2), lo = to_tf32((float)(c2 - (double)hi));
+  if (lo_image) {
+    tile_at(D) = to_tf32((float)(c2 - (double)hi - (double)lo));
+  } else {
+    tile_at(D) = hi;
+    tile_at(D + 1) = lo;
+  }
 }
 
-int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, void* pack, cudaStream_t st) {
-  const int64_t n = (int64_t)(L.n_models + 1) * L.Kp;
+int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, int ref_model, void* pack,
+                   cudaStream_t st) {
+  const int64_t n = (int64_t)(L.n_models + kSvBaseImages) * L.Kp;
   const int threads = 128;
   gmm_pack_sv_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(w, var, mu, L.n_models, L.K, L.Kp, L.D, L.KS,
-                                                                              (float*)pack);
+                                                                              ref_model, (float*)pack);
   SSP_LAUNCH_CHECK("gmm_pack_sv_kernel");
   return SSP_OK;
 }

@@ -6,11 +6,18 @@
 // linear in the frame:
 //
 //     L2[t, s, c] = q[t, c] + r[t, s, c]
-//     q[t, c]     = [x_t^2, 1, 1] . [-1/(2 var_c), cq_hi, cq_lo] * log2(e)      cq = log w_c - D/2 log 2pi - 1/2 sum log var_c
-//     r[t, s, c]  = [x_t,   1, 1] . [mu_sc/var_c,  ck_hi, ck_lo] * log2(e)      ck = -1/2 sum mu_sc^2 / var_c
+//     q[t, c]     = [x_t^2, 1, 1] . [-1/(2 var_c), cq..] * log2(e)              cq = log w_c - D/2 log 2pi - 1/2 sum log var_c
+//                 + [x_t,   1, 1] . [mu_ref,c/var_c, ck..] * log2(e)            ck = -1/2 sum mu_ref,c^2 / var_c
+//     r[t, s, c]  = [x_t,   1, 1] . [(mu_sc - mu_ref,c)/var_c, dck_hi, dck_lo] * log2(e)
 //
 // so the per-speaker contraction has K = D + 2 (48 after padding at D = 39) instead of 2D + 2 (80): 40 % fewer
 // tensor-core cycles, and the common part is computed once per (256 frames, 64 components) and kept in registers.
+// q is the full logit of a REFERENCE model of the set (the UBM), evaluated to FP32 grade in the 3xTF32 manner: the
+// model operand as hi + lo TF32 pieces (four images per tile) and the frames' own rounding residuals
+// [x^2 - tf32(x^2), x - tf32(x)] as a BF16 operand against a BF16 image of the model (kind::f16 into the same FP32
+// accumulator).  A speaker enters only through its DIFFERENCE from the reference, so the TF32 rounding of the
+// per-speaker part scales with |mu_s - mu_ref| (gmm_pack.cu: gmm_pack_sv_kernel).  The common part is 1/32 of the
+// tensor work, so the extra passes cost ~1 %.
 //
 //   one persistent CTA per SM, unit = 256 frames (two 128-row blocks), component tile = 64
 //   loop order per unit:  chunk of 32 models (outer)  x  component tile j  x  model in the chunk (inner)
@@ -29,6 +36,8 @@
 //   per-frame log-likelihoods, are summed per utterance inside the warp and added to the (utterance, model) scores.
 //   A sum outside [2^-100, 2^100] (a model nowhere near the reference) turns the score into NaN and
 //   sv_fixup_kernel re-scores that (utterance, model) pair with a plain FP32 online log-sum-exp.
+#include <cuda_bf16.h>
+
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -40,16 +49,25 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int MB = 2;
 constexpr int UNIT = BM * MB;
+static_assert(UNIT == kSvUnit, "sv_smem_bytes");
 constexpr int BN = kSvTileN;
-constexpr int NSTAGE = 8;
-constexpr int NSLOT = 6;                 // 3 per row block
+constexpr int NSTAGE = kSvStages;
+constexpr int NSLOT = kSvSlots;                 // 3 per row block
 constexpr int EPI_WARPS = 16;
 constexpr int EPI = EPI_WARPS * 32;
 constexpr int CTRL = 128;                // warpgroup 0: producer, two MMA issuers, one idle warp (setmaxnreg is per warpgroup)
 constexpr int THREADS = CTRL + EPI;
 constexpr int CTRL_REGS = 32, EPI_REGS = 112;  // launched at 96: 128 x (96 - 32) registers released == 512 x (112 - 96) acquired
-constexpr int CHUNK = 32;                // models per chunk: partial sums [2 column halves][CHUNK][UNIT] fp32 = 64 KB
+constexpr int NQ = kSvBaseImages;          // images of the common part: [x^2] hi, lo (both operands in shared memory), [x] reference hi, lo (frames in
+                                         // TMEM), BF16 [x^2 | x] against the frames' rounding residuals
+constexpr int CHUNK = kSvChunk;                // models per chunk: partial sums [2 column halves][CHUNK][UNIT] fp32 = 64 KB
 constexpr uint32_t ACC_COL0 = 128;       // TMEM: [0, 2 KS) frame operand of the two row blocks, [128, 512) accumulators
+#ifndef SSP_SV_RSTEPS
+#define SSP_SV_RSTEPS 0  // A/B builds only: K steps issued per model job (0 = all; fewer gives wrong results, for timing)
+#endif
+#ifndef SSP_SV_QMASK
+#define SSP_SV_QMASK 0x1f  // which of the NQ images of the common part are multiplied (all; cleared bits are A/B builds)
+#endif
 constexpr int kDefaultPolyPairs = 4;  // measured on B200 (2000 utts x 1001 models): 0/4/6/8 pairs -> 163/136/142/155 ms
 constexpr int kDefaultPolyDeg = 4;
 
@@ -57,13 +75,14 @@ struct Args {
   const float* feats;
   const int64_t* offsets;
   int64_t n_utts, total_frames;
-  const float* tiles;  // [n_tiles][1 + S][KS/4][BN] float4 images of the WHOLE set (S models); image 0 of a tile is the common q part
+  const float* tiles;  // [n_tiles][NQ + S][KS/4][BN] float4 images of the WHOLE set (S models); images 0..NQ-1 of a tile are the common q part
   // One launch scores the models [model0, model0 + n_models) of the set -- an L2-resident group (see launch_score_sv):
-  const float* tiles_group;  // == tiles + model0 images: image 1 + m of a tile is model model0 + m
+  const float* tiles_group;  // == tiles + model0 images: image NQ + m of a tile is model model0 + m
   int n_models;              // models of this launch
-  int set_images;            // 1 + S: images per tile
+  int set_images;            // NQ + S: images per tile
   int set_models;            // S: row stride of the score matrix
-  int n_tiles, D, KS, ref_model, normalize;
+  int n_tiles, D, KS, normalize;
+  int KL;              // contraction length of the residual pass: roundup(2 D, 16)
   float* stab;         // [total_frames] per-frame exponent stabiliser: written by the first launch (kFirst), read by the others
   double* scores;      // + model0
   float* frame_lse;    // + model0 * total_frames
@@ -239,7 +258,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
   constexpr uint32_t tile_bytes = (uint32_t)BN * KS * 4u;       // one model tile image
   constexpr uint32_t aq_block_bytes = (uint32_t)BM * KS * 4u;   // q operand of one row block
   float* sAq = reinterpret_cast<float*>(smem);                                  // [MB][KS/4][BM][4]
-  unsigned char* sB = smem + (size_t)MB * aq_block_bytes;                       // [NSTAGE][KS/4][BN][4]
+  __nv_bfloat16* sAl = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)MB * aq_block_bytes);  // [MB][KL/8][BM][8] residuals
+  const uint32_t al_block_bytes = (uint32_t)a.KL * BM * 2u;
+  unsigned char* sB = smem + (size_t)MB * aq_block_bytes + (size_t)MB * al_block_bytes;  // [NSTAGE][KS/4][BN][4]
   float* sPart = reinterpret_cast<float*>(sB + (size_t)NSTAGE * tile_bytes);    // [2][CHUNK][UNIT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * CHUNK * UNIT);
   const uint32_t b_full = smem_u32(bars);  // barrier i of a group at +8 i
@@ -249,8 +270,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
   const uint32_t a_full = t_empty + 8u * NSLOT;
   const uint32_t a_empty = a_full + 8u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NSLOT + 2);
-  float* mx = reinterpret_cast<float*>(tmem_slot + 4);  // [2][UNIT] row maxima of the two column halves
-  float* mstab = mx + 2 * UNIT;                          // [UNIT] per-frame stabiliser
+  float* mstab = reinterpret_cast<float*>(tmem_slot + 4);  // [UNIT] per-frame stabiliser
+  float* mx = sPart;  // [2][UNIT] row maxima of the two column halves: pre-pass only, the partial sums are idle (zero) then
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -297,14 +318,14 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       if (kFirst)
         for (int j = 0; j < NT; ++j) {
           const float* tj = a.tiles + (size_t)j * tile_stride;
-          load(tj);
-          load(tj + (size_t)(1 + a.ref_model) * tile_floats);
+          for (int i = 0; i < NQ; ++i, tj += tile_floats) load(tj);
         }
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
-          load(a.tiles + (size_t)j * tile_stride);
-          const float* src = a.tiles_group + (size_t)j * tile_stride + (size_t)(1 + m0) * tile_floats;
+          const float* tj = a.tiles + (size_t)j * tile_stride;
+          for (int i = 0; i < NQ; ++i, tj += tile_floats) load(tj);
+          const float* src = a.tiles_group + (size_t)j * tile_stride + (size_t)(NQ + m0) * tile_floats;
           for (int m = 0; m < nm; ++m, src += tile_floats) load(src);
         }
       }
@@ -316,7 +337,10 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     constexpr uint32_t ks_a = (2u * lbo_a) >> 4, ks_b = (2u * lbo_b) >> 4;  // one K = 8 step in descriptor units
     constexpr uint32_t tile_units = tile_bytes >> 4;
     const uint64_t aq_desc = make_desc(smem_u32(sAq) + (uint32_t)g * aq_block_bytes, lbo_a, sbo);
+    const uint64_t al_desc = make_desc(smem_u32(sAl) + (uint32_t)g * al_block_bytes, lbo_a, sbo);  // 16-byte chunks of 8 BF16: same strides
     const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_b, sbo);
+    constexpr uint32_t idesc_bf = make_idesc_bf16(BM, BN);
+    const int klsteps = a.KL >> 4;
     const uint32_t at = tmem_base + (uint32_t)(g * KS);
     const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
     uint32_t stage = 0, bph = 0, s3 = 0, sph = 0, unit_idx = 0;
@@ -332,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
         const uint64_t bd = b_desc0 + (uint64_t)(stage * tile_units);
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : preinit);
+        for (int k = 0; k < (SSP_SV_RSTEPS ? SSP_SV_RSTEPS : KSTEPS); ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : preinit);
         bar_commit(t_full + 8u * slot);
         bar_commit(b_empty + 8u * stage);
       }
@@ -340,42 +364,48 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       next_stage();
       next_slot();
     };
-    // q part (both operands in shared memory), optionally followed by the reference model's r part
-    auto job_q = [&](bool with_r) {
-      bar_spin_relaxed(b_full + 8u * stage, bph);
-      const uint32_t stage_q = stage;
-      next_stage();
-      if (with_r) bar_spin_relaxed(b_full + 8u * stage, bph);
+    // common part = full logit of the reference model: images 0, 1 against [x^2, 1, 1] in shared memory, images 2, 3
+    // against [x, 1, 1] in TMEM, image 4 (BF16) against the rounding residuals of the frames, all into one accumulator;
+    // an image's ring stage is released as soon as its MMAs retire
+    auto job_q = [&]() {
       const uint32_t slot = (uint32_t)g + 2u * s3;
       bar_spin_relaxed(t_empty + 8u * slot, sph ^ 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
-        const uint64_t bq = b_desc0 + (uint64_t)(stage_q * tile_units);
+      const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32(d_tmem, aq_desc + (uint64_t)(k * ks_a), bq + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : 0u);
-        if (with_r) {
-          const uint64_t br = b_desc0 + (uint64_t)(stage * tile_units);
+      for (int part = 0; part < NQ; ++part) {
+        bar_spin_relaxed(b_full + 8u * stage, bph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bd = b_desc0 + (uint64_t)(stage * tile_units);
+          if (!((SSP_SV_QMASK >> part) & 1)) {
+            // A/B builds only: this image's MMAs are left out (benchmarks/sv_ab.sh)
+          } else if (part < 2) {
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, br + (uint64_t)(k * ks_b), idesc, 1u);
+            for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32(d_tmem, aq_desc + (uint64_t)(k * ks_a), bd + (uint64_t)(k * ks_b), idesc, (part | k) ? 1u : 0u);
+          } else if (part == 4) {
+#pragma unroll 1
+            for (int k = 0; k < klsteps; ++k) mma_bf16_ss(d_tmem, al_desc + (uint64_t)(k * ks_a), bd + (uint64_t)(k * ks_b), idesc_bf, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, 1u);
+          }
+          if (part == NQ - 1) bar_commit(t_full + 8u * slot);
+          bar_commit(b_empty + 8u * stage);
         }
-        bar_commit(t_full + 8u * slot);
-        bar_commit(b_empty + 8u * stage_q);
-        if (with_r) bar_commit(b_empty + 8u * stage);
+        __syncwarp();
+        next_stage();
       }
-      __syncwarp();
-      if (with_r) next_stage();
       next_slot();
     };
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
       bar_spin_relaxed(a_full, unit_idx & 1u);
       tc_fence_after();
       if (kFirst)
-        for (int j = 0; j < NT; ++j) job_q(true);   // pre-pass: full logits of the reference model
+        for (int j = 0; j < NT; ++j) job_q();       // pre-pass: logits of the reference model
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
-          job_q(false);                           // common part of tile j
+          job_q();                                // common part of tile j
 #pragma unroll 1
           for (int m = 0; m < nm; ++m) job_r(m >= 2 ? 1u : 0u);
         }
@@ -439,6 +469,24 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         }
       }
       {
+        // ---- what TF32 rounding dropped, as BF16: [x^2 - tf32(x^2) | x - tf32(x) | 0..], (row r, column j) of block mb at
+        //      ((mb*KL/8 + j/8)*BM + r)*8 + j%8
+        const int64_t fr = frame0 + frow;
+        const bool live = fr < a.total_frames;
+        const float* xr = a.feats + fr * a.D;
+        __nv_bfloat16* dst = sAl + (size_t)(frow >> 7) * (BM * a.KL) + (size_t)(frow & (BM - 1)) * 8;
+        const int j0 = fpart * (a.KL >> 1), j1 = j0 + (a.KL >> 1);
+        for (int j = j0; j < j1; ++j) {
+          float v = 0.f;
+          if (live && j < 2 * a.D) {
+            const float x = xr[j < a.D ? j : j - a.D];
+            const float y = j < a.D ? x * x : x;
+            v = y - rna_tf32(y);
+          }
+          dst[(size_t)(j >> 3) * (BM * 8) + (j & 7)] = __float2bfloat16_rn(v);
+        }
+      }
+      {
         // ---- r operand [x, 1, 1, 0..] straight into TMEM: lane == row, column == contraction index
         const int64_t fe = frame0 + urow;
         const bool live = fe < a.total_frames;
@@ -483,6 +531,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         mx[half * UNIT + urow] = rmax;
         named_bar_sync(1 + g, 2 * BM);
         m_t = rintf(fmaxf(mx[urow], mx[UNIT + urow]));
+        named_bar_sync(1 + g, 2 * BM);
+        if (half == 0) { mx[urow] = 0.f; mx[UNIT + urow] = 0.f; }  // both are partial sums of this thread (models 0 and 1)
         if (half == 0 && a.stab && frame0 + urow < a.total_frames) a.stab[frame0 + urow] = m_t;
       } else {
         m_t = frame0 + urow < a.total_frames ? a.stab[frame0 + urow] : 0.f;
@@ -574,15 +624,16 @@ __global__ void __launch_bounds__(256) sv_fixup_kernel(const Args a, int64_t n_p
       const float* xr = a.feats + t * D;
       float mrun = -3.0e38f, srun = 0.f;
       for (int c = lane; c < a.n_tiles * BN; c += 32) {
-        const float* tq = a.tiles + ((size_t)(c / BN) * (S + 1)) * tile_floats;
-        const float* tr = tq + (size_t)(1 + m) * tile_floats;
+        const float* tq = a.tiles + ((size_t)(c / BN) * (S + NQ)) * tile_floats;   // [x^2] hi, lo; [x] reference hi, lo
+        const float* tr = tq + (size_t)(NQ + m) * tile_floats;                         // [x] model minus reference
         const int n = c % BN;
         auto at = [&](const float* tile, int j) { return tile[((size_t)(j >> 2) * BN + n) * 4 + (j & 3)]; };
-        float l = at(tq, D) + at(tq, D + 1) + at(tr, D) + at(tr, D + 1);
+        float l = at(tr, D) + at(tr, D + 1);
+        for (int i = 0; i < NQ; ++i) l += at(tq + i * tile_floats, D) + at(tq + i * tile_floats, D + 1);
         for (int j = 0; j < D; ++j) {
           const float x = xr[j];
-          l = fmaf(x, at(tr, j), l);
-          l = fmaf(x * x, at(tq, j), l);
+          l = fmaf(x, at(tr, j) + (at(tq + 2 * tile_floats, j) + at(tq + 3 * tile_floats, j)), l);
+          l = fmaf(x * x, at(tq, j) + at(tq + tile_floats, j), l);
         }
         const float mn = fmaxf(mrun, l);
         srun = srun * exp2f(mrun - mn) + exp2f(l - mn);
@@ -610,9 +661,7 @@ static int num_sms() {
 
 template <int kPoly, int kDeg, int KSTEPS>
 static int launch_one(const Args& a, unsigned grid, bool first, cudaStream_t st) {
-  constexpr size_t tile_bytes = (size_t)BN * KSTEPS * 8 * 4, aq_bytes = (size_t)UNIT * KSTEPS * 8 * 4;
-  constexpr size_t smem = aq_bytes + NSTAGE * tile_bytes + (size_t)2 * CHUNK * UNIT * sizeof(float) +
-                          (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 + 3 * UNIT * sizeof(float);
+  const size_t smem = sv_smem_bytes(KSTEPS * 8, a.KL);  // make_sv_layout has checked it against the 227 KB limit
   if (first) {
     SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, true><<<grid, THREADS, smem, st>>>(a);
@@ -662,8 +711,7 @@ int64_t score_sv_workspace_bytes(const SvLayout& L, int64_t total_frames) {
 }
 
 int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
-                    const SvLayout& L, int ref_model, bool normalize, double* scores, float* frame_lse, void* workspace,
-                    cudaStream_t st) {
+                    const SvLayout& L, bool normalize, double* scores, float* frame_lse, void* workspace, cudaStream_t st) {
   using namespace sv;
   SSP_CUDA_OK(cudaMemsetAsync(scores, 0, sizeof(double) * n_utts * L.n_models, st));
   if (total_frames == 0) return SSP_OK;
@@ -674,12 +722,12 @@ int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.n_utts = n_utts;
   a.total_frames = total_frames;
   a.tiles = (const float*)pack;
-  a.set_images = L.n_models + 1;
+  a.set_images = L.n_models + NQ;
   a.set_models = L.n_models;
   a.n_tiles = L.Kp / BN;
   a.D = L.D;
   a.KS = L.KS;
-  a.ref_model = ref_model;
+  a.KL = sv_residual_len(L.D);
   a.normalize = normalize ? 1 : 0;
   a.stab = group < L.n_models ? (float*)workspace : nullptr;
   const int64_t n_units = (total_frames + UNIT - 1) / UNIT;

@@ -175,8 +175,11 @@ class SharedModelSet:
     """``n_models`` diagonal GMMs that share ONE weight vector and ONE variance matrix and differ in their means --
     what mean-only MAP enrolment from a UBM yields (:func:`~speech_signal_processing_b200.ubm.map_adapt` with
     ``adapt=("means",)``).  Scored by the shared-variance tensor kernel (``ssp_gmm_score_shared``): the part of the
-    log-likelihood common to all models is evaluated once per frame block, the per-model contraction is D + 2 long
-    instead of 2D + 2.  Results equal :class:`ModelSet` ``.score(precision="tf32")`` on the expanded set."""
+    log-likelihood common to all models -- the logit of the reference member ``ref_model`` (the UBM), with the model
+    operand split in two TF32 pieces -- is evaluated once per frame block; the per-model contraction is D + 2 long
+    instead of 2D + 2 and acts on ``means[s] - means[ref_model]``, so TF32 rounding scales with the distance from the
+    reference and cancels in log-likelihood ratios against it.  Results equal :class:`ModelSet`
+    ``.score(precision="tf32")`` on the expanded set to TF32 rounding or better."""
 
     def __init__(self, weights, variances, means, ref_model=-1, device=None):
         torch = _lib.require_cuda()
@@ -198,11 +201,12 @@ class SharedModelSet:
         self.dims = _lib.GmmDims(self.n_models, self.n_comp, self.n_feat)
         nbytes = int(self.lib.ssp_gmm_shared_pack_bytes(C.byref(self.dims)))
         if nbytes <= 0:
-            raise ValueError(f"unsupported dims K={self.n_comp} D={self.n_feat} for the shared-variance kernel (need D <= 62)")
+            raise ValueError(f"unsupported dims K={self.n_comp} D={self.n_feat} for the shared-variance kernel (need D <= 40)")
         self.pack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ssp_gmm_pack_shared(_lib.ptr(w), _lib.ptr(var), _lib.ptr(mu), C.byref(self.dims),
-                                                    _lib.ptr(self.pack), _lib.stream_ptr()), "ssp_gmm_pack_shared")
+                                                    self.ref_model, _lib.ptr(self.pack), _lib.stream_ptr()),
+                       "ssp_gmm_pack_shared")
         self._params = (w, var, mu)
         self._ws = None
 
@@ -233,7 +237,7 @@ class SharedModelSet:
         if ws_bytes and (self._ws is None or self._ws.numel() < ws_bytes):
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         rc = self.lib.ssp_gmm_score_shared(_lib.ptr(feats), _lib.ptr(d_off), n_utts, total, _lib.ptr(self.pack),
-                                           C.byref(self.dims), self.ref_model, _lib.ptr(scores), _lib.ptr(lse),
+                                           C.byref(self.dims), _lib.ptr(scores), _lib.ptr(lse),
                                            _lib.ptr(self._ws) if ws_bytes else None, ws_bytes, _lib.stream_ptr())
         _lib.check(rc, "ssp_gmm_score_shared")
         self._keep = d_off

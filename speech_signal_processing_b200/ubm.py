@@ -110,7 +110,7 @@ def identify(utts, speakers, ubm=None, precision="auto", device=None):
             base = _base_params(ubm) if ubm is not None else None
             # mean-only MAP speakers (e.g. unpickled models adapted from this UBM): shared-variance kernel, with the UBM
             # as one more mean set -- only when the UBM (if any) is KNOWN to carry the same weights and variances
-            if (single_pass and smu.shape[2] <= 62 and SharedModelSet.shares_base(sw, svar)
+            if (single_pass and smu.shape[2] <= 40 and SharedModelSet.shares_base(sw, svar)
                     and (ubm is None or (base is not None and np.array_equal(base[0], sw[0]) and np.array_equal(base[1], svar[0])))):
                 if ubm is None:
                     means = smu

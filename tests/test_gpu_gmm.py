@@ -313,9 +313,11 @@ def test_full_size_identify_properties():
     sms = ssp.SharedModelSet(w, t_var, torch.cat([t_mu, torch.as_tensor(mu, device=dev)[None]]), ref_model=s)
     sv, _ = sms.score(feats, offs)
     assert bool(torch.isfinite(sv).all())
-    assert float(((sv - scores).abs() / scores.abs()).max()) < 2e-5
+    assert float(((sv - scores).abs() / scores.abs()).max()) < 1e-4      # the general kernel's single TF32 pass
     assert bool(((sv[:, :s] - sv[:, s:]).argmax(dim=1) == truth).all())
-    assert float(((sv[sub] - s32).abs() / s32.abs()).max()) < 1e-4
+    assert float(((sv[sub] - s32).abs() / s32.abs()).max()) < 3e-5        # common part FP32-grade, differences in TF32
+    llr32 = s32[:, :s] - s32[:, s:]
+    assert float(((sv[sub][:, :s] - sv[sub][:, s:]) - llr32).abs().max()) < LLR_ATOL
 
 
 # ------------------------------------------------------------------------------------------------
@@ -401,12 +403,12 @@ def test_map_enrol_identify_equals_general_path():
     aw, amu, avar = ssp.map_adapt(ubm, enrol, relevance=16.0)
     pred, who = ssp.identify(tests, ssp.ModelSet(aw, amu, avar), ubm, precision="fp32")
     assert pred_sv.shape == pred.shape == (len(tests), n_spk)
-    # single-pass TF32 at this small K: 1e-4 relative on |score| ~ 55 per term of the difference
-    np.testing.assert_allclose(pred_sv, pred, rtol=0, atol=1.2e-2)
+    # the shared-variance kernel rounds only the speakers' DIFFERENCES from the UBM: LLRs within the survey's 1e-3
+    np.testing.assert_allclose(pred_sv, pred, rtol=0, atol=LLR_ATOL)
     assert (who_sv == who).all() and (who == np.arange(len(tests)) % n_spk).all()
-    # against the general TENSOR kernel the model-side rounding is identical: the two agree far more closely
+    # the general tensor kernel in one TF32 pass rounds the full means of every model: 1e-4 relative on |score| ~ 55
     pred_tc, who_tc = ssp.identify(tests, ssp.ModelSet(aw, amu, avar), ubm, precision="tf32")
-    np.testing.assert_allclose(pred_sv, pred_tc, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(pred_tc, pred, rtol=0, atol=1.2e-2)
     assert (who_sv == who_tc).all()
 
 
