@@ -60,33 +60,37 @@ struct PackLayout {
 };
 
 // Shared-variance model sets (gmm_score_sv.cu): every model has the base model's weights and variances and its own
-// means.  One buffer of tcgen05 shared-memory images, [Kp/64 tiles][kSvBaseImages + n_models][KS/4][64] float4, all
-// scaled by log2(e); "hi" / "lo" are the two TF32 pieces of a value (hi + lo exact to ~2^-22):
-//   images 0, 1  = common part, hi / lo     [-1/(2 var), cq pieces, 0..],  cq = log w - D/2 log 2pi - 1/2 sum log var
-//   images 2, 3  = reference model, hi / lo [mu_ref/var, ck pieces, 0..],  ck = -1/2 sum mu_ref^2 / var
-//   image 4      = BF16 image [KL/8][64][8] of [-1/(2 var) | mu_ref/var | 0..], KL = roundup(2D, 16): multiplies the
-//                  frames' TF32 rounding residuals [x^2 - tf32(x^2) | x - tf32(x)]
-//   image 5 + s  = model s MINUS the reference  [(mu_s - mu_ref)/var, (ck_s - ck_ref) hi, lo, 0..]
+// means.  One buffer of tcgen05 shared-memory images (K-major, no swizzle), [Kp/64 tiles][kSvBaseImages + n_models]
+// [KS/8][64][8] FP16, all scaled by log2(e), + a 128-byte tail (overflow flag of the pack kernel).  The common part is
+// the full logit of the REFERENCE member, contraction [x^2 | x | 1, 1] of length KQ, as two FP16 pieces (hi + lo exact
+// to ~2^-22) cut into ring-slot-sized column ranges:
+//   images 0, 1  = hi piece, columns [0, KS) and [KS, KQ) of [-1/(2 var) | mu_ref/var | c1, c2 | 0..]
+//   images 2, 3  = lo piece, same columns ................ of [residuals ..................| c3, 0 | 0..]
+//                  c = log w - D/2 log 2pi - 1/2 sum log var - 1/2 sum mu_ref^2 / var as three pieces
+//   image 4 + s  = model s MINUS the reference  [(mu_s - mu_ref)/var, ca, cb, 0..] against [x, 1, 1024]:
+//                  ca + 1024 cb = ck_s - ck_ref,  ck = -1/2 sum mu^2/var
 constexpr int kSvTileN = 64;
 constexpr int kSvMaxKS = 64;
-constexpr int kSvBaseImages = 5;
+constexpr int kSvBaseImages = 4;
+constexpr float kSvConstScale = 1024.f;  // second "one" column of the per-model frame operand (range of the model constants)
 // shape of gmm_score_sv_kernel (here because it bounds the feature width the layout accepts)
 #ifndef SSP_SV_STAGES
-#define SSP_SV_STAGES 6
+#define SSP_SV_STAGES 12
 #endif
 constexpr int kSvStages = SSP_SV_STAGES, kSvSlots = 6, kSvChunk = 32, kSvUnit = 256;
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
-constexpr int kSvMaxFeat = 40;          // widest feature vector whose operands fit (sv_smem_bytes)
+constexpr int kSvMaxFeat = 39;          // widest feature vector whose operands fit (sv_smem_bytes)
 struct SvLayout {
   int n_models, K, D;
   int Kp;  // K rounded up to kSvTileN
-  int KS;  // contraction length: roundup(D + 2, 8)
+  int KS;  // contraction length of the per-model part: roundup(D + 2, 16)
+  int KQ;  // contraction length of the common part: roundup(2 D + 2, 16) <= 2 KS
+  size_t flag_offset;  // int32 at the tail: set by the pack kernel when a value leaves FP16's range
   size_t bytes;
 };
-inline int sv_residual_len(int D) { return (2 * D + 15) / 16 * 16; }
-inline size_t sv_smem_bytes(int KS, int KL) {
-  return (size_t)kSvUnit * KS * 4 + (size_t)kSvUnit * KL * 2 + (size_t)kSvStages * kSvTileN * KS * 4 +
-         (size_t)2 * kSvChunk * kSvUnit * 4 + (2 * kSvStages + 2 * kSvSlots + 2) * 8 + 16 + kSvUnit * 4;
+inline size_t sv_smem_bytes(int KS, int KQ) {
+  return (size_t)2 * kSvUnit * KQ * 2 + (size_t)kSvStages * kSvTileN * KS * 2 + (size_t)2 * kSvChunk * kSvUnit * 4 +
+         (2 * kSvStages + 2 * kSvSlots + 2) * 8 + 16 + kSvUnit * 4;
 }
 inline bool make_sv_layout(const ssp_gmm_dims* dims, SvLayout* L) {
   if (!dims || dims->n_models < 1 || dims->n_comp < 1 || dims->n_feat < 1) return false;
@@ -94,9 +98,11 @@ inline bool make_sv_layout(const ssp_gmm_dims* dims, SvLayout* L) {
   L->K = dims->n_comp;
   L->D = dims->n_feat;
   L->Kp = (L->K + kSvTileN - 1) / kSvTileN * kSvTileN;
-  L->KS = (L->D + 2 + 7) / 8 * 8;
-  if (L->KS > kSvMaxKS || sv_smem_bytes(L->KS, sv_residual_len(L->D)) > kMaxDynSmem) return false;  // D <= kSvMaxFeat
-  L->bytes = (size_t)(L->Kp / kSvTileN) * (size_t)(L->n_models + kSvBaseImages) * kSvTileN * L->KS * sizeof(float);
+  L->KS = (L->D + 2 + 15) / 16 * 16;
+  L->KQ = (2 * L->D + 2 + 15) / 16 * 16;
+  if (L->KS > kSvMaxKS || sv_smem_bytes(L->KS, L->KQ) > kMaxDynSmem) return false;  // D <= kSvMaxFeat
+  L->flag_offset = (size_t)(L->Kp / kSvTileN) * (size_t)(L->n_models + kSvBaseImages) * kSvTileN * L->KS * 2;
+  L->bytes = L->flag_offset + 128;
   return true;
 }
 

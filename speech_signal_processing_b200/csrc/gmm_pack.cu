@@ -1,6 +1,7 @@
 // Model packing, M-step and MAP adaptation: small double-precision kernels that keep the whole
 // EM / enrolment loop resident in HBM (no host round trip of parameters between iterations).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -113,91 +114,94 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
   return SSP_OK;
 }
 
-// Shared-variance pack (SvLayout): one thread per (image, padded component).  Images 0..3 are the part common to all
-// models INCLUDING the reference model's means, as hi + lo TF32 pieces (split-B: model-side rounding of the common part
-// drops to ~2^-22); image kSvBaseImages + s holds model s as its DIFFERENCE from the reference, so TF32 rounding acts
-// on (mu_s - mu_ref) / var -- an order of magnitude smaller than mu_s / var for MAP-adapted speakers -- and the
-// reference model's own image is exactly zero: a log-likelihood RATIO against it carries the rounding of the
-// differences only.
+// Shared-variance pack (SvLayout, common.cuh): one thread per (image, padded component), FP16 images.  The common part
+// (images 0..3) is the full logit of the reference member as hi + lo FP16 pieces; image kSvBaseImages + s holds model s
+// as its DIFFERENCE from the reference, so rounding acts on (mu_s - mu_ref) / var -- an order of magnitude smaller than
+// mu_s / var for MAP-adapted speakers -- and the reference model's own image is exactly zero.
 __global__ void gmm_pack_sv_kernel(const double* __restrict__ w, const double* __restrict__ var, const double* __restrict__ mu,
-                                   int S, int K, int Kp, int D, int KS, int ref, float* __restrict__ tiles) {
+                                   int S, int K, int Kp, int D, int KS, int KQ, int ref, __half* __restrict__ tiles,
+                                   int* __restrict__ overflow) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_images = S + kSvBaseImages;
   if (idx >= (int64_t)n_images * Kp) return;
   const int image = (int)(idx / Kp), c = (int)(idx % Kp);
   const int n = c % kSvTileN;
-  float* tile = tiles + ((int64_t)(c / kSvTileN) * n_images + image) * (int64_t)kSvTileN * KS;
-  auto tile_at = [&](int j) -> float& { return tile[((j >> 2) * kSvTileN + n) * 4 + (j & 3)]; };
+  __half* tile = tiles + ((int64_t)(c / kSvTileN) * n_images + image) * (int64_t)kSvTileN * KS;
+  auto tile_at = [&](int j) -> __half& { return tile[((j >> 3) * kSvTileN + n) * 8 + (j & 7)]; };
+  for (int j = 0; j < KS; ++j) tile_at(j) = __float2half_rn(0.f);
   const double LOG2E = 1.4426950408889634074;
-  const double* var_r = var + (int64_t)c * D;
-  const double* ref_r = mu + ((int64_t)ref * K + c) * D;
-  if (image == 4) {  // BF16 [KL/8][64][8] in the same slot (KL <= 2 KS): what the frames' rounding residuals multiply
-    __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(tile);
-    for (int j = 0; j < 2 * KS; ++j) {
-      double v = 0.0;
-      if (c < K && j < 2 * D) v = (j < D ? -0.5 : ref_r[j - D]) / var_r[j < D ? j : j - D] * LOG2E;
-      tb[((j >> 3) * kSvTileN + n) * 8 + (j & 7)] = __float2bfloat16_rn((float)v);
-    }
-    return;
-  }
-  for (int j = 0; j < KS; ++j) tile_at(j) = 0.f;
-  if (c >= K) {
-    if (image == 0) tile_at(D) = to_tf32(-1e30f);  // padded components never contribute
-    return;
-  }
-  const bool lo_image = image == 1 || image == 3;
-  auto hi_of = [](double v) { return to_tf32((float)v); };
-  auto piece = [&](double v) {  // the hi or the lo TF32 piece of v, by image
-    const float h = hi_of(v);
-    return lo_image ? to_tf32((float)(v - (double)h)) : h;
+  const double kFloor = -60000.0;  // FP16-exact; 2^-60000 == 0: padded or zero-weight components never contribute
+  bool bad = false;
+  auto put = [&](int j, double v, int piece) {  // piece 0, 1, 2 of v as FP16 values (v ~ p0 + p1 + p2)
+    const __half p0 = __float2half_rn((float)v);
+    const double r1 = v - (double)__half2float(p0);
+    const __half p1 = __float2half_rn((float)r1);
+    const __half pc = piece == 0 ? p0 : piece == 1 ? p1 : __float2half_rn((float)(r1 - (double)__half2float(p1)));
+    if (!(fabs((double)__half2float(p0)) <= 65504.0)) bad = true;
+    tile_at(j) = pc;
   };
-  double cc;
-  if (image < 2) {          // [x^2, 1, 1] . log2(e) [-1/(2 var), cq ...],  cq = log w - D/2 log 2pi - 1/2 sum log var
-    double logdet = 0.0;
+  if (image < kSvBaseImages) {
+    // column range [j0, j1) of the common contraction [x^2 (D) | x (D) | 1, 1 | 0..] and which piece
+    const int j0 = (image & 1) ? KS : 0, j1 = (image & 1) ? KQ : KS, lo = image >> 1;
+    if (c >= K) {
+      if (!lo && 2 * D >= j0 && 2 * D < j1) tile_at(2 * D - j0) = __float2half_rn((float)kFloor);
+      return;
+    }
+    const double* var_r = var + (int64_t)c * D;
+    const double* ref_r = mu + ((int64_t)ref * K + c) * D;
+    double logdet = 0.0, quad = 0.0;
     for (int d = 0; d < D; ++d) {
       const double p = 1.0 / var_r[d];
       logdet += log(p);
-      tile_at(d) = piece(-0.5 * p * LOG2E);
-    }
-    cc = log(w[c]) - 0.5 * D * 1.8378770664093454836 + 0.5 * logdet;
-    if (!(cc > -1e30)) cc = -1e30;  // w == 0
-  } else if (image < kSvBaseImages) {  // [x, 1, 1] . log2(e) [mu_ref / var, ck ...],  ck = -1/2 sum mu_ref^2 / var
-    double quad = 0.0;
-    for (int d = 0; d < D; ++d) {
-      const double p = 1.0 / var_r[d];
       quad += ref_r[d] * ref_r[d] * p;
-      tile_at(d) = piece(ref_r[d] * p * LOG2E);
+      if (d >= j0 && d < j1) put(d - j0, -0.5 * p * LOG2E, lo);
+      if (D + d >= j0 && D + d < j1) put(D + d - j0, ref_r[d] * p * LOG2E, lo);
     }
-    cc = -0.5 * quad;
-  } else {                   // [x, 1, 1] . log2(e) [(mu_s - mu_ref) / var, ck_s - ck_ref ...]
+    // log w - D/2 log 2pi - 1/2 sum log var - 1/2 sum mu_ref^2 / var, as three FP16 pieces against the two columns of 1.0
+    double cc = (log(w[c]) - 0.5 * D * 1.8378770664093454836 + 0.5 * logdet - 0.5 * quad) * LOG2E;
+    if (!(cc > kFloor)) cc = kFloor;  // w == 0
+    if (2 * D >= j0 && 2 * D < j1) put(2 * D - j0, cc, lo ? 2 : 0);
+    if (!lo && 2 * D + 1 >= j0 && 2 * D + 1 < j1) put(2 * D + 1 - j0, cc, 1);
+  } else if (c < K) {  // [x, 1, 1] . log2(e) [(mu_s - mu_ref) / var, ck_s - ck_ref as two pieces]
+    const double* var_r = var + (int64_t)c * D;
+    const double* ref_r = mu + ((int64_t)ref * K + c) * D;
     const double* mu_r = mu + ((int64_t)(image - kSvBaseImages) * K + c) * D;
     double dquad = 0.0;
     for (int d = 0; d < D; ++d) {
       const double p = 1.0 / var_r[d], dm = mu_r[d] - ref_r[d];
       dquad += dm * (mu_r[d] + ref_r[d]) * p;
-      tile_at(d) = hi_of(dm * p * LOG2E);
+      put(d, dm * p * LOG2E, 0);
     }
-    cc = -0.5 * dquad;
+    // the constant against the frame operand's columns [1, 1024]: cb * 1024 + ca, so that a model far from the
+    // reference (|constant| up to 6.7e7; its scores go through sv_fixup_kernel) stays inside FP16's range
+    const double cd = -0.5 * dquad * LOG2E;
+    const __half cb = __float2half_rn((float)(cd / kSvConstScale));
+    const __half ca = __float2half_rn((float)(cd - kSvConstScale * (double)__half2float(cb)));
+    if (!(fabs((double)__half2float(cb)) <= 65504.0)) bad = true;
+    tile_at(D) = ca;
+    tile_at(D + 1) = cb;
   }
-  // the constant as exactly representable TF32 pieces against the frame operand's two columns of 1.0: two in a hi (or
-  // difference) image, the third in the lo image
-  const double c2 = cc * LOG2E;
-  const float hi = hi_of(c2), lo = to_tf32((float)(c2 - (double)hi));
-  if (lo_image) {
-    tile_at(D) = to_tf32((float)(c2 - (double)hi - (double)lo));
-  } else {
-    tile_at(D) = hi;
-    tile_at(D + 1) = lo;
-  }
+  if (bad) *overflow = 1;
 }
 
 int launch_pack_sv(const double* w, const double* var, const double* mu, const SvLayout& L, int ref_model, void* pack,
                    cudaStream_t st) {
   const int64_t n = (int64_t)(L.n_models + kSvBaseImages) * L.Kp;
   const int threads = 128;
+  int* flag = (int*)((char*)pack + L.flag_offset);
+  SSP_CUDA_OK(cudaMemsetAsync(flag, 0, 128, st));
   gmm_pack_sv_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(w, var, mu, L.n_models, L.K, L.Kp, L.D, L.KS,
-                                                                              ref_model, (float*)pack);
+                                                                              L.KQ, ref_model, (__half*)pack, flag);
   SSP_LAUNCH_CHECK("gmm_pack_sv_kernel");
+  // packing is rare (once per model set): one read-back tells the caller that the set does not fit FP16
+  int h_flag = 0;
+  SSP_CUDA_OK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SSP_CUDA_OK(cudaStreamSynchronize(st));
+  if (h_flag) {
+    set_error("ssp_gmm_pack_shared: a model parameter leaves the FP16 range of the shared-variance kernel (|value| > 65504: "
+              "means / variances far from normalised features); score the set with ssp_gmm_score instead");
+    return SSP_EUNSUP;
+  }
   return SSP_OK;
 }
 

@@ -3,40 +3,43 @@
 // Mean-only relevance-MAP enrolment (Reynolds 2000; the north-star's "MAP adaptation + scoring" workload) gives
 // every speaker the UBM's weights and variances and its own means.  The diagonal-Gaussian log-likelihood
 // (sklearn _gaussian_mixture.py:536-553) then splits into a part that is common to all speakers and a part that is
-// linear in the frame:
+// linear in the frame (log2 domain):
 //
 //     L2[t, s, c] = q[t, c] + r[t, s, c]
-//     q[t, c]     = [x_t^2, 1, 1] . [-1/(2 var_c), cq..] * log2(e)              cq = log w_c - D/2 log 2pi - 1/2 sum log var_c
-//                 + [x_t,   1, 1] . [mu_ref,c/var_c, ck..] * log2(e)            ck = -1/2 sum mu_ref,c^2 / var_c
-//     r[t, s, c]  = [x_t,   1, 1] . [(mu_sc - mu_ref,c)/var_c, dck_hi, dck_lo] * log2(e)
+//     q[t, c]     = [x_t^2, x_t, 1, 1] . [-1/(2 var_c), mu_ref,c/var_c, c..] * log2(e)     the full logit of a REFERENCE member
+//     r[t, s, c]  = [x_t, 1, 1024] . [(mu_sc - mu_ref,c)/var_c, ca, cb] * log2(e)           speaker s MINUS the reference
 //
-// so the per-speaker contraction has K = D + 2 (48 after padding at D = 39) instead of 2D + 2 (80): 40 % fewer
-// tensor-core cycles, and the common part is computed once per (256 frames, 64 components) and kept in registers.
-// q is the full logit of a REFERENCE model of the set (the UBM), evaluated to FP32 grade in the 3xTF32 manner: the
-// model operand as hi + lo TF32 pieces (four images per tile) and the frames' own rounding residuals
-// [x^2 - tf32(x^2), x - tf32(x)] as a BF16 operand against a BF16 image of the model (kind::f16 into the same FP32
-// accumulator).  A speaker enters only through its DIFFERENCE from the reference, so the TF32 rounding of the
-// per-speaker part scales with |mu_s - mu_ref| (gmm_pack.cu: gmm_pack_sv_kernel).  The common part is 1/32 of the
-// tensor work, so the extra passes cost ~1 %.
+// so the per-speaker contraction is D + 2 long (41 -> 48 at D = 39) instead of 2D + 2 (80), and the common part is
+// computed once per (256 frames, 64 components, 32 models) and kept in registers.
+//
+// Operands are FP16 (kind::f16, FP32 accumulation): an FP16 significand has the 11 bits of TF32, one MMA covers K = 16
+// instead of 8 -- half the tcgen05.mma instructions (an M128 x N64 instruction costs ~49 cycles whatever its kind,
+// benchmarks/ubench_mma.cu), half the bytes per model image.  Cepstra after CMVN and (mu_s - mu_ref)/var are far inside
+// FP16's range; a frame outside it turns its scores into NaN, which sv_fixup_kernel re-scores in FP32, and
+// ssp_gmm_pack_shared refuses models outside it.
+//   * r rounds only the DIFFERENCE of a speaker from the reference: its error scales with |mu_s - mu_ref|, and the
+//     reference model's own r is exactly zero;
+//   * q is evaluated to FP32 grade in the 3-pass manner, A_hi.B_hi + A_lo.B_hi + A_hi.B_lo with FP16 pieces of the
+//     frame operand (built per unit in shared memory) and of the model operand (two images), 15 MMAs per 32 models.
 //
 //   one persistent CTA per SM, unit = 256 frames (two 128-row blocks), component tile = 64
 //   loop order per unit:  chunk of 32 models (outer)  x  component tile j  x  model in the chunk (inner)
-//   warp 0      : producer   - cp.async.bulk of the 12 KB tile images through an 8-stage ring
-//   warps 1, 2  : MMA issuers, one per row block - r-tiles: tcgen05.mma kind::tf32 with the FRAME operand in TMEM
+//   warp 0      : producer   - cp.async.bulk of the 6 KB tile images through a 12-stage ring
+//   warps 1, 2  : MMA issuers, one per row block - r-tiles: tcgen05.mma kind::f16 with the FRAME operand in TMEM
 //                 (written once per unit by tcgen05.st, thread == row) and the model tile in shared memory -> no
 //                 shared-memory traffic for the frames at all; q-tiles: both operands in shared memory.
-//                 M128 x N64 x K8, 6 accumulator slots (3 per row block) so the tensor core runs ahead of the epilogue
-//   (warps 0..3 shrink to 32 registers, the epilogue warps grow to 120: setmaxnreg)
+//                 M128 x N64 x K16, 6 accumulator slots (3 per row block) so the tensor core runs ahead of the epilogue
+//   (warps 0..3 shrink to 32 registers, the epilogue warps grow to 112: setmaxnreg)
 //   warps 4..19 : epilogue   - thread == (frame row, 32 of the tile's 64 columns); keeps q[t, its 32 columns] - m_t in
-//                 registers across the models of a chunk, per tile: tcgen05.ld, release the slot, d = r + (q - m_t),
-//                 sum 2^d (MUFU ex2 + an FMA-pipe polynomial share), added to the (model, frame) partial sum in
-//                 shared memory
-//   per-frame stabiliser m_t = round(max_c logit of a reference model), found in a short pre-pass, fixed for the whole
+//                 registers across the models of a chunk, per tile: tcgen05.ld, leave q - m_t in the slot for the job
+//                 three ahead, sum 2^d (MUFU ex2 + an FMA-pipe polynomial share), added to the (model, frame) partial
+//                 sum in shared memory
+//   per-frame stabiliser m_t = round(max_c logit of the reference model), found in a short pre-pass, fixed for the whole
 //   unit, so partial sums of different component tiles simply add.  After a chunk's last tile the partial sums become
 //   per-frame log-likelihoods, are summed per utterance inside the warp and added to the (utterance, model) scores.
 //   A sum outside [2^-100, 2^100] (a model nowhere near the reference) turns the score into NaN and
 //   sv_fixup_kernel re-scores that (utterance, model) pair with a plain FP32 online log-sum-exp.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -58,15 +61,17 @@ constexpr int EPI = EPI_WARPS * 32;
 constexpr int CTRL = 128;                // warpgroup 0: producer, two MMA issuers, one idle warp (setmaxnreg is per warpgroup)
 constexpr int THREADS = CTRL + EPI;
 constexpr int CTRL_REGS = 32, EPI_REGS = 112;  // launched at 96: 128 x (96 - 32) registers released == 512 x (112 - 96) acquired
-constexpr int NQ = kSvBaseImages;          // images of the common part: [x^2] hi, lo (both operands in shared memory), [x] reference hi, lo (frames in
-                                         // TMEM), BF16 [x^2 | x] against the frames' rounding residuals
+constexpr int NQ = kSvBaseImages;          // ring slots of the common part: B_hi columns [0, KS) and [KS, KQ), B_lo likewise
 constexpr int CHUNK = kSvChunk;                // models per chunk: partial sums [2 column halves][CHUNK][UNIT] fp32 = 64 KB
 constexpr uint32_t ACC_COL0 = 128;       // TMEM: [0, 2 KS) frame operand of the two row blocks, [128, 512) accumulators
+#ifndef SSP_SV_RELAX_NS
+#define SSP_SV_RELAX_NS 1000  // suspend-time hint of the control warps' mbarrier waits
+#endif
 #ifndef SSP_SV_RSTEPS
 #define SSP_SV_RSTEPS 0  // A/B builds only: K steps issued per model job (0 = all; fewer gives wrong results, for timing)
 #endif
 #ifndef SSP_SV_QMASK
-#define SSP_SV_QMASK 0x1f  // which of the NQ images of the common part are multiplied (all; cleared bits are A/B builds)
+#define SSP_SV_QMASK 0xf  // which of the NQ images of the common part are multiplied (all; cleared bits are A/B builds)
 #endif
 constexpr int kDefaultPolyPairs = 4;  // measured on B200 (2000 utts x 1001 models): 0/4/6/8 pairs -> 163/136/142/155 ms
 constexpr int kDefaultPolyDeg = 4;
@@ -75,14 +80,14 @@ struct Args {
   const float* feats;
   const int64_t* offsets;
   int64_t n_utts, total_frames;
-  const float* tiles;  // [n_tiles][NQ + S][KS/4][BN] float4 images of the WHOLE set (S models); images 0..NQ-1 of a tile are the common q part
+  const __half* tiles;  // [n_tiles][NQ + S][KS/8][BN][8] FP16 images of the WHOLE set (S models); images 0..NQ-1 of a tile are the common q part
   // One launch scores the models [model0, model0 + n_models) of the set -- an L2-resident group (see launch_score_sv):
-  const float* tiles_group;  // == tiles + model0 images: image NQ + m of a tile is model model0 + m
+  const __half* tiles_group;  // == tiles + model0 images: image NQ + m of a tile is model model0 + m
   int n_models;              // models of this launch
   int set_images;            // NQ + S: images per tile
   int set_models;            // S: row stride of the score matrix
   int n_tiles, D, KS, normalize;
-  int KL;              // contraction length of the residual pass: roundup(2 D, 16)
+  int KQ;              // contraction length of the common part: roundup(2 D + 2, 16) <= 2 KS
   float* stab;         // [total_frames] per-frame exponent stabiliser: written by the first launch (kFirst), read by the others
   double* scores;      // + model0
   float* frame_lse;    // + model0 * total_frames
@@ -145,7 +150,7 @@ __device__ __forceinline__ void bar_spin_relaxed(uint32_t bar, uint32_t parity) 
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000u)
+        : "r"(bar), "r"(parity), "r"((uint32_t)SSP_SV_RELAX_NS)
         : "memory");
     if (ok) return;
 #if SSP_SV_CLOCK_WATCHDOG
@@ -170,12 +175,11 @@ __device__ __forceinline__ void bulk_g2s_u32(uint32_t smem_dst, const void* gmem
                : "memory");
 }
 
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       :
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -254,13 +258,12 @@ __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float 
 template <int kPoly, int kDeg, int KSTEPS, bool kFirst>
 __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int KS = KSTEPS * 8;
-  constexpr uint32_t tile_bytes = (uint32_t)BN * KS * 4u;       // one model tile image
-  constexpr uint32_t aq_block_bytes = (uint32_t)BM * KS * 4u;   // q operand of one row block
-  float* sAq = reinterpret_cast<float*>(smem);                                  // [MB][KS/4][BM][4]
-  __nv_bfloat16* sAl = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)MB * aq_block_bytes);  // [MB][KL/8][BM][8] residuals
-  const uint32_t al_block_bytes = (uint32_t)a.KL * BM * 2u;
-  unsigned char* sB = smem + (size_t)MB * aq_block_bytes + (size_t)MB * al_block_bytes;  // [NSTAGE][KS/4][BN][4]
+  constexpr int KS = KSTEPS * 16;
+  constexpr uint32_t tile_bytes = (uint32_t)BN * KS * 2u;       // one model tile image (one ring stage)
+  const uint32_t aq_block_bytes = (uint32_t)a.KQ * BM * 2u;     // q operand of one row block
+  __half* sAh = reinterpret_cast<__half*>(smem);                                  // [MB][KQ/8][BM][8]  fp16([x^2, x, 1, 1, 0..])
+  __half* sAl = reinterpret_cast<__half*>(smem + (size_t)MB * aq_block_bytes);    // same shape: what that rounding dropped
+  unsigned char* sB = smem + (size_t)2 * MB * aq_block_bytes;                     // [NSTAGE][KS/8][BN][8]
   float* sPart = reinterpret_cast<float*>(sB + (size_t)NSTAGE * tile_bytes);    // [2][CHUNK][UNIT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * CHUNK * UNIT);
   const uint32_t b_full = smem_u32(bars);  // barrier i of a group at +8 i
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
 
   const int64_t n_units = (a.total_frames + UNIT - 1) / UNIT;
   const int S = a.n_models, NT = a.n_tiles;
-  constexpr size_t tile_floats = (size_t)BN * KS;
+  constexpr size_t tile_halfs = (size_t)BN * KS;
 
   if (warp < CTRL / 32) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     // ===================== producer =====================
     const uint32_t sB_u32 = smem_u32(sB);
     uint32_t stage = 0, ph = 0;
-    auto load = [&](const float* src) {
+    auto load = [&](const __half* src) {
       bar_spin_relaxed(b_empty + 8u * stage, ph ^ 1u);
       if (elect_one()) {
         bar_arrive_expect_tx(b_full + 8u * stage, tile_bytes);
@@ -313,20 +316,20 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       __syncwarp();
       if (++stage == NSTAGE) { stage = 0; ph ^= 1u; }
     };
-    const size_t tile_stride = (size_t)a.set_images * tile_floats;
+    const size_t tile_stride = (size_t)a.set_images * tile_halfs;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
       if (kFirst)
         for (int j = 0; j < NT; ++j) {
-          const float* tj = a.tiles + (size_t)j * tile_stride;
-          for (int i = 0; i < NQ; ++i, tj += tile_floats) load(tj);
+          const __half* tj = a.tiles + (size_t)j * tile_stride;
+          for (int i = 0; i < NQ; ++i, tj += tile_halfs) load(tj);
         }
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
-          const float* tj = a.tiles + (size_t)j * tile_stride;
-          for (int i = 0; i < NQ; ++i, tj += tile_floats) load(tj);
-          const float* src = a.tiles_group + (size_t)j * tile_stride + (size_t)(NQ + m0) * tile_floats;
-          for (int m = 0; m < nm; ++m, src += tile_floats) load(src);
+          const __half* tj = a.tiles + (size_t)j * tile_stride;
+          for (int i = 0; i < NQ; ++i, tj += tile_halfs) load(tj);
+          const __half* src = a.tiles_group + (size_t)j * tile_stride + (size_t)(NQ + m0) * tile_halfs;
+          for (int m = 0; m < nm; ++m, src += tile_halfs) load(src);
         }
       }
     }
@@ -334,15 +337,14 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
     // ===================== MMA issuers: warp 1 owns row block 0, warp 2 row block 1 =====================
     const int g = warp - 1;
     constexpr uint32_t lbo_a = BM * 16u, lbo_b = BN * 16u, sbo = 128u;
-    constexpr uint32_t ks_a = (2u * lbo_a) >> 4, ks_b = (2u * lbo_b) >> 4;  // one K = 8 step in descriptor units
+    constexpr uint32_t ks_a = (2u * lbo_a) >> 4, ks_b = (2u * lbo_b) >> 4;  // one K = 16 step (two 16-byte chunks) in descriptor units
     constexpr uint32_t tile_units = tile_bytes >> 4;
-    const uint64_t aq_desc = make_desc(smem_u32(sAq) + (uint32_t)g * aq_block_bytes, lbo_a, sbo);
-    const uint64_t al_desc = make_desc(smem_u32(sAl) + (uint32_t)g * al_block_bytes, lbo_a, sbo);  // 16-byte chunks of 8 BF16: same strides
+    const uint64_t ah_desc = make_desc(smem_u32(sAh) + (uint32_t)g * aq_block_bytes, lbo_a, sbo);
+    const uint64_t al_desc = make_desc(smem_u32(sAl) + (uint32_t)g * aq_block_bytes, lbo_a, sbo);
     const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_b, sbo);
-    constexpr uint32_t idesc_bf = make_idesc_bf16(BM, BN);
-    const int klsteps = a.KL >> 4;
-    const uint32_t at = tmem_base + (uint32_t)(g * KS);
-    const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+    const uint32_t at = tmem_base + (uint32_t)(g * (KS / 2));   // two FP16 per TMEM column
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    const int steps_b = (a.KQ - KS) >> 4;                       // K steps of the q columns beyond the first KS
     uint32_t stage = 0, bph = 0, s3 = 0, sph = 0, unit_idx = 0;
     auto next_stage = [&]() { if (++stage == NSTAGE) { stage = 0; bph ^= 1u; } };
     auto next_slot = [&]() { if (++s3 == 3) { s3 = 0; sph ^= 1u; } };
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         const uint32_t d_tmem = tmem_base + ACC_COL0 + slot * BN;
         const uint64_t bd = b_desc0 + (uint64_t)(stage * tile_units);
 #pragma unroll
-        for (int k = 0; k < (SSP_SV_RSTEPS ? SSP_SV_RSTEPS : KSTEPS); ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : preinit);
+        for (int k = 0; k < (SSP_SV_RSTEPS ? SSP_SV_RSTEPS : KSTEPS); ++k) mma_f16_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, k > 0 ? 1u : preinit);
         bar_commit(t_full + 8u * slot);
         bar_commit(b_empty + 8u * stage);
       }
@@ -364,9 +366,9 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       next_stage();
       next_slot();
     };
-    // common part = full logit of the reference model: images 0, 1 against [x^2, 1, 1] in shared memory, images 2, 3
-    // against [x, 1, 1] in TMEM, image 4 (BF16) against the rounding residuals of the frames, all into one accumulator;
-    // an image's ring stage is released as soon as its MMAs retire
+    // common part = full logit of the reference model, FP32 grade: ring slots 0, 1 hold the columns [0, KS) and [KS, KQ)
+    // of B_hi and multiply A_hi and A_lo, slots 2, 3 the same columns of B_lo and multiply A_hi; all into one
+    // accumulator; a slot's ring stage is released as soon as its MMAs retire
     auto job_q = [&]() {
       const uint32_t slot = (uint32_t)g + 2u * s3;
       bar_spin_relaxed(t_empty + 8u * slot, sph ^ 1u);
@@ -376,18 +378,22 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         bar_spin_relaxed(b_full + 8u * stage, bph);
         tc_fence_after();
         if (elect_one()) {
+          // straight-line issue: compile-time descriptor offsets, the steps beyond KQ masked by a uniform predicate (a
+          // rolled loop cost this warp ~17 instructions per MMA and left the epilogue waiting for every common part)
           const uint64_t bd = b_desc0 + (uint64_t)(stage * tile_units);
-          if (!((SSP_SV_QMASK >> part) & 1)) {
-            // A/B builds only: this image's MMAs are left out (benchmarks/sv_ab.sh)
-          } else if (part < 2) {
+          const bool second = (part & 1) != 0;
+          const uint64_t a_off = second ? (uint64_t)(KSTEPS * ks_a) : 0ull;
+          if ((SSP_SV_QMASK >> part) & 1) {  // (cleared bits: A/B builds only, benchmarks/sv_ab.sh)
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32(d_tmem, aq_desc + (uint64_t)(k * ks_a), bd + (uint64_t)(k * ks_b), idesc, (part | k) ? 1u : 0u);
-          } else if (part == 4) {
-#pragma unroll 1
-            for (int k = 0; k < klsteps; ++k) mma_bf16_ss(d_tmem, al_desc + (uint64_t)(k * ks_a), bd + (uint64_t)(k * ks_b), idesc_bf, 1u);
-          } else {
+            for (int k = 0; k < KSTEPS; ++k)
+              if (!second || k < steps_b)
+                mma_f16_ss(d_tmem, ah_desc + a_off + (uint64_t)(k * ks_a), bd + (uint64_t)(k * ks_b), idesc, (part | k) ? 1u : 0u);
+            if (part < 2) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) tc_mma_tf32_ts(d_tmem, at + 8u * k, bd + (uint64_t)(k * ks_b), idesc, 1u);
+              for (int k = 0; k < KSTEPS; ++k)
+                if (!second || k < steps_b)
+                  mma_f16_ss(d_tmem, al_desc + a_off + (uint64_t)(k * ks_a), bd + (uint64_t)(k * ks_b), idesc, 1u);
+            }
           }
           if (part == NQ - 1) bar_commit(t_full + 8u * slot);
           bar_commit(b_empty + 8u * stage);
@@ -455,39 +461,28 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       bar_spin(a_empty, (unit_idx & 1u) ^ 1u);
       tc_fence_after();
       {
-        // ---- q operand [x^2, 1, 1, 0..] in shared memory: row r of block mb at ((mb*KS/4 + j/4)*BM + r)*4 + j%4
+        // ---- q operand [x^2 | x | 1, 1, 0..] in shared memory as two FP16 pieces (A_hi, and what that rounding dropped):
+        //      (row r, column j) of block mb at ((mb*KQ/8 + j/8)*BM + r)*8 + j%8
         const int64_t fr = frame0 + frow;
         const bool live = fr < a.total_frames;
         const float* xr = a.feats + fr * a.D;
-        float* dst = sAq + (size_t)(frow >> 7) * (BM * KS) + (size_t)(frow & (BM - 1)) * 4;
-        const int j0 = fpart * (KS >> 1), j1 = j0 + (KS >> 1);
+        const size_t at0 = (size_t)(frow >> 7) * (BM * a.KQ) + (size_t)(frow & (BM - 1)) * 8;
+        const int j0 = fpart * (a.KQ >> 1), j1 = j0 + (a.KQ >> 1);
         for (int j = j0; j < j1; ++j) {
-          float v = 0.f;
-          if (j < a.D) { const float x = live ? xr[j] : 0.f; v = rna_tf32(x * x); }
-          else if (j < a.D + 2) v = 1.f;
-          dst[(size_t)(j >> 2) * (BM * 4) + (j & 3)] = v;
-        }
-      }
-      {
-        // ---- what TF32 rounding dropped, as BF16: [x^2 - tf32(x^2) | x - tf32(x) | 0..], (row r, column j) of block mb at
-        //      ((mb*KL/8 + j/8)*BM + r)*8 + j%8
-        const int64_t fr = frame0 + frow;
-        const bool live = fr < a.total_frames;
-        const float* xr = a.feats + fr * a.D;
-        __nv_bfloat16* dst = sAl + (size_t)(frow >> 7) * (BM * a.KL) + (size_t)(frow & (BM - 1)) * 8;
-        const int j0 = fpart * (a.KL >> 1), j1 = j0 + (a.KL >> 1);
-        for (int j = j0; j < j1; ++j) {
-          float v = 0.f;
-          if (live && j < 2 * a.D) {
-            const float x = xr[j < a.D ? j : j - a.D];
-            const float y = j < a.D ? x * x : x;
-            v = y - rna_tf32(y);
+          float y = 0.f;
+          if (j < 2 * a.D) {
+            if (live) { const float x = xr[j < a.D ? j : j - a.D]; y = j < a.D ? x * x : x; }
+          } else if (j < 2 * a.D + 2) {
+            y = 1.f;
           }
-          dst[(size_t)(j >> 3) * (BM * 8) + (j & 7)] = __float2bfloat16_rn(v);
+          const __half h = __float2half_rn(y);
+          const size_t at1 = at0 + (size_t)(j >> 3) * (BM * 8) + (j & 7);
+          sAh[at1] = h;
+          sAl[at1] = __float2half_rn(y - __half2float(h));
         }
       }
       {
-        // ---- r operand [x, 1, 1, 0..] straight into TMEM: lane == row, column == contraction index
+        // ---- r operand [x, 1, 1024, 0..] as FP16 straight into TMEM: lane == row, column c holds contraction indices 2c, 2c + 1
         const int64_t fe = frame0 + urow;
         const bool live = fe < a.total_frames;
         const float* xr = a.feats + fe * a.D;
@@ -495,13 +490,20 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
           uint32_t v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int j = 8 * c + e;
-            float x = 0.f;
-            if (j < a.D) x = live ? rna_tf32(xr[j]) : 0.f;
-            else if (j < a.D + 2) x = 1.f;
-            v[e] = __float_as_uint(x);
+            float x2[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int j = 16 * c + 2 * e + i;
+              float x = 0.f;
+              if (j < a.D) x = live ? xr[j] : 0.f;
+              else if (j == a.D) x = 1.f;
+              else if (j == a.D + 1) x = kSvConstScale;
+              x2[i] = x;
+            }
+            const __half2 hh = __floats2half2_rn(x2[0], x2[1]);   // .x (low half) = the lower contraction index
+            v[e] = *reinterpret_cast<const uint32_t*>(&hh);
           }
-          tc_st8(tmem_base + lane_addr + (uint32_t)(g * KS + 8 * c), v);
+          tc_st8(tmem_base + lane_addr + (uint32_t)(g * (KS / 2) + 8 * c), v);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
@@ -605,13 +607,13 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
 }
 
 // Re-score the (utterance, model) pairs the tensor kernel gave up on (NaN score): one warp per pair, FP32 online
-// log-sum-exp over the same TF32-rounded model tiles, exact frames.
+// log-sum-exp over the same FP16 model images, exact frames.
 __global__ void __launch_bounds__(256) sv_fixup_kernel(const Args a, int64_t n_pairs) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int S = a.set_models, KS = a.KS, D = a.D;   // launched once over the whole set
-  const size_t tile_floats = (size_t)BN * KS;
+  const int S = a.set_models, KS = a.KS, KQ = a.KQ, D = a.D;   // launched once over the whole set
+  const size_t tile_halfs = (size_t)BN * KS;
   const float LN2 = 0.69314718055994530942f;
   for (int64_t p = warp0; p < n_pairs; p += n_warps) {
     const double cur = a.scores[p];
@@ -624,16 +626,21 @@ __global__ void __launch_bounds__(256) sv_fixup_kernel(const Args a, int64_t n_p
       const float* xr = a.feats + t * D;
       float mrun = -3.0e38f, srun = 0.f;
       for (int c = lane; c < a.n_tiles * BN; c += 32) {
-        const float* tq = a.tiles + ((size_t)(c / BN) * (S + NQ)) * tile_floats;   // [x^2] hi, lo; [x] reference hi, lo
-        const float* tr = tq + (size_t)(NQ + m) * tile_floats;                         // [x] model minus reference
+        const __half* tq = a.tiles + ((size_t)(c / BN) * (S + NQ)) * tile_halfs;   // B_hi [0, KS), [KS, KQ); B_lo likewise
+        const __half* tr = tq + (size_t)(NQ + m) * tile_halfs;                      // model minus reference
         const int n = c % BN;
-        auto at = [&](const float* tile, int j) { return tile[((size_t)(j >> 2) * BN + n) * 4 + (j & 3)]; };
-        float l = at(tr, D) + at(tr, D + 1);
-        for (int i = 0; i < NQ; ++i) l += at(tq + i * tile_floats, D) + at(tq + i * tile_floats, D + 1);
+        auto at = [&](const __half* tile, int j) { return __half2float(tile[((size_t)(j >> 3) * BN + n) * 8 + (j & 7)]); };
+        auto bq = [&](int j) {  // column j of the common part, hi + lo
+          const __half* t_hi = j < KS ? tq : tq + tile_halfs;
+          const int jj = j < KS ? j : j - KS;
+          return at(t_hi, jj) + at(t_hi + 2 * tile_halfs, jj);
+        };
+        float l = at(tr, D) + kSvConstScale * at(tr, D + 1);
+        for (int j = 2 * D; j < KQ; ++j) l += bq(j);
         for (int j = 0; j < D; ++j) {
           const float x = xr[j];
-          l = fmaf(x, at(tr, j) + (at(tq + 2 * tile_floats, j) + at(tq + 3 * tile_floats, j)), l);
-          l = fmaf(x * x, at(tq, j) + at(tq + tile_floats, j), l);
+          l = fmaf(x, at(tr, j) + bq(D + j), l);
+          l = fmaf(x * x, bq(j), l);
         }
         const float mn = fmaxf(mrun, l);
         srun = srun * exp2f(mrun - mn) + exp2f(l - mn);
@@ -661,7 +668,7 @@ static int num_sms() {
 
 template <int kPoly, int kDeg, int KSTEPS>
 static int launch_one(const Args& a, unsigned grid, bool first, cudaStream_t st) {
-  const size_t smem = sv_smem_bytes(KSTEPS * 8, a.KL);  // make_sv_layout has checked it against the 227 KB limit
+  const size_t smem = sv_smem_bytes(KSTEPS * 16, a.KQ);  // make_sv_layout has checked it against the 227 KB limit
   if (first) {
     SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_score_sv_kernel<kPoly, kDeg, KSTEPS, true><<<grid, THREADS, smem, st>>>(a);
@@ -674,16 +681,12 @@ static int launch_one(const Args& a, unsigned grid, bool first, cudaStream_t st)
 template <int kPoly, int kDeg>
 static int launch_ks(const Args& a, unsigned grid, bool first, cudaStream_t st) {
   switch (a.KS) {
-    case 8: return launch_one<kPoly, kDeg, 1>(a, grid, first, st);
-    case 16: return launch_one<kPoly, kDeg, 2>(a, grid, first, st);
-    case 24: return launch_one<kPoly, kDeg, 3>(a, grid, first, st);
-    case 32: return launch_one<kPoly, kDeg, 4>(a, grid, first, st);
-    case 40: return launch_one<kPoly, kDeg, 5>(a, grid, first, st);
-    case 48: return launch_one<kPoly, kDeg, 6>(a, grid, first, st);
-    case 56: return launch_one<kPoly, kDeg, 7>(a, grid, first, st);
-    case 64: return launch_one<kPoly, kDeg, 8>(a, grid, first, st);
+    case 16: return launch_one<kPoly, kDeg, 1>(a, grid, first, st);
+    case 32: return launch_one<kPoly, kDeg, 2>(a, grid, first, st);
+    case 48: return launch_one<kPoly, kDeg, 3>(a, grid, first, st);
+    case 64: return launch_one<kPoly, kDeg, 4>(a, grid, first, st);
   }
-  set_error("ssp_gmm_score_shared: contraction length %d is not a multiple of 8 in [8, 64]", a.KS);
+  set_error("ssp_gmm_score_shared: contraction length %d is not a multiple of 16 in [16, 64]", a.KS);
   return SSP_EINVAL;
 }
 
@@ -700,7 +703,7 @@ static int sv_group_models(const SvLayout& L) {
     mb = e ? atof(e) : 24.0;
   }
   if (mb <= 0.0) return L.n_models;
-  const double per_model = (double)L.Kp * L.KS * sizeof(float);
+  const double per_model = (double)L.Kp * L.KS * 2.0;  // FP16 images
   int g = (int)(mb * 1048576.0 / per_model) / sv::CHUNK * sv::CHUNK;
   if (g < sv::CHUNK) g = sv::CHUNK;
   return g >= L.n_models ? L.n_models : g;
@@ -721,13 +724,13 @@ int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.offsets = offsets;
   a.n_utts = n_utts;
   a.total_frames = total_frames;
-  a.tiles = (const float*)pack;
+  a.tiles = (const __half*)pack;
   a.set_images = L.n_models + NQ;
   a.set_models = L.n_models;
   a.n_tiles = L.Kp / BN;
   a.D = L.D;
   a.KS = L.KS;
-  a.KL = sv_residual_len(L.D);
+  a.KQ = L.KQ;
   a.normalize = normalize ? 1 : 0;
   a.stab = group < L.n_models ? (float*)workspace : nullptr;
   const int64_t n_units = (total_frames + UNIT - 1) / UNIT;
@@ -741,7 +744,7 @@ int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, 
   }
   for (int m0 = 0; m0 < L.n_models; m0 += group) {
     a.n_models = L.n_models - m0 < group ? L.n_models - m0 : group;
-    a.tiles_group = a.tiles + (size_t)m0 * BN * L.KS;
+    a.tiles_group = a.tiles + (size_t)m0 * BN * L.KS;   // images are BN * KS FP16 values
     a.scores = scores + m0;
     a.frame_lse = frame_lse ? frame_lse + (size_t)m0 * total_frames : nullptr;
     const bool first = m0 == 0;

@@ -110,6 +110,13 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// the same with FP16 operands (a/b_format 0); kind::f16 serves both, so the instruction wrapper is shared
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(

@@ -201,7 +201,7 @@ class SharedModelSet:
         self.dims = _lib.GmmDims(self.n_models, self.n_comp, self.n_feat)
         nbytes = int(self.lib.ssp_gmm_shared_pack_bytes(C.byref(self.dims)))
         if nbytes <= 0:
-            raise ValueError(f"unsupported dims K={self.n_comp} D={self.n_feat} for the shared-variance kernel (need D <= 40)")
+            raise ValueError(f"unsupported dims K={self.n_comp} D={self.n_feat} for the shared-variance kernel (need D <= 39)")
         self.pack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ssp_gmm_pack_shared(_lib.ptr(w), _lib.ptr(var), _lib.ptr(mu), C.byref(self.dims),

@@ -110,7 +110,7 @@ def identify(utts, speakers, ubm=None, precision="auto", device=None):
             base = _base_params(ubm) if ubm is not None else None
             # mean-only MAP speakers (e.g. unpickled models adapted from this UBM): shared-variance kernel, with the UBM
             # as one more mean set -- only when the UBM (if any) is KNOWN to carry the same weights and variances
-            if (single_pass and smu.shape[2] <= 40 and SharedModelSet.shares_base(sw, svar)
+            if (single_pass and smu.shape[2] <= 39 and SharedModelSet.shares_base(sw, svar)
                     and (ubm is None or (base is not None and np.array_equal(base[0], sw[0]) and np.array_equal(base[1], svar[0])))):
                 if ubm is None:
                     means = smu
@@ -118,12 +118,16 @@ def identify(utts, speakers, ubm=None, precision="auto", device=None):
                     means = np.concatenate([smu, ubm._params[1].cpu().numpy()])
                 else:
                     means = np.concatenate([smu, np.asarray(ubm.means_)[None]])
-                sms = SharedModelSet(sw[0], svar[0], means, ref_model=-1, device=dev)
-                scores, _ = sms.score(feats, offs)
-                if ubm is not None:
-                    scores = scores[:, :-1] - scores[:, -1:]
-                pred = scores.cpu().numpy()
-                return pred, pred.argmax(axis=1)
+                try:
+                    sms = SharedModelSet(sw[0], svar[0], means, ref_model=-1, device=dev)
+                except NotImplementedError:   # parameters outside the FP16 range of that kernel: general kernel below
+                    sms = None
+                if sms is not None:
+                    scores, _ = sms.score(feats, offs)
+                    if ubm is not None:
+                        scores = scores[:, :-1] - scores[:, -1:]
+                    pred = scores.cpu().numpy()
+                    return pred, pred.argmax(axis=1)
             ms = ModelSet(sw, smu, svar, device=dev)
         if isinstance(ms, SharedModelSet) and precision not in ("tf32", "auto"):
             ms = ms.expand()

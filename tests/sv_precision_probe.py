@@ -1,7 +1,7 @@
 """Error of the shared-variance scoring kernel against the float64 oracle, per configuration: largest relative error of a
 per-utterance score, largest absolute error of a log-likelihood ratio against the reference member (GMM_UBM.py:194),
 largest relative error of a per-frame log-likelihood.  Sets the tolerances of tests/test_gpu_gmm.py.
-    gpurun -- 'python benchmarks/sv_precision.py'
+    gpurun -- 'python tests/sv_precision_probe.py'   (lives under tests/: it calls the oracle)
 """
 import json
 import os
