@@ -24,8 +24,10 @@ Audio, models and checks
 `e2e`    = frames/s through the public host-to-host call `ssp.identify_pcm` from pinned HOST PCM (H2D copy inside the
            timed region, its tail overlapped with the kernels of the head part) to the decisions read back on the host.
 `roofline` = the tcgen05 scoring kernel against the tensor roofline: algorithmic 4*D*K FLOP per (frame, model) / its
-           CUDA-event time / the measured TF32 GEMM peak (profiles/tf32_peak.json); `frac_hw` = the same against
-           SM clock x 4096 FLOP/clk/SM x SMs (the kind::tf32 issue rate at the clock the run actually held).
+           CUDA-event time / the measured dense rate of the pipe it issues on -- kind::f16 for the shared-variance kernel
+           (MEASURED_PEAKS.json bf16_tflops_sustained), kind::tf32 for the general one (profiles/tf32_peak.json);
+           `frac_hw` = the same against SM clock x FLOP/clk/SM x SMs at the clock the run actually held; `mufu` = the
+           exponentials of the log-sum-exp against the MUFU rate, the resource that actually binds.
 `secondary` = BASELINE.json configs[1], [2], [4] (front-end throughput, frame-sharded UBM EM with its all-reduce
            isolated, 2048-component sweep), each with its own roofline and -- at N = 1 -- CPU baseline on a stated sample.
 """
@@ -770,25 +772,44 @@ def run_b200(a):
     flop_per_launch = 4.0 * D * K * (frames / a.steps) * n_models
     k_ms = float(np.mean(score_ms))
     achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
-    if a.precision != "fp32":
+    if shared:
+        # the shared-variance kernel issues kind::f16 MMAs (FP16 operands, FP32 accumulation): its pipe's measured dense rate
+        peak, bound = peaks["bf16_tflops_sustained"], "tensor"
+        peak_note = ("MEASURED_PEAKS.json bf16_tflops_sustained (kind::f16: FP16 and BF16 operands run at the same dense rate; "
+                     "sustained: the kernel is timed inside a long step)")
+    elif a.precision != "fp32":
         peak, peak_note, bound = peaks["tf32_tflops_sustained"], peaks["tf32_source"] + " (sustained: the kernel is timed inside a long step)", "tensor"
     else:
         peak, peak_note, bound = 70.0, "nominal FP32 CUDA-core FMA peak (no measured figure)", "tensor"
     kernel = "gmm_score_sv_kernel" if shared else ("gmm_score_tc_kernel" if a.precision != "fp32" else "gmm_score_simt_kernel")
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    hw_peak = N_SMS * TF32_FLOP_PER_CLK_SM * sm_mhz * 1e6 / 1e12
+    flop_per_clk_sm = 2 * TF32_FLOP_PER_CLK_SM if shared else TF32_FLOP_PER_CLK_SM   # kind::f16 issues at twice the kind::tf32 rate
+    hw_peak = N_SMS * flop_per_clk_sm * sm_mhz * 1e6 / 1e12
     roof_extra = {"frac_hw": achieved / hw_peak, "hw_peak": hw_peak,
-                  "hw_peak_note": f"{N_SMS} SMs x {TF32_FLOP_PER_CLK_SM} FLOP/clk/SM x {sm_mhz:.0f} MHz (median SM clock of the timed region)"}
+                  "hw_peak_note": f"{N_SMS} SMs x {flop_per_clk_sm} FLOP/clk/SM x {sm_mhz:.0f} MHz (median SM clock of the timed region)"}
     if shared:
         # with the shared-variance shortcut the executed tensor work is smaller than the algorithmic 4DK:
-        # per (frame, model) 2 * KS * Kp with KS = roundup(D + 2, 8), plus the common part once per 32 models
-        ks, kp = (D + 2 + 7) // 8 * 8, (K + 63) // 64 * 64
-        exec_flop = 2.0 * ks * kp * (frames / a.steps) * (n_models * (1.0 + 1.0 / 32.0) + 2.0)
+        # per (frame, model) 2 * KS * Kp with KS = roundup(D + 2, 16); the common part (3 passes over roundup(2D + 2, 16))
+        # once per 32 models and once more in the pre-pass
+        ks, kq, kp = (D + 2 + 15) // 16 * 16, (2 * D + 2 + 15) // 16 * 16, (K + 63) // 64 * 64
+        frames_step = frames / a.steps
+        exec_flop = 2.0 * kp * frames_step * (ks * n_models + 3.0 * kq * (n_models / 32.0 + 1.0))
         ex = exec_flop / (k_ms * 1e-3) / 1e12
+        # the resource that binds: one exponential per (frame, model, component); 12 of 16 column pairs go through MUFU ex2
+        # (16 per clock per SM), 4 through an FMA-pipe polynomial
+        exps = frames_step * n_models * kp
+        mufu_peak = N_SMS * 16.0 * sm_mhz * 1e6
         roof_extra.update({"executed_tflops": ex, "executed_frac": ex / peak, "executed_frac_hw": ex / hw_peak,
-                           "note": "achieved = algorithmic 4*D*K FLOP per (frame, model); the shared-variance kernel executes "
-                                   "2*(D+2 padded to 48)*K on the tensor pipe and is bound by the 3.05e12 exponentials of the "
-                                   "log-sum-exp (MUFU ex2 + an FMA-pipe polynomial share), see profiles/"})
+                           "frac_of_tf32_peak": achieved / peaks["tf32_tflops_sustained"],
+                           "mufu": {"exponentials_per_launch": exps, "on_mufu": 0.75, "mufu_per_s_peak": mufu_peak,
+                                    "frac": 0.75 * exps / mufu_peak / (k_ms * 1e-3),
+                                    "frac_if_all_on_mufu": exps / mufu_peak / (k_ms * 1e-3),
+                                    "note": "MUFU ex2 time at the measured SM clock over the kernel time: the exponentials of the "
+                                            "log-sum-exp, not the tensor pipe, bound this kernel"},
+                           "note": "achieved = algorithmic 4*D*K FLOP per (frame, model) against the dense rate of the pipe the kernel "
+                                   "uses (kind::f16, FP16 operands with TF32's 11-bit significand, FP32 accumulation); the "
+                                   "shared-variance form executes 2*(D+2 padded to 48)*K per (frame, model) plus a 3-pass common "
+                                   "part per 32 models; round 1 issued kind::tf32 and quoted the TF32 peak (frac_of_tf32_peak)"})
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, from a committed ncu --set full capture
     traffic = None
     try:
@@ -802,9 +823,10 @@ def run_b200(a):
     line = {
         "metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tf32": "tf32", "tf32x2": "tf32 (2 passes)", "tf32x3": "tf32 (3 passes)", "fp32": "f32"}[a.precision], "data": "synthetic",
+        "dtype": ("f16 operands (11-bit significand, as tf32) / f32 accumulate; common part 3-pass f32 grade" if shared else
+                  {"tf32": "tf32", "tf32x2": "tf32 (2 passes)", "tf32x3": "tf32 (3 passes)", "fp32": "f32"}[a.precision]), "data": "synthetic",
         "config": {"workload": workload_name(a), "parallelism": f"utterances sharded x{world}, models replicated",
-                   "l2": "inputs per step (0.96 GB PCM, 0.2-0.33 GB model tiles) exceed the 126 MB L2", "scorer": a.scorer,
+                   "l2": "inputs per step (0.96 GB PCM, 0.1-0.33 GB model tiles) exceed the 126 MB L2", "scorer": a.scorer,
                    "audio": "synth.synth_pcm_torch (counter-based; the CPU arm and the oracle check regenerate the same utterances)",
                    "models": "UBM: 4 EM iterations on the enrolment features; speakers: mean-only MAP (r = 16) from 10 utterances each",
                    "frames_x_models_per_s": total_frames * n_models / (dev_ms * 1e-3)},

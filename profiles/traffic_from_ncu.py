@@ -29,8 +29,9 @@ for r in rows[2:]:  # every captured launch of the kernel: one scoring step may 
         total += float(r[i].replace(",", "")) * scale[units[i]]
 frames = utts * 298
 # algorithmic bytes of the scoring launch: features in + model images once + scores out
+# (FP16 images of 64 components x 48: the speakers, the UBM as one more mean set, and the 4 images of the common part)
 ks, kp = 48, (comps + 63) // 64 * 64
-algo = frames * 39 * 4 + (kp // 64) * (speakers + 2) * 64 * ks * 4 + utts * (speakers + 1) * 8
+algo = frames * 39 * 4 + (kp // 64) * (speakers + 1 + 4) * 64 * ks * 2 + utts * (speakers + 1) * 8
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
 data = json.load(open(path)) if os.path.exists(path) else {}
 data[kernel] = {"launches_per_step": n_launches, "utts": utts, "speakers": speakers, "components": comps, "dram_bytes": int(total), "algorithmic_bytes": int(algo),
