@@ -317,8 +317,14 @@ class FrontEnd:
 
     # -- host entry: list of 1-D numpy signals -----------------------------------------------
     def pack_host(self, signals):
-        """Concatenate utterances into one pinned host buffer + offsets (int16 stays int16)."""
+        """Concatenate utterances into one pinned host buffer + offsets (int16 stays int16).  A
+        :class:`~speech_signal_processing_b200.wavio.PcmBatch` (``read_wav_batch``) already is one: no copy."""
         torch = _lib.require_cuda()
+        from .wavio import PcmBatch
+
+        if isinstance(signals, PcmBatch):
+            pcm = signals.pcm if isinstance(signals.pcm, torch.Tensor) else torch.from_numpy(signals.pcm)
+            return pcm, np.asarray(signals.sample_offsets, dtype=np.int64)
         sigs = [np.asarray(s) for s in signals]
         for s in sigs:
             if s.ndim != 1:
@@ -336,7 +342,7 @@ class FrontEnd:
 
     @_lib.on_device
     def extract(self, signals, want_log_energy: bool = False):
-        """signals: list of 1-D arrays.  Returns (feats (sum T, out_dim) cuda float32,
+        """signals: list of 1-D arrays, or a PcmBatch.  Returns (feats (sum T, out_dim) cuda float32,
         frame_offsets np.int64 (n+1,), log_energy cuda float32 | None)."""
         host, offs = self.pack_host(signals)
         pcm = host.to(self.device, non_blocking=True)

@@ -21,6 +21,7 @@ import numpy as np
 
 from . import _lib
 from . import frontend as fe
+from .wavio import read_wav_batch
 from .mixture import (SINGLE_PASS_MIN_COMPONENTS, GaussianMixture, ModelSet, SharedModelSet, concat_utterances, fit_batch,
                       resolve_precision)
 
@@ -288,27 +289,48 @@ def _side_stream(dev):
 label_encoder: dict = {}
 
 
-def load_data(path="dataset/ASR_GMM"):
-    """``GMM_UBM.load_data`` (GMM_UBM.py:24-50): walk ``path/<speaker>/<session>/<wav>``, read every file with
-    ``scipy.io.wavfile.read`` (utils/tools.py:45-47), encode speakers in directory order into the module-level
-    ``label_encoder``.  Returns ``(x, y)``: list of int16 arrays, list of labels.  Stereo files keep their
-    first channel (the handling MFCC_DTW.py:141-144 applies)."""
-    from scipy.io import wavfile
-
-    t0 = time.time()
-    print("Loading data...")
-    x, y = [], []
+def list_wavs(path="dataset/ASR_GMM"):
+    """The files ``GMM_UBM.load_data`` reads, in its order (``os.listdir`` of ``path/<speaker>/<session>/``), with their
+    labels; fills the module-level ``label_encoder`` the way GMM_UBM.py:36-38 does."""
+    files, y = [], []
     for num, speaker in enumerate(os.listdir(path)):
         label_encoder[speaker] = num
         spk_dir = os.path.join(path, speaker)
         for session in os.listdir(spk_dir):
             ses_dir = os.path.join(spk_dir, session)
             for wav in os.listdir(ses_dir):
-                _, audio = wavfile.read(os.path.join(ses_dir, wav))
-                if audio.ndim == 2:
-                    audio = audio[:, 0]
-                x.append(audio)
+                files.append(os.path.join(ses_dir, wav))
                 y.append(num)
+    return files, y
+
+
+def load_batch(path="dataset/ASR_GMM"):
+    """``load_data`` without the list: ``(PcmBatch, y)`` -- every file of the tree decoded by worker threads straight into
+    one pinned staging buffer (:func:`~speech_signal_processing_b200.wavio.read_wav_batch`), ready for ONE upload and ONE
+    front-end launch (``FrontEnd.extract(batch)``)."""
+    files, y = list_wavs(path)
+    return read_wav_batch(files), y
+
+
+def load_data(path="dataset/ASR_GMM"):
+    """``GMM_UBM.load_data`` (GMM_UBM.py:24-50): walk ``path/<speaker>/<session>/<wav>``, encode speakers in directory
+    order into the module-level ``label_encoder``.  Returns ``(x, y)``: list of int16 arrays, list of labels.  The
+    files are decoded in one batch (headers first, then ``readinto`` the slices of one pinned buffer from worker threads)
+    and ``x`` holds views of that buffer; a tree with anything but 16-bit PCM files is read file by file with
+    ``scipy.io.wavfile.read`` as the reference does (utils/tools.py:45-47).  Stereo files keep their first channel (the
+    handling MFCC_DTW.py:141-144 applies)."""
+    t0 = time.time()
+    print("Loading data...")
+    files, y = list_wavs(path)
+    try:
+        x = read_wav_batch(files).utterances()
+    except ValueError:
+        from scipy.io import wavfile
+
+        x = []
+        for f in files:
+            _, audio = wavfile.read(f)
+            x.append(audio[:, 0] if audio.ndim == 2 else audio)
     print("Complete! Spend {:.2f}s".format(time.time() - t0))
     return x, y
 

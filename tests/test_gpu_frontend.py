@@ -211,3 +211,28 @@ def test_librosa_mfcc_options_match_oracle():
         want = ofe.librosa_mfcc(sig.astype(np.float32), **full)
         assert got.shape == want.shape and got.shape[0] == 13
         assert_ceps_close(got, want)
+
+
+def test_wav_batch_goes_to_the_front_end_without_a_repack(tmp_path):
+    """read_wav_batch -> FrontEnd.extract(batch): the pinned staging buffer is uploaded as it is; same features as the
+    list of arrays scipy returns for the same files (mono and stereo, ragged)."""
+    from scipy.io import wavfile
+
+    fe = ssp.FrontEnd(ssp.sidekit_recipe(), delta_order=2, cmvn=True)
+    paths, sigs = [], []
+    for i, n in enumerate((16000, 4000, 48000, 399, 9000)):
+        sig = synth.synth_utterance(i, 70, n_samples=n)
+        if i == 2:
+            sig = np.stack([sig, sig[::-1]], axis=1)
+        p = tmp_path / f"u{i}.wav"
+        wavfile.write(str(p), 16000, sig)
+        paths.append(p)
+        sigs.append(sig[:, 0] if sig.ndim == 2 else sig)
+    batch = ssp.read_wav_batch(paths)
+    assert batch.pcm.is_pinned()
+    host, offs = fe.pack_host(batch)
+    assert host.data_ptr() == batch.pcm.data_ptr()
+    f_batch, o_batch, _ = fe.extract(batch)
+    f_list, o_list, _ = fe.extract(sigs)
+    assert np.array_equal(o_batch, o_list)
+    assert bool((f_batch == f_list).all())

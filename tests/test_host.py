@@ -293,3 +293,99 @@ def test_counter_based_audio_is_a_pure_function_of_its_ids():
     assert spk[1234] == 234 and utt[1234] == bench.TEST_UTT_BASE + 1 and utt.min() >= bench.TEST_UTT_BASE > bench.ENROL_UTTS
     pcm = bench.gen_pcm(spk[:3], utt[:3], "cpu", n_samples=2000, chunk=2)
     assert torch.equal(pcm.reshape(3, 2000), synth.synth_pcm_torch(spk[:3], utt[:3], 2000, "cpu"))
+
+
+# ------------------------------------------------------------------------------------------------
+# batched WAV ingest (wavio.py) against scipy.io.wavfile.read, the reader the reference uses (utils/tools.py:45-47)
+# ------------------------------------------------------------------------------------------------
+def _write_wav_with_extra_chunks(path, rate, data, extensible=False):
+    """A 16-bit PCM file with a LIST chunk of odd size before the data chunk (and optionally WAVE_FORMAT_EXTENSIBLE)."""
+    import struct
+
+    data = np.ascontiguousarray(data, dtype="<i2")
+    ch = 1 if data.ndim == 1 else data.shape[1]
+    if extensible:
+        fmt = struct.pack("<HHIIHH", 0xFFFE, ch, rate, rate * 2 * ch, 2 * ch, 16) + struct.pack("<HHI", 22, 16, 0) + \
+            struct.pack("<H", 1) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+    else:
+        fmt = struct.pack("<HHIIHH", 1, ch, rate, rate * 2 * ch, 2 * ch, 16)
+    lst = b"INFOabc"  # 7 bytes: padded to 8
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", len(lst)) + lst + b"\x00" + \
+        b"data" + struct.pack("<I", data.nbytes) + data.tobytes()
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def test_read_wav_batch_equals_scipy(tmp_path):
+    from scipy.io import wavfile
+
+    import speech_signal_processing_b200 as ssp
+
+    rs = np.random.RandomState(3)
+    cases = []
+    for i, (n, ch) in enumerate([(16000, 1), (1, 1), (0, 1), (4801, 2), (333, 1), (777, 3)]):
+        sig = rs.randint(-32768, 32767, size=(n,) if ch == 1 else (n, ch)).astype(np.int16)
+        p = tmp_path / f"a{i}.wav"
+        if i in (1, 3, 4):
+            _write_wav_with_extra_chunks(str(p), 8000 + i, sig, extensible=(i == 4))
+        else:
+            wavfile.write(str(p), 16000, sig)
+        cases.append(p)
+    batch = ssp.read_wav_batch(cases, threads=3)
+    assert len(batch) == len(cases) and batch.sample_offsets[0] == 0
+    utts = batch.utterances()
+    for p, got, rate in zip(cases, utts, batch.rates):
+        want_rate, want = wavfile.read(str(p))
+        want = want[:, 0] if want.ndim == 2 else want
+        assert rate == want_rate and got.dtype == np.int16 and np.array_equal(got, want)
+    assert batch.sample_offsets[-1] == sum(len(u) for u in utts)
+    # anything but 16-bit PCM is refused (load_data then reads the tree the reference's way)
+    wavfile.write(str(tmp_path / "f32.wav"), 16000, rs.randn(100).astype(np.float32))
+    with pytest.raises(ValueError):
+        ssp.read_wav_batch([tmp_path / "f32.wav"])
+    (tmp_path / "junk.wav").write_bytes(b"not a wav file at all")
+    with pytest.raises(ValueError):
+        ssp.read_wav_batch([tmp_path / "junk.wav"])
+
+
+def test_load_data_walks_the_tree_like_the_reference(tmp_path, capsys):
+    """x, y and label_encoder as GMM_UBM.load_data (GMM_UBM.py:24-50) builds them, through the batched reader and -- for a
+    tree holding a float file -- through the per-file fallback."""
+    from scipy.io import wavfile
+
+    import speech_signal_processing_b200 as ssp
+    from speech_signal_processing_b200 import ubm
+
+    rs = np.random.RandomState(4)
+    root = tmp_path / "ASR_GMM"
+    for s in range(3):
+        for ses in range(2):
+            d = root / f"spk{s}" / f"ses{ses}"
+            d.mkdir(parents=True)
+            for u in range(2):
+                wavfile.write(str(d / f"u{u}.wav"), 16000, rs.randint(-3000, 3000, size=400 + 10 * u).astype(np.int16))
+
+    def reference_walk():
+        x, y, enc = [], [], {}
+        for num, spk in enumerate(os.listdir(root)):
+            enc[spk] = num
+            for ses in os.listdir(root / spk):
+                for w in os.listdir(root / spk / ses):
+                    x.append(wavfile.read(str(root / spk / ses / w))[1])
+                    y.append(num)
+        return x, y, enc
+
+    ubm.label_encoder.clear()
+    x, y = ssp.load_data(str(root))
+    rx, ry, enc = reference_walk()
+    assert y == ry and dict(ubm.label_encoder) == enc and len(x) == 12
+    assert all(np.array_equal(a, b) for a, b in zip(x, rx))
+    assert "Loading data..." in capsys.readouterr().out
+    batch, y2 = ssp.load_batch(str(root))
+    assert y2 == ry and all(np.array_equal(a, b) for a, b in zip(batch.utterances(), rx))
+    wavfile.write(str(root / "spk0" / "ses0" / "u0.wav"), 16000, rs.randn(50).astype(np.float32))
+    ubm.label_encoder.clear()
+    x3, y3 = ssp.load_data(str(root))
+    rx3, ry3, _ = reference_walk()
+    assert y3 == ry3 and all(np.array_equal(a, b) for a, b in zip(x3, rx3))
+    ubm.label_encoder.clear()
