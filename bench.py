@@ -795,17 +795,18 @@ def run_b200(a):
         frames_step = frames / a.steps
         exec_flop = 2.0 * kp * frames_step * (ks * n_models + 3.0 * kq * (n_models / 32.0 + 1.0))
         ex = exec_flop / (k_ms * 1e-3) / 1e12
-        # the resource that binds: one exponential per (frame, model, component); 12 of 16 column pairs go through MUFU ex2
-        # (16 per clock per SM), 4 through an FMA-pipe polynomial
+        # the resource that binds: one exponential per (frame, model, component); by default 10 of 16 column pairs go through
+        # MUFU ex2 (16 per clock per SM), 6 through a degree-3 FMA-pipe polynomial (SSP_SV_POLY_PAIRS)
         exps = frames_step * n_models * kp
         mufu_peak = N_SMS * 16.0 * sm_mhz * 1e6
+        on_mufu = 1.0 - int(os.environ.get("SSP_SV_POLY_PAIRS", "6")) / 16.0
         roof_extra.update({"executed_tflops": ex, "executed_frac": ex / peak, "executed_frac_hw": ex / hw_peak,
                            "frac_of_tf32_peak": achieved / peaks["tf32_tflops_sustained"],
-                           "mufu": {"exponentials_per_launch": exps, "on_mufu": 0.75, "mufu_per_s_peak": mufu_peak,
-                                    "frac": 0.75 * exps / mufu_peak / (k_ms * 1e-3),
+                           "mufu": {"exponentials_per_launch": exps, "on_mufu": on_mufu, "mufu_per_s_peak": mufu_peak,
+                                    "frac": on_mufu * exps / mufu_peak / (k_ms * 1e-3),
                                     "frac_if_all_on_mufu": exps / mufu_peak / (k_ms * 1e-3),
                                     "note": "MUFU ex2 time at the measured SM clock over the kernel time: the exponentials of the "
-                                            "log-sum-exp, not the tensor pipe, bound this kernel"},
+                                            "log-sum-exp (MUFU + FMA pipes + their issue slots), not the tensor pipe, bound this kernel"},
                            "note": "achieved = algorithmic 4*D*K FLOP per (frame, model) against the dense rate of the pipe the kernel "
                                    "uses (kind::f16, FP16 operands with TF32's 11-bit significand, FP32 accumulation); the "
                                    "shared-variance form executes 2*(D+2 padded to 48)*K per (frame, model) plus a 3-pass common "

@@ -73,8 +73,11 @@ constexpr uint32_t ACC_COL0 = 128;       // TMEM: [0, 2 KS) frame operand of the
 #ifndef SSP_SV_QMASK
 #define SSP_SV_QMASK 0xf  // which of the NQ images of the common part are multiplied (all; cleared bits are A/B builds)
 #endif
-constexpr int kDefaultPolyPairs = 4;  // measured on B200 (2000 utts x 1001 models): 0/4/6/8 pairs -> 163/136/142/155 ms
-constexpr int kDefaultPolyDeg = 4;
+// Share of the exponentials on the FMA pipe, measured on B200 (bench.py config 4, ms per scoring call, benchmarks/sv_poly_ab.sh;
+// the float64 oracle check reads 1.35e-5 / 1.36e-5 relative for degree 4 / 3): FP16 kernel, (pairs, degree) = (2,4) 728, (4,4) 711,
+// (6,4) 706, (6,3) 691, (8,3) 720.  (The TF32 kernel of round 1, power-capped and with twice the MMA instructions, was best at (4,4).)
+constexpr int kDefaultPolyPairs = 6;
+constexpr int kDefaultPolyDeg = 3;
 
 struct Args {
   const float* feats;
@@ -205,7 +208,8 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
 // sum over 32 accumulator columns of 2^(r + qm) (kAdd) or 2^r (the accumulator already held qm when the MMA ran).
 // kPoly of the 16 column pairs go to the FMA pipe:
 // 2^d = 2^n p(f), n = round(d) by the 1.5 * 2^23 magic add, f = d - n in [-0.5, 0.5], p = minimax polynomial
-// (degree 4: 2.7e-6 relative, degree 3: 7.5e-5), 2^n applied by adding n to the exponent field; the rest is MUFU ex2.
+// (degree 4: 2.7e-6 relative, degree 3: 7.5e-5 -- 3e-5 absolute on a frame's log-likelihood at the default share, 5e-7 of
+// its magnitude), 2^n applied by adding n to the exponent field; the rest is MUFU ex2.
 template <int kPoly, int kDeg, bool kAdd>
 __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float (&qm)[32]) {
   static_assert(kPoly % 2 == 0 && kPoly <= 16, "pairs are consumed two at a time");
@@ -754,6 +758,7 @@ int launch_score_sv(const float* feats, const int64_t* offsets, int64_t n_utts, 
     else if (deg == 4 && poly == 4) rc = launch_ks<4, 4>(a, grid, first, st);
     else if (deg == 4 && poly == 6) rc = launch_ks<6, 4>(a, grid, first, st);
     else if (deg == 4 && poly == 8) rc = launch_ks<8, 4>(a, grid, first, st);
+    else if (deg == 3 && poly == 4) rc = launch_ks<4, 3>(a, grid, first, st);
     else if (deg == 3 && poly == 6) rc = launch_ks<6, 3>(a, grid, first, st);
     else if (deg == 3 && poly == 8) rc = launch_ks<8, 3>(a, grid, first, st);
     else set_error("SSP_SV_POLY_PAIRS / SSP_SV_POLY_DEG: unsupported combination (%d, %d)", poly, deg);
