@@ -30,10 +30,10 @@
 //                 shared-memory traffic for the frames at all; q-tiles: both operands in shared memory.
 //                 M128 x N64 x K16, 6 accumulator slots (3 per row block) so the tensor core runs ahead of the epilogue
 //   (warps 0..3 shrink to 32 registers, the epilogue warps grow to 112: setmaxnreg)
-//   warps 4..19 : epilogue   - thread == (frame row, 32 of the tile's 64 columns); keeps q[t, its 32 columns] - m_t in
-//                 registers across the models of a chunk, per tile: tcgen05.ld, leave q - m_t in the slot for the job
-//                 three ahead, sum 2^d (MUFU ex2 + an FMA-pipe polynomial share), added to the (model, frame) partial
-//                 sum in shared memory
+//   warps 4..19 : epilogue   - thread == (frame row, 32 of the tile's 64 columns); keeps the weights P = 2^(q - m_t) of its
+//                 32 columns in registers across the models of a chunk; per model job: tcgen05.ld, release the slot,
+//                 sum_c P_c 2^r_c (MUFU ex2 + an FMA-pipe polynomial share, one packed FMA per pair), added to the
+//                 (model, frame) partial sum in shared memory
 //   per-frame stabiliser m_t = round(max_c logit of the reference model), found in a short pre-pass, fixed for the whole
 //   unit, so partial sums of different component tiles simply add.  After a chunk's last tile the partial sums become
 //   per-frame log-likelihoods, are summed per utterance inside the warp and added to the (utterance, model) scores.
@@ -64,6 +64,9 @@ constexpr int CTRL_REGS = 32, EPI_REGS = 112;  // launched at 96: 128 x (96 - 32
 constexpr int NQ = kSvBaseImages;          // ring slots of the common part: B_hi columns [0, KS) and [KS, KQ), B_lo likewise
 constexpr int CHUNK = kSvChunk;                // models per chunk: partial sums [2 column halves][CHUNK][UNIT] fp32 = 64 KB
 constexpr uint32_t ACC_COL0 = 128;       // TMEM: [0, 2 KS) frame operand of the two row blocks, [128, 512) accumulators
+#ifndef SSP_SV_WEIGHTS
+#define SSP_SV_WEIGHTS 1  // 1: the epilogue keeps 2^(q - m_t) as weights; 0: q - m_t is left in the accumulator slots (round-1 scheme)
+#endif
 #ifndef SSP_SV_RELAX_NS
 #define SSP_SV_RELAX_NS 1000  // suspend-time hint of the control warps' mbarrier waits
 #endif
@@ -210,8 +213,12 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
 // 2^d = 2^n p(f), n = round(d) by the 1.5 * 2^23 magic add, f = d - n in [-0.5, 0.5], p = minimax polynomial
 // (degree 4: 2.7e-6 relative, degree 3: 7.5e-5 -- 3e-5 absolute on a frame's log-likelihood at the default share, 5e-7 of
 // its magnitude), 2^n applied by adding n to the exponent field; the rest is MUFU ex2.
-template <int kPoly, int kDeg, bool kAdd>
+// kMode 0: the accumulator already holds r + (q - m_t) (the MMA ran on top of it); 1: qm = q - m_t is added here; 2: qm holds
+// the WEIGHTS 2^(q - m_t) and the sum is sum_c qm_c 2^r_c -- same instruction count as mode 0 (the packed add of the running
+// sum becomes a packed FMA), and nothing has to be left in the accumulator slot for a later job.
+template <int kPoly, int kDeg, int kMode>
 __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float (&qm)[32]) {
+  constexpr bool kAdd = kMode == 1, kMul = kMode == 2;
   static_assert(kPoly % 2 == 0 && kPoly <= 16, "pairs are consumed two at a time");
   const float MAGIC = 12582912.f;  // 1.5 * 2^23
   const float2 mg = make_float2(MAGIC, MAGIC), nmg = make_float2(-MAGIC, -MAGIC), neg1 = make_float2(-1.f, -1.f);
@@ -239,7 +246,7 @@ __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float 
     float2 e;
     e.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
     e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
-    accp = __fadd2_rn(accp, e);
+    accp = kMul ? __ffma2_rn(e, make_float2(qm[2 * i], qm[2 * i + 1]), accp) : __fadd2_rn(accp, e);
   }
 #pragma unroll
   for (int i = kPoly; i < 16; i += 2) {
@@ -249,8 +256,13 @@ __device__ __forceinline__ float exp_sum32(const uint32_t (&r)[32], const float 
       d0 = __fadd2_rn(d0, make_float2(qm[2 * i], qm[2 * i + 1]));
       d1 = __fadd2_rn(d1, make_float2(qm[2 * i + 2], qm[2 * i + 3]));
     }
-    accm0 = __fadd2_rn(accm0, make_float2(ex2(d0.x), ex2(d0.y)));
-    accm1 = __fadd2_rn(accm1, make_float2(ex2(d1.x), ex2(d1.y)));
+    if (kMul) {
+      accm0 = __ffma2_rn(make_float2(ex2(d0.x), ex2(d0.y)), make_float2(qm[2 * i], qm[2 * i + 1]), accm0);
+      accm1 = __ffma2_rn(make_float2(ex2(d1.x), ex2(d1.y)), make_float2(qm[2 * i + 2], qm[2 * i + 3]), accm1);
+    } else {
+      accm0 = __fadd2_rn(accm0, make_float2(ex2(d0.x), ex2(d0.y)));
+      accm1 = __fadd2_rn(accm1, make_float2(ex2(d1.x), ex2(d1.y)));
+    }
   }
   const float2 tot = __fadd2_rn(__fadd2_rn(accm0, accm1), accp);
   return tot.x + tot.y;
@@ -417,7 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
         for (int j = 0; j < NT; ++j) {
           job_q();                                // common part of tile j
 #pragma unroll 1
-          for (int m = 0; m < nm; ++m) job_r(m >= 2 ? 1u : 0u);
+          for (int m = 0; m < nm; ++m) job_r(!SSP_SV_WEIGHTS && m >= 2 ? 1u : 0u);
         }
       }
       if (elect_one()) bar_commit(a_empty);
@@ -549,6 +561,26 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
       for (int m0 = 0; m0 < S; m0 += CHUNK) {
         const int nm = min(CHUNK, S - m0);
         for (int j = 0; j < NT; ++j) {
+#if SSP_SV_WEIGHTS
+          // sum_c 2^(q - m_t + r) = sum_c P_c 2^r_c with the weights P = 2^(q - m_t) of this thread's 32 columns kept in
+          // registers for the models of the chunk: one MUFU per column and tile, and a model job is tcgen05.ld, release,
+          // 32 x (ex2 | polynomial) and a packed FMA per pair.  (Round 1 left q - m_t in the accumulator slot for the MMA
+          // three jobs ahead to run on top of: a tcgen05.st + wait per job, and the slot was released only after it.)
+          float qm[32];
+          {
+            uint32_t r[32];
+            fetch(r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) qm[i] = ex2(__uint_as_float(r[i]) - m_t);
+          }
+          float* dst = my_part;
+#pragma unroll 1
+          for (int m = 0; m < nm; ++m, dst += UNIT) {
+            uint32_t r[32];
+            fetch(r);
+            *dst += exp_sum32<kPoly, kDeg, 2>(r, qm);
+          }
+#else
           // Job i of this tile (i = 0: common part, i = 1 + m: model m) shares its accumulator slot with job i + 3.
           // If that one is a model of the same tile, q - m_t is left in the slot and the MMA accumulates on top of
           // it, so the sum needs no add; the first two models of a tile (their slots were last used by the previous
@@ -576,14 +608,15 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
           for (int m = 0; m < nm && m < 2; ++m, dst += UNIT) {
             uint32_t r[32];
             fetch(r, m + 3 < nm ? &qm : nullptr);
-            *dst += exp_sum32<kPoly, kDeg, true>(r, qm);
+            *dst += exp_sum32<kPoly, kDeg, 1>(r, qm);
           }
 #pragma unroll 1
           for (int m = 2; m < nm; ++m, dst += UNIT) {
             uint32_t r[32];
             fetch(r, m + 3 < nm ? &qm : nullptr);
-            *dst += exp_sum32<kPoly, kDeg, false>(r, qm);
+            *dst += exp_sum32<kPoly, kDeg, 0>(r, qm);
           }
+#endif
         }
         // ---- partial sums of this chunk -> per-frame log-likelihood -> per-utterance score
         named_bar_sync(3, EPI);
