@@ -160,11 +160,12 @@ def test_em_trajectory_matches_sklearn(golden, tag, iters):
         gm.fit(x)
     assert gm.n_iter_ == int(g[f"{tag}_fit{iters}_niter"])
     assert gm.converged_ == bool(g[f"{tag}_fit{iters}_conv"])
-    assert abs(gm.lower_bound_ - float(g[f"{tag}_fit{iters}_lb"])) < 2e-5 * abs(float(g[f"{tag}_fit{iters}_lb"]))
-    loose = 1.0 if iters == 100 else 0.1  # fp32 E-step differences compound over ~dozens of iterations
-    np.testing.assert_allclose(gm.weights_, g[f"{tag}_fit{iters}_w"], rtol=1e-2 * loose, atol=1e-4 * loose)
-    np.testing.assert_allclose(gm.means_, g[f"{tag}_fit{iters}_mu"], rtol=0, atol=2e-2 * loose)
-    np.testing.assert_allclose(gm.covariances_, g[f"{tag}_fit{iters}_var"], rtol=5e-2 * loose, atol=1e-3)
+    assert abs(gm.lower_bound_ - float(g[f"{tag}_fit{iters}_lb"])) < 5e-6 * abs(float(g[f"{tag}_fit{iters}_lb"]))
+    # measured (tests/em_trajectory_probe.py): weights 7e-5 relative, means 1.4e-4 absolute, variances 1.2e-4 relative at
+    # 1, 3 and 100 iterations alike -- the TF32 rounding of the posteriors in the statistics GEMM, which does not compound
+    np.testing.assert_allclose(gm.weights_, g[f"{tag}_fit{iters}_w"], rtol=3e-4, atol=1e-6)
+    np.testing.assert_allclose(gm.means_, g[f"{tag}_fit{iters}_mu"], rtol=0, atol=5e-4)
+    np.testing.assert_allclose(gm.covariances_, g[f"{tag}_fit{iters}_var"], rtol=5e-4, atol=1e-6)
     np.testing.assert_allclose(gm.precisions_cholesky_, 1 / np.sqrt(gm.covariances_))
 
 
