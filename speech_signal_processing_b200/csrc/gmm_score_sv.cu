@@ -574,6 +574,8 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_score_sv_kernel(const Args a) 
             for (int i = 0; i < 32; ++i) qm[i] = ex2(__uint_as_float(r[i]) - m_t);
           }
           float* dst = my_part;
+          // (Reading an accumulator as two 16-column halves, the next job's first half in flight behind the second, was 18 %
+          // SLOWER -- 793 vs 672 ms: every tcgen05.wait::ld costs a fixed ~100 cycles, so one 32-column load per job it is.)
 #pragma unroll 1
           for (int m = 0; m < nm; ++m, dst += UNIT) {
             uint32_t r[32];
