@@ -80,7 +80,8 @@ __host__ __device__ inline size_t carve_floats(const ssp_frontend_cfg& c, int ma
 constexpr int SK_FL = 400, SK_SH = 160, SK_NF = 24, SK_NC = 13;
 
 template <typename PcmT, bool kSk>
-__global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, const int materialize, const int64_t n_utts) {
+__global__ void __launch_bounds__(256, 2) frontend512_kernel(const FrontendArgs a, const int flags, const int64_t n_utts) {
+  const int materialize = flags & 1;  // bit 1: never take the direct-load path (A/B knob SSP_FE_STAGED)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ssp_frontend_cfg& cfg = a.cfg;
   const int NC = kSk ? SK_NC : cfg.n_ceps, NF = kSk ? SK_NF : cfg.n_filt, FL = kSk ? SK_FL : cfg.frame_len,
@@ -209,115 +210,8 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
   if (T <= 0) continue;
   const int n_batches = (T + W - 1) / W;
 
-  // The staging loads of batch b+1 are issued before batch b is processed and only written to shared memory
-  // after it, so their global-memory latency hides behind a whole frame of FFT work.
-  constexpr int PF = 8;  // samples per thread per batch: (W-1)*shift + frame_len + 1 <= 256 * PF
-  float pf[PF];
-  // int16 PCM whose utterance starts on a 16-byte boundary: thread t stages samples [8t, 8t + 8) of the batch with one
-  // 16-byte load (W * shift is a multiple of 8, so every batch stays aligned); the sample before the batch (needed by
-  // the pre-emphasis) goes through thread 255.  Otherwise: one sample per load, 8 loads per thread.
-  const bool vec = sizeof(PcmT) == 2 && ((s_begin & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.pcm) & 15) == 0);
-  auto prefetch = [&](int b) {
-    const int64_t base = (int64_t)b * W * SH;
-    if (vec) {
-      const int64_t j = base + 8 * tid;
-      if (8 * tid < stg - 1 && j + 7 < n_samp) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(a.pcm) + s_begin + j);
-        pf[0] = __uint_as_float(raw.x); pf[1] = __uint_as_float(raw.y); pf[2] = __uint_as_float(raw.z); pf[3] = __uint_as_float(raw.w);
-      } else {
-        // tail of the utterance: per-sample loads, packed the same way so that the unpack below is shared
-        uint32_t wds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int64_t g = j + 2 * e;
-          const int lo = (8 * tid < stg - 1 && g < n_samp) ? (int)reinterpret_cast<const int16_t*>(a.pcm)[s_begin + g] : 0;
-          const int hi = (8 * tid < stg - 1 && g + 1 < n_samp) ? (int)reinterpret_cast<const int16_t*>(a.pcm)[s_begin + g + 1] : 0;
-          wds[e] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
-        }
-        pf[0] = __uint_as_float(wds[0]); pf[1] = __uint_as_float(wds[1]); pf[2] = __uint_as_float(wds[2]); pf[3] = __uint_as_float(wds[3]);
-      }
-      pf[4] = (tid == 255 && base > 0 && base - 1 < n_samp) ? load_pcm<PcmT>(a.pcm, s_begin + base - 1) : 0.f;
-      return;
-    }
-    const int64_t g0 = base - 1;
-#pragma unroll
-    for (int r = 0; r < PF; ++r) {
-      const int i = tid + 256 * r;
-      const int64_t g = g0 + i;
-      pf[r] = (i < stg && g >= 0 && g < n_samp) ? load_pcm<PcmT>(a.pcm, s_begin + g) : 0.f;
-    }
-  };
-  prefetch(0);
-  for (int b = 0; b < n_batches; ++b) {
-    float* stage = stage0 + (b & 1) * stage_stride;
-    if (vec) {
-      if (8 * tid < stg - 1) {
-        float smp[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t wd = __float_as_uint(pf[e]);
-          smp[2 * e] = (float)(int16_t)(wd & 0xffffu);
-          smp[2 * e + 1] = (float)(int16_t)(wd >> 16);
-        }
-        float4* dst = reinterpret_cast<float4*>(stage + 1 + 8 * tid);   // 16-byte aligned; the buffer has slack for whole stores
-        dst[0] = make_float4(smp[0], smp[1], smp[2], smp[3]);
-        dst[1] = make_float4(smp[4], smp[5], smp[6], smp[7]);
-      }
-      if (tid == 255) stage[0] = pf[4];
-    } else {
-#pragma unroll
-      for (int r = 0; r < PF; ++r) {
-        const int i = tid + 256 * r;
-        if (i < stg) stage[i] = pf[r];
-      }
-    }
-    __syncthreads();  // batch b is staged; buffer (b + 1) & 1 was last read in batch b - 1, which every warp has left
-    if (b + 1 < n_batches) prefetch(b + 1);
-    const int f = b * W + warp;
-    if (f >= T) continue;
-    const float* s = stage + 1 + warp * SH;              // s[i] = sample i of this frame, s[-1] the one before
-    const int64_t s0 = (int64_t)f * SH;
-    const int n_valid = (int)min((int64_t)FL, n_samp - s0);  // samples of the frame that exist (zero padded tail)
-
-    // ---- load + pre-emphasis + energy + window, packed z[n] = (x[2n], x[2n+1]); lane holds z[32 j + lane]
-    float2 v[8];
-    float energy = 0.f;
-    if (kSk) {
-      // every frame is complete (framing 0): no tail handling; samples as aligned pairs, window taps from registers
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int i = 64 * j + 2 * lane;
-        float2 x = make_float2(0.f, 0.f);
-        float xm1 = 0.f;
-        if (j < 6 || i < SK_FL) {
-          x = *reinterpret_cast<const float2*>(s + i);
-          xm1 = (j == 0 && lane == 0) ? x.x : s[i - 1];
-        }
-        const float y0 = fmaf(-pre, xm1, x.x), y1 = fmaf(-pre, x.x, x.y);
-        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
-        v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
-      }
-      v[7] = make_float2(0.f, 0.f);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = 64 * j + 2 * lane;
-        float y0 = 0.f, y1 = 0.f;
-        if (i < n_valid) {
-          const float x0 = s[i];
-          float xm1 = s[i - 1];
-          if (i == 0 && pmode == 1) xm1 = x0;
-          y0 = pmode ? fmaf(-pre, xm1, x0) : x0;
-          if (i + 1 < n_valid) {
-            const float x1 = s[i + 1];
-            y1 = pmode ? fmaf(-pre, x0, x1) : x1;
-          }
-        }
-        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
-        const float w0 = i < FL ? win[i] : 0.f, w1 = i + 1 < FL ? win[i + 1] : 0.f;
-        v[j] = make_float2(y0 * w0, y1 * w1);
-      }
-    }
+  // everything of a frame after the windowed samples: FFT, spectrum, filterbank, log, DCT -> cepstra of frame f
+  auto finish_frame = [&](const int f, float2 (&v)[8], float energy) {
     energy = warp_sum(energy);
 
     // ---- 256-point FFT: n = 32 n1 + n2 (n2 = lane), k = k1 + 8 k2
@@ -496,8 +390,159 @@ __global__ void __launch_bounds__(256) frontend512_kernel(const FrontendArgs a, 
     }
     }
     if (lane == 0 && a.out_log_energy && cfg.energy_mode == 1) a.out_log_energy[f_begin + f] = kSk ? __logf(energy) : logf(energy);
+  };
+
+  // kSk, int16 PCM on a 4-byte boundary: NO staging and no CTA barrier per batch.  A lane's samples of a frame are seven
+  // aligned pairs z[32 j + lane] = (x[64 j + 2 lane], x[.. + 1]) -- seven coalesced 4-byte loads straight from global memory
+  // (a sample is read by the 2.5 frames that cover it, from L1 after the first), the sample before a pair comes from the
+  // neighbouring lane by shuffle, and the loads of the warp's NEXT frame are in flight while this one is transformed.  The
+  // warps of a CTA run decoupled until the delta / CMVN phase.
+  const bool direct = kSk && sizeof(PcmT) == 2 && ((s_begin & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.pcm) & 3) == 0) && !(flags & 2);
+  if (direct) {
+    const uint32_t* pairs = reinterpret_cast<const uint32_t*>(reinterpret_cast<const int16_t*>(a.pcm) + s_begin) + lane;
+    uint32_t cur[7], nxt[7];
+    auto load_frame = [&](int f, uint32_t (&wd)[7]) {
+      const uint32_t* q = pairs + (int64_t)f * (SK_SH / 2);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) wd[j] = (j < 6 || lane < (SK_FL - 384) / 2) ? __ldg(q + 32 * j) : 0u;
+    };
+    if (warp < T) load_frame(warp, cur);
+    for (int f = warp; f < T; f += W) {
+      if (f + W < T) load_frame(f + W, nxt);
+      float2 v[8];
+      float energy = 0.f, hi_prev = 0.f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const float lo = (float)(int16_t)(cur[j] & 0xffffu), hi = (float)(int16_t)(cur[j] >> 16);
+        // x[i - 1]: the odd sample of the lane below; lane 0 takes lane 31's odd sample of the previous pair row
+        float xm1 = __shfl_sync(0xffffffffu, lane == 31 ? hi_prev : hi, (lane + 31) & 31);
+        if (j == 0 && lane == 0) xm1 = lo;   // per-frame pre-emphasis: the first sample is its own predecessor
+        hi_prev = hi;
+        float y0 = fmaf(-pre, xm1, lo), y1 = fmaf(-pre, lo, hi);
+        if (j == 6 && lane >= (SK_FL - 384) / 2) { y0 = 0.f; y1 = 0.f; }
+        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+        v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
+      }
+      v[7] = make_float2(0.f, 0.f);
+      finish_frame(f, v, energy);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) cur[j] = nxt[j];
+    }
+    __syncthreads();
+  } else {
+  // The staging loads of batch b+1 are issued before batch b is processed and only written to shared memory
+  // after it, so their global-memory latency hides behind a whole frame of FFT work.
+  constexpr int PF = 8;  // samples per thread per batch: (W-1)*shift + frame_len + 1 <= 256 * PF
+  float pf[PF];
+  // int16 PCM whose utterance starts on a 16-byte boundary: thread t stages samples [8t, 8t + 8) of the batch with one
+  // 16-byte load (W * shift is a multiple of 8, so every batch stays aligned); the sample before the batch (needed by
+  // the pre-emphasis) goes through thread 255.  Otherwise: one sample per load, 8 loads per thread.
+  const bool vec = sizeof(PcmT) == 2 && ((s_begin & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.pcm) & 15) == 0);
+  auto prefetch = [&](int b) {
+    const int64_t base = (int64_t)b * W * SH;
+    if (vec) {
+      const int64_t j = base + 8 * tid;
+      if (8 * tid < stg - 1 && j + 7 < n_samp) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(a.pcm) + s_begin + j);
+        pf[0] = __uint_as_float(raw.x); pf[1] = __uint_as_float(raw.y); pf[2] = __uint_as_float(raw.z); pf[3] = __uint_as_float(raw.w);
+      } else {
+        // tail of the utterance: per-sample loads, packed the same way so that the unpack below is shared
+        uint32_t wds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t g = j + 2 * e;
+          const int lo = (8 * tid < stg - 1 && g < n_samp) ? (int)reinterpret_cast<const int16_t*>(a.pcm)[s_begin + g] : 0;
+          const int hi = (8 * tid < stg - 1 && g + 1 < n_samp) ? (int)reinterpret_cast<const int16_t*>(a.pcm)[s_begin + g + 1] : 0;
+          wds[e] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+        }
+        pf[0] = __uint_as_float(wds[0]); pf[1] = __uint_as_float(wds[1]); pf[2] = __uint_as_float(wds[2]); pf[3] = __uint_as_float(wds[3]);
+      }
+      pf[4] = (tid == 255 && base > 0 && base - 1 < n_samp) ? load_pcm<PcmT>(a.pcm, s_begin + base - 1) : 0.f;
+      return;
+    }
+    const int64_t g0 = base - 1;
+#pragma unroll
+    for (int r = 0; r < PF; ++r) {
+      const int i = tid + 256 * r;
+      const int64_t g = g0 + i;
+      pf[r] = (i < stg && g >= 0 && g < n_samp) ? load_pcm<PcmT>(a.pcm, s_begin + g) : 0.f;
+    }
+  };
+  prefetch(0);
+  for (int b = 0; b < n_batches; ++b) {
+    float* stage = stage0 + (b & 1) * stage_stride;
+    if (vec) {
+      if (8 * tid < stg - 1) {
+        float smp[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t wd = __float_as_uint(pf[e]);
+          smp[2 * e] = (float)(int16_t)(wd & 0xffffu);
+          smp[2 * e + 1] = (float)(int16_t)(wd >> 16);
+        }
+        float4* dst = reinterpret_cast<float4*>(stage + 1 + 8 * tid);   // 16-byte aligned; the buffer has slack for whole stores
+        dst[0] = make_float4(smp[0], smp[1], smp[2], smp[3]);
+        dst[1] = make_float4(smp[4], smp[5], smp[6], smp[7]);
+      }
+      if (tid == 255) stage[0] = pf[4];
+    } else {
+#pragma unroll
+      for (int r = 0; r < PF; ++r) {
+        const int i = tid + 256 * r;
+        if (i < stg) stage[i] = pf[r];
+      }
+    }
+    __syncthreads();  // batch b is staged; buffer (b + 1) & 1 was last read in batch b - 1, which every warp has left
+    if (b + 1 < n_batches) prefetch(b + 1);
+    const int f = b * W + warp;
+    if (f >= T) continue;
+    const float* s = stage + 1 + warp * SH;              // s[i] = sample i of this frame, s[-1] the one before
+    const int64_t s0 = (int64_t)f * SH;
+    const int n_valid = (int)min((int64_t)FL, n_samp - s0);  // samples of the frame that exist (zero padded tail)
+
+    // ---- load + pre-emphasis + energy + window, packed z[n] = (x[2n], x[2n+1]); lane holds z[32 j + lane]
+    float2 v[8];
+    float energy = 0.f;
+    if (kSk) {
+      // every frame is complete (framing 0): no tail handling; samples as aligned pairs, window taps from registers
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int i = 64 * j + 2 * lane;
+        float2 x = make_float2(0.f, 0.f);
+        float xm1 = 0.f;
+        if (j < 6 || i < SK_FL) {
+          x = *reinterpret_cast<const float2*>(s + i);
+          xm1 = (j == 0 && lane == 0) ? x.x : s[i - 1];
+        }
+        const float y0 = fmaf(-pre, xm1, x.x), y1 = fmaf(-pre, x.x, x.y);
+        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+        v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
+      }
+      v[7] = make_float2(0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = 64 * j + 2 * lane;
+        float y0 = 0.f, y1 = 0.f;
+        if (i < n_valid) {
+          const float x0 = s[i];
+          float xm1 = s[i - 1];
+          if (i == 0 && pmode == 1) xm1 = x0;
+          y0 = pmode ? fmaf(-pre, xm1, x0) : x0;
+          if (i + 1 < n_valid) {
+            const float x1 = s[i + 1];
+            y1 = pmode ? fmaf(-pre, x0, x1) : x1;
+          }
+        }
+        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+        const float w0 = i < FL ? win[i] : 0.f, w1 = i + 1 < FL ? win[i + 1] : 0.f;
+        v[j] = make_float2(y0 * w0, y1 * w1);
+      }
+    }
+    finish_frame(f, v, energy);
   }
   __syncthreads();
+  }  // staged path
 
   // ---- delta / delta-delta / CMVN
   const int N = cfg.delta_n;
@@ -600,6 +645,11 @@ int launch_frontend_fast(const FrontendArgs& a, int64_t n_utts, size_t* smem_out
   }
   const unsigned grid = (unsigned)(n_utts < 16 * (int64_t)sms ? n_utts : 16 * (int64_t)sms);
   const ssp_frontend_cfg& c = a.cfg;
+  static int staged = -1;
+  if (staged < 0) {
+    const char* e = getenv("SSP_FE_STAGED");  // A/B knob: 1 = stage the samples of 8 frames in shared memory (round-1 scheme)
+    staged = e ? atoi(e) : 0;
+  }
   static int no_sk = -1;
   if (no_sk < 0) {
     const char* e = getenv("SSP_FE_GENERIC");  // A/B knob: 1 = never take the compile-time specialisation
@@ -611,7 +661,7 @@ int launch_frontend_fast(const FrontendArgs& a, int64_t n_utts, size_t* smem_out
 #define SSP_FE_LAUNCH(T, SK)                                                                                              \
   do {                                                                                                                    \
     SSP_CUDA_OK(cudaFuncSetAttribute(ff::frontend512_kernel<T, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ff::frontend512_kernel<T, SK><<<grid, 256, smem, st>>>(a, mat ? 1 : 0, n_utts);                                      \
+    ff::frontend512_kernel<T, SK><<<grid, 256, smem, st>>>(a, (mat ? 1 : 0) | (staged ? 2 : 0), n_utts);                 \
   } while (0)
   if (c.pcm_dtype == 0) {
     if (sk) SSP_FE_LAUNCH(int16_t, true); else SSP_FE_LAUNCH(int16_t, false);
