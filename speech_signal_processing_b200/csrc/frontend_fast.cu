@@ -20,6 +20,7 @@
 //     registers, samples are read as aligned 8-byte pairs (round 1: 4-byte loads at stride 2 floats, the bulk of the
 //     26 % bank-conflict wavefronts), the DCT runs two lanes per cepstrum, and log is lg2.approx * ln 2 (|error| ~1e-6).
 #include <cstdlib>
+#include <type_traits>
 
 #include "frontend_common.cuh"
 
@@ -397,37 +398,66 @@ __global__ void __launch_bounds__(256, 2) frontend512_kernel(const FrontendArgs 
   // (a sample is read by the 2.5 frames that cover it, from L1 after the first), the sample before a pair comes from the
   // neighbouring lane by shuffle, and the loads of the warp's NEXT frame are in flight while this one is transformed.  The
   // warps of a CTA run decoupled until the delta / CMVN phase.
-  const bool direct = kSk && sizeof(PcmT) == 2 && ((s_begin & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.pcm) & 3) == 0) && !(flags & 2);
+  const bool direct = kSk && sizeof(PcmT) == 2 && ((reinterpret_cast<uintptr_t>(a.pcm) & 3) == 0) && !(flags & 2);
   if (direct) {
-    const uint32_t* pairs = reinterpret_cast<const uint32_t*>(reinterpret_cast<const int16_t*>(a.pcm) + s_begin) + lane;
+    // an utterance that starts on an odd sample reads the pairs one sample earlier: word = (x[i - 1], x[i]), x[i + 1] comes
+    // from the lane above
+    const bool odd = (s_begin & 1) != 0;
+    const int16_t* pcm16 = reinterpret_cast<const int16_t*>(a.pcm) + s_begin;
+    const uint32_t* pairs = reinterpret_cast<const uint32_t*>(pcm16 - (odd ? 1 : 0)) + lane;
+    constexpr int LAST = (SK_FL - 384) / 2;   // lanes of pair row 6 inside the frame
     uint32_t cur[7], nxt[7];
     auto load_frame = [&](int f, uint32_t (&wd)[7]) {
       const uint32_t* q = pairs + (int64_t)f * (SK_SH / 2);
 #pragma unroll
-      for (int j = 0; j < 7; ++j) wd[j] = (j < 6 || lane < (SK_FL - 384) / 2) ? __ldg(q + 32 * j) : 0u;
+      for (int j = 0; j < 6; ++j) wd[j] = __ldg(q + 32 * j);
+      wd[6] = lane < LAST ? __ldg(q + 192) : 0u;
+      // odd start: lane LAST holds (x[399], x[400]); only x[399] is part of the frame (and of the buffer)
+      if (odd && lane == LAST) wd[6] = (uint32_t)(uint16_t)pcm16[(int64_t)f * SK_SH + SK_FL - 1];
     };
-    if (warp < T) load_frame(warp, cur);
-    for (int f = warp; f < T; f += W) {
-      if (f + W < T) load_frame(f + W, nxt);
-      float2 v[8];
-      float energy = 0.f, hi_prev = 0.f;
+    // (one loop per alignment, chosen per utterance: with both unpack variants inside one loop the kernel lost the 10 % the
+    // direct loads had gained)
+    auto run = [&](auto odd_tag) {
+      constexpr bool kOdd = decltype(odd_tag)::value;
+      if (warp < T) load_frame(warp, cur);
+      for (int f = warp; f < T; f += W) {
+        if (f + W < T) load_frame(f + W, nxt);
+        float2 v[8];
+        float energy = 0.f;
+        if (!kOdd) {
+          float hi_prev = 0.f;
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const float lo = (float)(int16_t)(cur[j] & 0xffffu), hi = (float)(int16_t)(cur[j] >> 16);
-        // x[i - 1]: the odd sample of the lane below; lane 0 takes lane 31's odd sample of the previous pair row
-        float xm1 = __shfl_sync(0xffffffffu, lane == 31 ? hi_prev : hi, (lane + 31) & 31);
-        if (j == 0 && lane == 0) xm1 = lo;   // per-frame pre-emphasis: the first sample is its own predecessor
-        hi_prev = hi;
-        float y0 = fmaf(-pre, xm1, lo), y1 = fmaf(-pre, lo, hi);
-        if (j == 6 && lane >= (SK_FL - 384) / 2) { y0 = 0.f; y1 = 0.f; }
-        energy = fmaf(y0, y0, fmaf(y1, y1, energy));
-        v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
+          for (int j = 0; j < 7; ++j) {
+            const float lo = (float)(int16_t)(cur[j] & 0xffffu), hi = (float)(int16_t)(cur[j] >> 16);
+            // x[i - 1]: the odd sample of the lane below; lane 0 takes lane 31's odd sample of the previous pair row
+            float xm1 = __shfl_sync(0xffffffffu, lane == 31 ? hi_prev : hi, (lane + 31) & 31);
+            if (j == 0 && lane == 0) xm1 = lo;   // per-frame pre-emphasis: the first sample is its own predecessor
+            hi_prev = hi;
+            float y0 = fmaf(-pre, xm1, lo), y1 = fmaf(-pre, lo, hi);
+            if (j == 6 && lane >= LAST) { y0 = 0.f; y1 = 0.f; }
+            energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+            v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const float xm = (float)(int16_t)(cur[j] & 0xffffu), x0 = (float)(int16_t)(cur[j] >> 16);   // x[i - 1], x[i]
+            const float lo_next_row = j < 6 ? (float)(int16_t)(cur[j < 6 ? j + 1 : j] & 0xffffu) : 0.f;
+            // x[i + 1]: the even-position sample of the lane above; lane 31 takes lane 0's of the next pair row
+            const float x1 = __shfl_sync(0xffffffffu, lane == 0 ? lo_next_row : xm, (lane + 1) & 31);
+            float y0 = fmaf(-pre, (j == 0 && lane == 0) ? x0 : xm, x0), y1 = fmaf(-pre, x0, x1);
+            if (j == 6 && lane >= LAST) { y0 = 0.f; y1 = 0.f; }
+            energy = fmaf(y0, y0, fmaf(y1, y1, energy));
+            v[j] = make_float2(y0 * wreg[j].x, y1 * wreg[j].y);
+          }
+        }
+        v[7] = make_float2(0.f, 0.f);
+        finish_frame(f, v, energy);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) cur[j] = nxt[j];
       }
-      v[7] = make_float2(0.f, 0.f);
-      finish_frame(f, v, energy);
-#pragma unroll
-      for (int j = 0; j < 7; ++j) cur[j] = nxt[j];
-    }
+    };
+    if (odd) run(std::true_type{}); else run(std::false_type{});
     __syncthreads();
   } else {
   // The staging loads of batch b+1 are issued before batch b is processed and only written to shared memory
