@@ -187,14 +187,18 @@ int64_t ssp_gmm_pack_bytes(const ssp_gmm_dims* dims);
  * out_pack  device, ssp_gmm_pack_bytes() bytes, 128-byte aligned.  Holds, per model,
  *           (a) exact fp32 rows [mu/var, -1/(2 var)] + log-constant for the CUDA-core kernels and
  *           (b) TF32-rounded, log2(e)-scaled [mu/var, -1/(2 var), c_hi, c_lo] tiles laid out as
- *               tcgen05 shared-memory images (one bulk copy per 128-component tile).
+ *               tcgen05 shared-memory images (one bulk copy per 128-component tile), their residuals (2- / 3-pass
+ *               rungs), FP16 images of the same rows (single-pass rung) and BF16 hi + lo images (ssp_gmm_stats).
  */
 int ssp_gmm_pack_models(const double* weights, const double* means, const double* variances,
                         const ssp_gmm_dims* dims, void* out_pack, void* stream);
 
 #define SSP_PREC_FP32 0 /* CUDA-core FP32 FMA, ~1e-7 relative                              */
-#define SSP_PREC_TF32 1 /* tcgen05 kind::tf32 MMA, FP32 accumulate in TMEM: one pass, operands rounded to TF32;
-                           1e-4 relative on the utterance score at K >= 512 components and ~300 frames          */
+#define SSP_PREC_TF32 1 /* one tcgen05 pass, operands rounded to an 11-bit significand, FP32 accumulate in TMEM:
+                           1e-4 relative on the utterance score at K >= 512 components and ~300 frames.  Issued as
+                           kind::f16 from FP16 images of the pack (TF32's significand, K = 16 per MMA, half the bytes)
+                           when every model value fits FP16's range, else as kind::tf32; a frame outside that range is
+                           re-scored in FP32 (tc_fixup_kernel)                                                  */
 #define SSP_PREC_TF32X2 2 /* two passes, A.B_hi + A.B_lo: the model operand exact to 2^-22 (its rounding is the
                              systematic part of the one-pass error), frames still rounded                       */
 #define SSP_PREC_TF32X3 3 /* three passes (3xTF32), A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: FP32-grade, ~5e-7 relative;

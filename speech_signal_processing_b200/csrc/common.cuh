@@ -54,8 +54,8 @@ struct PackLayout {
   int Kp;  // K rounded up to kTileN (padded components have cst = -1e30, zero rows)
   int DP;  // D padded for the CUDA-core kernels: 16, 32, 40, 64 or 80
   int KD;  // contraction length of the tensor kernel: roundup(2D + 2, 8)
-  size_t off_ab, off_cst, off_tile, off_tile_lo, off_tile_bf, bytes;  // off_tile_bf == 0: no BF16 images (n_models > 1)
-  int KDb() const { return (2 * D + 2 + 15) / 16 * 16; }  // contraction length of the BF16 images (multiple of 16)
+  size_t off_ab, off_cst, off_tile, off_tile_lo, off_tile_bf, off_tile_h, off_flag, bytes;  // off_tile_bf == 0: no BF16 images (n_models > 1)
+  int KDb() const { return (2 * D + 2 + 15) / 16 * 16; }  // contraction length of the BF16 / FP16 images (multiple of 16)
   size_t tile_floats() const { return (size_t)kTileN * KD; }
 };
 
@@ -141,6 +141,17 @@ inline bool make_layout(const ssp_gmm_dims* dims, PackLayout* L) {
     L->off_tile_bf = o;
     o = up(o + (size_t)L->n_models * (L->Kp / kTileN) * 512 * L->KDb());
   }
+  // FP16 images of the same rows for the single-pass scoring rung (kind::f16: K = 16 per MMA, half the bytes; an FP16
+  // significand has TF32's 11 bits): [model][Kp/128 tiles][KDb/8][128][8 half], + a flag the pack kernel raises when a
+  // value leaves FP16's range (ssp_gmm_score then streams the TF32 images instead)
+  L->off_tile_h = 0;
+  L->off_flag = 0;
+  if (2 * L->D + 2 <= 80) {
+    L->off_tile_h = o;
+    o = up(o + (size_t)L->n_models * L->Kp * L->KDb() * 2);
+    L->off_flag = o;
+    o = up(o + 128);
+  }
   L->bytes = o;
   return true;
 }
@@ -191,6 +202,9 @@ __device__ __forceinline__ void warp_segmented_atomic_add(double* out, int seg, 
 int launch_pack(const double* w, const double* mu, const double* var, const PackLayout& L, void* pack, cudaStream_t st);
 int launch_score_simt(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
                       const PackLayout& L, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
+// host-side note of which packs may be scored from their FP16 images (gmm_score_tc.cu): reset by every pack call, resolved by
+// one read-back of the pack's overflow flag the first time the pack is scored in a single pass
+void note_pack(const void* pack);
 int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
                     const PackLayout& L, int parts, bool normalize, double* scores, float* frame_lse, cudaStream_t st);
 int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_segs, int64_t total_frames, const void* pack,

@@ -19,7 +19,8 @@ __device__ __forceinline__ float to_tf32(float x) {
 __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __restrict__ mu,
                                 const double* __restrict__ var, int n_models, int K, int Kp, int D, int DP, int KD,
                                 float2* __restrict__ ab, float* __restrict__ cst, float* __restrict__ tiles,
-                                float* __restrict__ tiles_lo, __nv_bfloat16* __restrict__ tiles_bf, int KDb) {
+                                float* __restrict__ tiles_lo, __nv_bfloat16* __restrict__ tiles_bf, int KDb,
+                                __half* __restrict__ tiles_h, int* __restrict__ h_overflow) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_models * Kp) return;
   int m = (int)(idx / Kp), c = (int)(idx % Kp);
@@ -43,8 +44,20 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   };
   if (tbf)
     for (int j = 0; j < KDb; ++j) { bf_at(0, j) = __float2bfloat16_rn(0.f); bf_at(1, j) = __float2bfloat16_rn(0.f); }
+  // FP16 image of the tile (single-pass scoring rung): element (j, n) at ((j/8)*128 + n)*8 + j%8
+  __half* th = tiles_h ? tiles_h + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KDb : nullptr;
+  bool h_bad = false;
+  auto h_put = [&](int j, double v) {
+    const __half h = __float2half_rn((float)v);
+    if (!(fabs((double)__half2float(h)) <= 65504.0)) h_bad = true;
+    th[(((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7)] = h;
+    return (double)__half2float(h);
+  };
+  if (th)
+    for (int j = 0; j < KDb; ++j) th[(((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7)] = __float2half_rn(0.f);
   const double LOG2E = 1.4426950408889634074;
   if (c >= K) {
+    if (th) h_put(2 * D, -60000.0);  // 2^-60000 == 0: padded components never contribute
     if (tbf) bf_at(0, 2 * D) = __float2bfloat16_rn(-1e30f);
     for (int d = 0; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
     cst[idx] = -1e30f;
@@ -74,6 +87,10 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
       bf_split(d, a1 * LOG2E);
       bf_split(D + d, a2 * LOG2E);
     }
+    if (th) {
+      h_put(d, a1 * LOG2E);
+      h_put(D + d, a2 * LOG2E);
+    }
   }
   for (int d = D; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
   double cc = log(w[(int64_t)m * K + c]) - 0.5 * (D * 1.8378770664093454836 + quad) + 0.5 * logdet;
@@ -90,6 +107,12 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
     lo_at(2 * D) = to_tf32((float)(c2 - (double)hi - (double)lo));  // third piece of the constant
     for (int j = 2 * D + 1; j < KD; ++j) lo_at(j) = 0.f;
   }
+  if (th) {  // two FP16 pieces of the constant against the two "one" columns
+    const double ch = c2 > -60000.0 ? c2 : -60000.0;   // (zero-weight components)
+    const double got = h_put(2 * D, ch);
+    h_put(2 * D + 1, ch - got);
+    if (h_bad) *h_overflow = 1;
+  }
   if (tbf) {  // three BF16 pieces of the constant (24 bits) against the two "one" columns of the frame operand
     const __nv_bfloat16 p1 = __float2bfloat16_rn((float)c2);
     const double r1 = c2 - (double)__bfloat162float(p1);
@@ -105,11 +128,15 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
   int64_t n = (int64_t)L.n_models * L.Kp;
   int threads = 128;
   int64_t blocks = (n + threads - 1) / threads;
+  if (L.off_flag) SSP_CUDA_OK(cudaMemsetAsync(base + L.off_flag, 0, 128, st));
   gmm_pack_kernel<<<(unsigned)blocks, threads, 0, st>>>(w, mu, var, L.n_models, L.K, L.Kp, L.D, L.DP, L.KD,
                                                        (float2*)(base + L.off_ab), (float*)(base + L.off_cst),
                                                        (float*)(base + L.off_tile),
                                                        L.off_tile_lo ? (float*)(base + L.off_tile_lo) : nullptr,
-                                                       L.off_tile_bf ? (__nv_bfloat16*)(base + L.off_tile_bf) : nullptr, L.KDb());
+                                                       L.off_tile_bf ? (__nv_bfloat16*)(base + L.off_tile_bf) : nullptr, L.KDb(),
+                                                       L.off_tile_h ? (__half*)(base + L.off_tile_h) : nullptr,
+                                                       L.off_flag ? (int*)(base + L.off_flag) : nullptr);
+  note_pack(pack);
   SSP_LAUNCH_CHECK("gmm_pack_kernel");
   return SSP_OK;
 }

@@ -22,7 +22,11 @@
 //
 // The log-constant rides through the MMA as two TF32-exact pieces (c_hi + c_lo) against A columns of 1.0,
 // so the epilogue is max / ex2 / add only.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "tc_common.cuh"
 
@@ -129,15 +133,19 @@ struct Args {
   float* frame_lse;
 };
 
-template <int kPolyPairs, int MB, int NPARTS>
+// kH: the single-pass rung from FP16 operands (kind::f16, K = 16 per MMA: half the MMA instructions, half the bytes of a model
+// tile and of the frame operand; an FP16 significand has TF32's 11 bits).  a.KD is then the FP16 contraction length.
+template <int kPolyPairs, int MB, int NPARTS, bool kH = false>
 __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const Args a) {
   static_assert(NPARTS >= 1 && NPARTS <= 3 && (MB == 1 || MB == 2) && (NPARTS < 3 || MB == 1), "see the rung table");
+  static_assert(!kH || NPARTS == 1, "FP16 operands serve the single-pass rung");
+  constexpr uint32_t ELT = kH ? 2u : 4u;
   constexpr int UNIT = BM * MB, EPI_WARPS = 8 * MB;
   constexpr int A_IMAGES = MB * (NPARTS == 3 ? 2 : 1);  // hi images of every row block, then the lo images
   extern __shared__ __align__(1024) unsigned char smem[];
   const int KD = a.KD;
-  const uint32_t tile_bytes = (uint32_t)BN * KD * 4u;
-  float* sA = reinterpret_cast<float*>(smem);                     // [A_IMAGES][KC][BM][4]
+  const uint32_t tile_bytes = (uint32_t)BN * KD * ELT;
+  float* sA = reinterpret_cast<float*>(smem);                     // [A_IMAGES][KC][BM][4]   (kH: [KD/8][BM][8] half)
   unsigned char* sB = smem + (size_t)A_IMAGES * tile_bytes;       // [NSTAGE][KC][BN][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NSTAGE * tile_bytes);
   uint64_t* b_full = bars;
@@ -184,7 +192,8 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
           mbar_wait(b_empty + stage, ph ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(b_full + stage, tile_bytes);
-            bulk_g2s(sB + (size_t)stage * tile_bytes, (part == 0 ? a.tiles : a.tiles_lo) + (size_t)t * tile_floats, tile_bytes,
+            bulk_g2s(sB + (size_t)stage * tile_bytes,
+                     reinterpret_cast<const unsigned char*>(part == 0 ? a.tiles : a.tiles_lo) + (size_t)t * tile_bytes, tile_bytes,
                      b_full + stage);
           }
           __syncwarp();
@@ -198,7 +207,8 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
     const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo, sbo);
     const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo, sbo);
     const uint32_t tile_units = tile_bytes >> 4;
-    const int ksteps = KD >> 3;
+    const int ksteps = kH ? KD >> 4 : KD >> 3;
+    constexpr uint32_t idesc = kH ? make_idesc_f16(BM, BN) : kIdesc;
     uint32_t it = 0, q = 0, unit_idx = 0;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_idx) {
       mbar_wait(a_full, unit_idx & 1u);
@@ -222,8 +232,13 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
           const uint32_t d_tmem = tmem_base + slot * BN;
           const uint64_t ad0 = a_desc0 + (uint64_t)(mb * tile_units), al0 = a_desc0 + (uint64_t)((MB + mb) * tile_units);
           if (elect_one()) {
+            if (kH) {
+              mma_f16_ss(d_tmem, ad0, bd0, idesc, 0u);
+              for (int k = 1; k < ksteps; ++k) mma_f16_ss(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), idesc, 1u);
+            } else {
             tc_mma_tf32(d_tmem, ad0, bd0, kIdesc, 0u);
             for (int k = 1; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), kIdesc, 1u);
+            }
             if (NPARTS >= 2)
               for (int k = 0; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bl0 + (uint64_t)(k * kstep), kIdesc, 1u);
             if (NPARTS == 3)
@@ -262,12 +277,17 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
         const bool live = fr < a.total_frames;
         const float* xr = a.feats + fr * a.D;
         float* dst = sA + (size_t)(brow >> 7) * tile_floats + (size_t)(brow & (BM - 1)) * 4;
+        __half* dst_h = reinterpret_cast<__half*>(sA) + (size_t)(brow >> 7) * tile_floats + (size_t)(brow & (BM - 1)) * 8;
         const int j0 = part * (KD >> 1), j1 = j0 + (KD >> 1);
         for (int j = j0; j < j1; ++j) {
           float v = 0.f;
           if (j < a.D) v = live ? xr[j] : 0.f;
           else if (j < 2 * a.D) { float x = live ? xr[j - a.D] : 0.f; v = x * x; }
           else if (j < 2 * a.D + 2) v = 1.f;
+          if (kH) {   // a frame outside FP16's range gives inf -> NaN scores for its utterance; see launch_score_tc
+            dst_h[(size_t)(j >> 3) * (BM * 8) + (j & 7)] = __float2half_rn(v);
+            continue;
+          }
           const float hi = rna_tf32(v);
           dst[(size_t)(j >> 2) * (BM * 4) + (j & 3)] = hi;
           if (NPARTS == 3) dst[(size_t)MB * tile_floats + (size_t)(j >> 2) * (BM * 4) + (j & 3)] = rna_tf32(v - hi);
@@ -348,7 +368,84 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
   }
 }
 
+// FP16 operands: a frame outside FP16's range (|x| > 255: x^2 overflows) turns the scores of its utterance into NaN / inf.
+// One warp per (utterance, model) pair scans the score matrix and re-scores such pairs in FP32 from the exact section
+// of the pack (ab = (mu/var, -1/(2 var)), cst), online log-sum-exp per frame.
+struct FixArgs {
+  const float* feats;
+  const int64_t* offsets;
+  int64_t n_utts, total_frames;
+  const float2* ab;
+  const float* cst;
+  int n_models, Kp, K, D, DP, normalize;
+  double* scores;
+  float* frame_lse;
+};
+__global__ void __launch_bounds__(256) tc_fixup_kernel(const FixArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_pairs = a.n_utts * a.n_models;
+  for (int64_t p = warp0; p < n_pairs; p += n_warps) {
+    const double cur = a.scores[p];
+    if (cur == cur && fabs(cur) < 1.0e300) continue;
+    const int64_t utt = p / a.n_models;
+    const int m = (int)(p % a.n_models);
+    const int64_t t0 = a.offsets[utt], t1 = a.offsets[utt + 1];
+    double total = 0.0;
+    for (int64_t t = t0; t < t1; ++t) {
+      const float* xr = a.feats + t * a.D;
+      float mrun = -3.0e38f, srun = 0.f;
+      for (int c = lane; c < a.K; c += 32) {
+        const float2* row = a.ab + ((int64_t)m * a.Kp + c) * a.DP;
+        float l = a.cst[(int64_t)m * a.Kp + c];
+        for (int j = 0; j < a.D; ++j) {
+          const float x = xr[j];
+          l = fmaf(x, row[j].x, l);
+          l = fmaf(x * x, row[j].y, l);
+        }
+        const float mn = fmaxf(mrun, l);
+        srun = srun * __expf(mrun - mn) + __expf(l - mn);
+        mrun = mn;
+      }
+      const float mall = warp_max(mrun);
+      const float sall = warp_sum(srun * __expf(mrun - mall));
+      const float lse = mall + __logf(sall);
+      if (lane == 0 && a.frame_lse) a.frame_lse[(int64_t)m * a.total_frames + t] = lse;
+      total += (double)lse;
+    }
+    if (lane == 0) a.scores[p] = a.normalize && t1 > t0 ? total / (double)(t1 - t0) : total;
+  }
+}
+
 }  // namespace tc
+
+// ---- which packs may be scored from their FP16 images
+static std::mutex g_pack_mu;
+static std::unordered_map<const void*, int> g_pack_h;   // -1: not read back yet, 0: a value left FP16's range, 1: usable
+void note_pack(const void* pack) {
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  g_pack_h[pack] = -1;
+}
+static bool pack_h_usable(const void* pack, const PackLayout& L, cudaStream_t st) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("SSP_TC_TF32");   // A/B knob: 1 = the single-pass rung always issues kind::tf32
+    off = e ? atoi(e) : 0;
+  }
+  if (off || !L.off_tile_h) return false;
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  auto it = g_pack_h.find(pack);
+  if (it == g_pack_h.end()) return false;   // a pack this process did not build (copied buffer): TF32 images are always valid
+  if (it->second < 0) {
+    int flag = 1;
+    if (cudaMemcpyAsync(&flag, (const char*)pack + L.off_flag, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return false;
+    it->second = flag ? 0 : 1;
+  }
+  return it->second == 1;
+}
 
 int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, int64_t total_frames, const void* pack,
                     const PackLayout& L, int parts, bool normalize, double* scores, float* frame_lse, cudaStream_t st) {
@@ -376,7 +473,12 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.scores = scores;
   a.frame_lse = frame_lse;
   const int mb = parts == 3 ? 1 : 2, unit = BM * mb;
-  const size_t tile_bytes = (size_t)BN * L.KD * 4;
+  const bool use_h = parts == 1 && pack_h_usable(pack, L, st);
+  if (use_h) {
+    a.tiles = (const float*)((const char*)pack + L.off_tile_h);
+    a.KD = L.KDb();
+  }
+  const size_t tile_bytes = (size_t)BN * a.KD * (use_h ? 2 : 4);
   const size_t smem = (2 + NSTAGE) * tile_bytes + (2 * NSTAGE + 2 * NSLOT + 2) * sizeof(uint64_t) + 16 +
                       2 * mb * BM * sizeof(float2);
   static int num_sms = 0;
@@ -395,8 +497,13 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   }
 #define SSP_TC_LAUNCH(pp, MBv, NP)                                                                                              \
   do {                                                                                                                          \
-    SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    gmm_score_tc_kernel<pp, MBv, NP><<<grid, threads_of(MBv), smem, st>>>(a);                                                  \
+    if (use_h) {                                                                                                                \
+      SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      gmm_score_tc_kernel<pp, MBv, 1, true><<<grid, threads_of(MBv), smem, st>>>(a);                                           \
+    } else {                                                                                                                    \
+      SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      gmm_score_tc_kernel<pp, MBv, NP><<<grid, threads_of(MBv), smem, st>>>(a);                                                \
+    }                                                                                                                           \
   } while (0)
   if (parts == 2) SSP_TC_LAUNCH(kDefaultPolyPairs, 2, 2);
   else if (parts == 3) SSP_TC_LAUNCH(kDefaultPolyPairs, 1, 3);
@@ -410,6 +517,26 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   }
 #undef SSP_TC_LAUNCH
   SSP_LAUNCH_CHECK(parts == 1 ? "gmm_score_tc_kernel" : parts == 2 ? "gmm_score_tc_kernel<2 passes>" : "gmm_score_tc_kernel<3 passes>");
+  if (use_h) {
+    FixArgs f;
+    f.feats = feats;
+    f.offsets = offsets;
+    f.n_utts = n_utts;
+    f.total_frames = total_frames;
+    f.ab = (const float2*)((const char*)pack + L.off_ab);
+    f.cst = (const float*)((const char*)pack + L.off_cst);
+    f.n_models = L.n_models;
+    f.Kp = L.Kp;
+    f.K = L.K;
+    f.D = L.D;
+    f.DP = L.DP;
+    f.normalize = normalize ? 1 : 0;
+    f.scores = scores;
+    f.frame_lse = frame_lse;
+    const int64_t n_pairs = n_utts * L.n_models, want = (n_pairs + 7) / 8, cap = 4 * (int64_t)num_sms;
+    tc_fixup_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(f);
+    SSP_LAUNCH_CHECK("tc_fixup_kernel");
+  }
   return SSP_OK;
 }
 

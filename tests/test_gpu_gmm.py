@@ -399,6 +399,42 @@ def test_shared_variance_fp16_range_is_guarded():
     assert (who == ref.argmax(axis=1)).all()
 
 
+def test_single_pass_rung_runs_from_fp16_images_and_guards_their_range():
+    """precision="tf32" (one pass, 11-bit significands) streams the FP16 images of the pack: same tolerance as the TF32 images
+    it replaces; a frame outside FP16's range is re-scored in FP32 by tc_fixup_kernel, a model set outside it falls back to
+    the TF32 images."""
+    from speech_signal_processing_b200 import _lib
+
+    k, d = 200, 26
+    w, mu, var = synth.synth_ubm(k, d, seed=33)
+    spk = np.concatenate([synth.synth_speaker_means(mu, 3, seed=34, shift=0.3), mu[None]])
+    utts = [synth.sample_gmm(w, spk[i % 3], var, n, seed=320 + i) for i, n in enumerate((298, 64, 130))]
+    want = np.array([[ogmm.score(u, w, m, var) for m in spk] for u in utts])
+    ms = ssp.ModelSet(np.tile(w, (4, 1)), spk, np.tile(var, (4, 1, 1)))
+    feats, offs = ssp.mixture.concat_utterances(utts, ms.device)
+    _lib.load().ssp_reset_launch_count()
+    got = ms.score(feats, offs, precision="tf32")[0].cpu().numpy()
+    assert _lib.launch_log() == {"gmm_score_tc_kernel": 1, "tc_fixup_kernel": 1}
+    np.testing.assert_allclose(got, want, rtol=REL["tf32"], atol=0)
+    wild = [u.copy() for u in utts]
+    wild[1][7, 2] = -900.0
+    want_w = np.array([[ogmm.score(u, w, m, var) for m in spk] for u in wild])
+    f2, o2 = ssp.mixture.concat_utterances(wild, ms.device)
+    got_w = ms.score(f2, o2, precision="tf32")[0].cpu().numpy()
+    assert np.isfinite(got_w).all()
+    np.testing.assert_allclose(got_w[1], want_w[1], rtol=5e-6, atol=0)        # the FP32 fix-up pass
+    np.testing.assert_allclose(got_w[[0, 2]], want_w[[0, 2]], rtol=REL["tf32"], atol=0)
+    tiny = var * 1e-7      # mu / var ~ 1e7: the pack kernel flags it, the TF32 images serve the call
+    ms_t = ssp.ModelSet(np.tile(w, (4, 1)), spk, np.tile(tiny, (4, 1, 1)))
+    near = [spk[0][:50] + 1e-5, spk[3][:70] - 1e-5]
+    f3, o3 = ssp.mixture.concat_utterances(near, ms_t.device)
+    _lib.load().ssp_reset_launch_count()
+    got_t = ms_t.score(f3, o3, precision="tf32")[0].cpu().numpy()
+    assert _lib.launch_log() == {"gmm_score_tc_kernel": 1}
+    want_t = np.array([[ogmm.score(u, w, m, tiny) for m in spk] for u in near])
+    assert (got_t.argmax(axis=1) == want_t.argmax(axis=1)).all()
+
+
 def test_shared_variance_many_units_and_models():
     """More frames than one wave of 256-frame units x more models than accumulator slots; decisions equal FP32."""
     k, d, n_spk = 256, 39, 33
