@@ -134,3 +134,25 @@ def test_host_framing_rule_equals_the_abi_rule(lib):
         assert want[lens > 4096].min() > 0   # the configuration was accepted (0 would mean "rejected")
         # the fused single-pass kernel holds a 3 s utterance of every convention (librosa keeps 128 bands per frame)
         assert lib.ssp_frontend_max_frames(C.byref(cfg)) >= max(300, int(fe.frame_counts([3 * 16000])[0]) if r.name != "librosa" else 100)
+
+
+def test_pack_sizes_follow_the_documented_layouts(lib):
+    """Host-only size queries: the shared-variance pack is [Kp/64 tiles][4 + S images] of 64 x roundup(D + 2, 16) FP16 values
+    + a 128-byte tail and accepts D <= 39 (shared-memory bound of gmm_score_sv_kernel); the general pack grows with the
+    number of models and carries the FP16 images of the single-pass rung."""
+    from speech_signal_processing_b200 import _lib
+
+    def sv(s, k, d):
+        return int(lib.ssp_gmm_shared_pack_bytes(C.byref(_lib.GmmDims(s, k, d))))
+
+    assert sv(1001, 1024, 39) == 16 * (1001 + 4) * 64 * 48 * 2 + 128
+    assert sv(3, 100, 13) == 2 * (3 + 4) * 64 * 16 * 2 + 128        # K padded to 128, D + 2 = 15 -> 16
+    assert sv(3, 64, 26) == 1 * (3 + 4) * 64 * 32 * 2 + 128
+    assert sv(3, 64, 40) == 0 and sv(3, 64, 0) == 0 and sv(0, 64, 13) == 0
+    general = [int(lib.ssp_gmm_pack_bytes(C.byref(_lib.GmmDims(m, 1024, 39)))) for m in (1, 2, 101)]
+    assert 0 < general[0] < general[1] < general[2]
+    per_model = (general[2] - general[1]) / 99.0
+    # per component: E-section (float2 x 40 + cst) + TF32 hi and lo tiles (80 floats each) + BF16 hi and lo images of the
+    # statistics kernels (80 each, sets of <= 1024 models) + FP16 tiles (80 halfs)
+    assert abs(per_model - 1024 * (40 * 8 + 4 + 2 * 80 * 4 + 2 * 80 * 2 + 80 * 2)) < 4096
+    assert int(lib.ssp_gmm_pack_bytes(C.byref(_lib.GmmDims(1, 64, 81)))) == 0
