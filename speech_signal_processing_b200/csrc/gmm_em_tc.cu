@@ -7,7 +7,7 @@
 //     em_plan_kernel   segments are padded to multiples of 64 frames ("blocks"); block -> (segment, first frame, frames)
 //     em_prep_kernel   per block: the tcgen05 shared-memory images of its frames
 //                        Fb  [x, x^2, 1, 1, 0..] as BF16 hi + lo, K-major rows of 128 frames  (logit GEMMs, both passes)
-//                        Xt  the same columns as TF32 hi + lo with the FRAME index contiguous (statistics GEMM)
+//                        Xt  the same columns as FP16 hi + lo with the FRAME index contiguous (statistics GEMM)
 //   per call (one EM iteration / one enrolment):
 //     gmm_em_lse_kernel    logits[frame, comp] for a PAIR of 128-component tiles per CTA, 128 frames per step:
 //                          3 x BF16 (hi.hi + lo.hi + hi.lo, FP32 accumulation in TMEM; emulated on the CPU: per-frame
@@ -18,8 +18,11 @@
 //     gmm_em_stats_kernel  TRANSPOSED logits[comp, frame] (same images, model tile as the M-side operand), 64 frames
 //                          per step, thread == component row: gamma = 2^(L - lse[frame]) is written by tcgen05.st IN
 //                          PLACE over the logits and is the TMEM-side operand of the statistics GEMM
-//                          stats[comp, :] += gamma . Xt (TF32, hi + lo), accumulated in TMEM over all blocks of a
-//                          segment and added to the float64 N / F / S outputs at segment ends.
+//                          stats[comp, :] += gamma . Xt (kind::f16: gamma as FP16 -- the 11-bit significand a TF32 gamma
+//                          had -- scaled by 2^12 so that posteriors down to 1e-11 survive FP16's range, Xt as FP16
+//                          hi + lo; K = 16 frames per MMA: 8 MMAs per step instead of the 16 of the TF32 form),
+//                          accumulated in TMEM over all blocks of a segment and added, unscaled, to the float64
+//                          N / F / S outputs at segment ends.
 //
 // No thread builds an operand any more: the producer warp streams images with cp.async.bulk, one warp issues the MMAs,
 // sixteen warps do the exponentials.  (Round 1 split the frames into hi / lo in every CTA of every pass of every
@@ -27,6 +30,7 @@
 // Blocks never straddle a segment, so one kernel set serves UBM EM (one segment) and batched MAP enrolment (one
 // segment per speaker).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -44,6 +48,7 @@ constexpr int EPI = 512;       // 16 epilogue warps
 constexpr int THREADS = 64 + EPI;
 constexpr int MAX_KD = 80;
 constexpr int NS_L = 3;        // Fb stages of the LSE pass
+constexpr float kGammaScale = 4096.f;   // gamma rides the statistics GEMM as FP16(gamma * 2^12); the merge kernel folds it into lse2
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct Ws {
@@ -51,7 +56,7 @@ struct Ws {
   int KDb;                     // contraction length, a multiple of 16: roundup(2D + 2, 16); also the N of the statistics GEMM
   size_t o_blk_start, o_blk_seg, o_blk_t0, o_blk_nt, o_lse2, o_partial, o_fb, o_xt, bytes;
   size_t img_bytes() const { return (size_t)512 * KDb; }   // Fb image of 128 frames == model tile image of 128 components
-  size_t xt_bytes() const { return (size_t)512 * KDb; }    // Xt image of one 64-frame block (hi + lo)
+  size_t xt_bytes() const { return (size_t)256 * KDb; }    // Xt image of one 64-frame block (FP16 hi + lo)
 };
 static Ws ws_layout(const PackLayout& L, int64_t total_frames, int64_t n_segs) {
   Ws w;
@@ -82,10 +87,10 @@ struct Args {
   int32_t* blk_seg;         // [nb_max] segment of a block, -1: padding
   int64_t* blk_t0;          // [nb_max] first frame
   int32_t* blk_nt;          // [nb_max] frames (1..64; 0: padding)
-  float* lse2;              // [P] per padded frame: log2-likelihood; 3e38 for dead rows
+  float* lse2;              // [P] per padded frame: log2-likelihood - log2(kGammaScale); 3e38 for dead rows
   float2* partial;          // [2 n_tiles][P]
   const unsigned char* fb;  // [nb_max / 2] images: [hi | lo][KDb/8][128 rows][8 bf16]
-  const unsigned char* xt;  // [nb_max] images:     [hi | lo][16][KDb rows][4 fp32]
+  const unsigned char* xt;  // [nb_max] images:     [hi | lo][8][KDb rows][8 half]
   int64_t nb_max, P;
   // model
   const unsigned char* tiles;  // [model][n_tiles] images [hi | lo][KDb/8][128 comps][8 bf16]
@@ -107,6 +112,15 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       :
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
@@ -249,23 +263,23 @@ __global__ void __launch_bounds__(256) em_prep_kernel(const Args a) {
       *reinterpret_cast<uint4*>(img + part_bytes + off) = *reinterpret_cast<const uint4*>(l);
     }
   }
-  // ---- Xt: item = (chunk of 4 frames, column j) -> float4 of hi and of lo
+  // ---- Xt: item = (chunk of 8 frames, column j) -> 16 bytes (8 FP16) of hi and of lo
   {
-    float* img = reinterpret_cast<float*>(const_cast<unsigned char*>(a.xt) + (size_t)b * 512 * KDb);
-    const size_t part_floats = (size_t)16 * KDb * 4;
-    for (int it = tid; it < 16 * KDb; it += 256) {
+    unsigned char* img = const_cast<unsigned char*>(a.xt) + (size_t)b * 256 * KDb;
+    const size_t part_bytes = (size_t)128 * KDb;  // [8][KDb][16 B]
+    for (int it = tid; it < 8 * KDb; it += 256) {
       const int fc = it / KDb, j = it % KDb;
-      float h[4], l[4];
+      __align__(16) __half h[8], l[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = 4 * fc + e;
+      for (int e = 0; e < 8; ++e) {
+        const int r = 8 * fc + e;
         // column 2D + 1 (the second "one" of the logit operand) is dead weight here: N is column 2D
         const float v = (r < nt && j <= 2 * D) ? feat_col(sx + r * D, j, D) : 0.f;
-        h[e] = rna_tf32(v);
-        l[e] = rna_tf32(v - h[e]);
+        h[e] = __float2half_rn(v);
+        l[e] = __float2half_rn(v - __half2float(h[e]));
       }
-      reinterpret_cast<float4*>(img)[it] = make_float4(h[0], h[1], h[2], h[3]);
-      reinterpret_cast<float4*>(img + part_floats)[it] = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<uint4*>(img + (size_t)it * 16) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(img + part_bytes + (size_t)it * 16) = *reinterpret_cast<const uint4*>(l);
     }
   }
 }
@@ -434,7 +448,7 @@ __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
     ll = lse2 * 0.69314718055994530942f;
     a.frame_lse[a.blk_t0[b] + r] = ll;
   }
-  a.lse2[p] = lse2;
+  a.lse2[p] = lse2 < 1.0e38f ? lse2 - 12.f : lse2;   // log2(kGammaScale) = 12
   const float tot = warp_sum(ll);
   if (lane == 0 && nt > 0 && tot != 0.f) atomicAdd(a.out_loglik + a.blk_seg[b], (double)tot);
 }
@@ -460,13 +474,14 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int KDb = KSTEPS * 16;
   const int D = a.D;
-  constexpr uint32_t TB = 512u * (uint32_t)KDb;  // model tile image; also one Xt image
+  constexpr uint32_t TB = 512u * (uint32_t)KDb;  // model tile image
+  constexpr uint32_t XB = 256u * (uint32_t)KDb;  // Xt image of a step (FP16 hi + lo)
   constexpr uint32_t FB = TB >> 1;               // the 64-row half of an Fb image (hi + lo)
   constexpr uint32_t FST = FB + 256u;            // F stage: + 64 lse values
   unsigned char* sB = smem;                      // [2][TB]
   unsigned char* sF = smem + 2 * (size_t)TB;     // [NF][FST]
-  unsigned char* sX = sF + (size_t)NF * FST;     // [NX][TB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)NX * TB);
+  unsigned char* sX = sF + (size_t)NF * FST;     // [NX][XB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)NX * XB);
   uint64_t* b_full = bars;           // model tiles landed
   uint64_t* f_full = bars + 1;       // [NF]
   uint64_t* f_empty = f_full + NF;   // [NF] the statistics GEMMs of the step are complete (its lse values are dead too)
@@ -530,8 +545,8 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
         __syncwarp();
         mbar_wait_relaxed(x_empty + xs, ((k / NX) & 1u) ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(x_full + xs, TB);
-          bulk_g2s(sX + (size_t)xs * TB, a.xt + (size_t)b * TB, TB, x_full + xs);
+          mbar_arrive_expect_tx(x_full + xs, XB);
+          bulk_g2s(sX + (size_t)xs * XB, a.xt + (size_t)b * XB, XB, x_full + xs);
         }
         __syncwarp();
       }
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
       constexpr uint32_t lbo_b = BN * 16u, lbo_f = BLK * 16u, lbo_x = (uint32_t)KDb * 16u;
       constexpr uint32_t ks_b = (2u * lbo_b) >> 4, ks_f = (2u * lbo_f) >> 4, ks_x = (2u * lbo_x) >> 4;
       constexpr uint32_t idesc1 = make_idesc_bf16(BN, BLK);
-      constexpr uint32_t idesc2 = make_idesc_tf32(BN, KDb, 0, 0);
+      constexpr uint32_t idesc2 = make_idesc_f16(BN, KDb);
       const uint32_t sF_u = smem_u32(sF), sX_u = smem_u32(sX);
       const uint64_t bh = make_desc(smem_u32(sB) + (uint32_t)t * TB, lbo_b, sbo), bl = bh + (uint64_t)((TB >> 1) >> 4);
       const uint32_t t_stat = tmem_base + COL_STAT + (uint32_t)(t * KDb);
@@ -563,12 +578,15 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
         }
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t xhi = make_desc(sX_u + xs * TB, lbo_x, sbo), xlo = xhi + (uint64_t)((TB >> 1) >> 4);
+          const uint64_t xhi = make_desc(sX_u + xs * XB, lbo_x, sbo), xlo = xhi + (uint64_t)((XB >> 1) >> 4);
           const uint32_t t_gam = tmem_base + COL_LOGIT + 64u * lb;
+          // K = 16 frames per MMA; the gamma of frames [32 h, 32 h + 32) sits packed in columns [32 h, 32 h + 16) of the buffer
 #pragma unroll
-          for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
+          for (int q = 0; q < BLK / 16; ++q)
+            mma_f16_ts(t_stat, t_gam + 32u * (q >> 1) + 8u * (q & 1), xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
 #pragma unroll
-          for (int q = 0; q < BLK / 8; ++q) mma_tf32_ts(t_stat, t_gam + 8u * q, xlo + (uint64_t)(q * ks_x), idesc2, 1u);
+          for (int q = 0; q < BLK / 16; ++q)
+            mma_f16_ts(t_stat, t_gam + 32u * (q >> 1) + 8u * (q & 1), xlo + (uint64_t)(q * ks_x), idesc2, 1u);
           if (flush) tc_commit(st_done + t);
           tc_commit(f_empty + p % NF);
           tc_commit(x_empty + xs);
@@ -630,15 +648,16 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
         uint32_t r[32];
         tc_ld32_issue(t_log, r);
         tc_ld_wait(r);
-        float gam[32];
+        // gamma * 2^12 (the scale is folded into lse2) as FP16, two frames per column over this thread's own logits
+        uint32_t gam[16];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          gam[4 * q + 0] = rna_tf32(ex2(__uint_as_float(r[4 * q + 0]) - ls[q].x));
-          gam[4 * q + 1] = rna_tf32(ex2(__uint_as_float(r[4 * q + 1]) - ls[q].y));
-          gam[4 * q + 2] = rna_tf32(ex2(__uint_as_float(r[4 * q + 2]) - ls[q].z));
-          gam[4 * q + 3] = rna_tf32(ex2(__uint_as_float(r[4 * q + 3]) - ls[q].w));
+          const __half2 g0 = __floats2half2_rn(ex2(__uint_as_float(r[4 * q + 0]) - ls[q].x), ex2(__uint_as_float(r[4 * q + 1]) - ls[q].y));
+          const __half2 g1 = __floats2half2_rn(ex2(__uint_as_float(r[4 * q + 2]) - ls[q].z), ex2(__uint_as_float(r[4 * q + 3]) - ls[q].w));
+          gam[2 * q] = *reinterpret_cast<const uint32_t*>(&g0);
+          gam[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&g1);
         }
-        tc_st32(t_log, gam);
+        tc_st16u(t_log, gam);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(g_full + lb);
@@ -657,7 +676,7 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int jj = c0 + e;
-                const double v = (double)__uint_as_float(s8[e]);
+                const double v = (double)__uint_as_float(s8[e]) * (1.0 / (double)kGammaScale);
                 if (jj < D) atomicAdd(a.out_f + ((int64_t)seg_cur * a.K + comp) * D + jj, v);
                 else if (jj < 2 * D) atomicAdd(a.out_s + ((int64_t)seg_cur * a.K + comp) * D + (jj - D), v);
                 else if (jj == 2 * D) atomicAdd(a.out_n + (int64_t)seg_cur * a.K + comp, v);
@@ -740,7 +759,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   const int64_t gx_l = min(gx, (nb_lo + 1) / 2), gx_s = min(gx, nb_lo);
   const size_t TB = w.img_bytes();
   const size_t smem_lse = (2 + NS_L) * TB + 16 * sizeof(uint64_t) + 64;
-  const size_t smem_stats = 2 * TB + p3::NF * (TB / 2 + 256) + p3::NX * TB + 24 * sizeof(uint64_t) + 64;
+  const size_t smem_stats = 2 * TB + p3::NF * (TB / 2 + 256) + p3::NX * (TB / 2) + 24 * sizeof(uint64_t) + 64;
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SSP_EM_POLY_PAIRS");  // share of the LSE pass's exponentials on the FMA pipe (pairs of 16)
