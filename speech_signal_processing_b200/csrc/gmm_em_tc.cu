@@ -419,38 +419,56 @@ __global__ void __launch_bounds__(THREADS, 1) gmm_em_lse_kernel(const Args a) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-// partials -> lse2 per padded frame, frame_lse per frame, log-likelihood per segment.  4 blocks per CTA; the partials of
-// a frame are loaded in one batch (independent loads in flight) and merged from registers.
+// partials -> lse2 per padded frame, frame_lse per frame, log-likelihood per segment.  Persistent CTAs walk groups of 4
+// blocks; the partials of a frame are loaded in one batch (independent loads in flight) and merged from registers.  A thread
+// carries the log-likelihood of its frames until the segment changes, so a UBM iteration (one segment) ends in a few
+// thousand double atomics on its address -- one per warp and 32 frames, as before, was 1.1 M serialised L2 atomics at
+// config 3 and most of this kernel's 2.6 ms.
 __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
   const int64_t nb = a.blk_start[a.n_segs];
-  const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int64_t nb2 = (nb + 1) & ~(int64_t)1;
   const int r = threadIdx.x & 63, lane = threadIdx.x & 31;
-  if (b >= ((nb + 1) & ~(int64_t)1)) return;
-  const int nt = a.blk_nt[b];
-  const int64_t p = b * BLK + r;
-  float lse2 = 3.0e38f, ll = 0.f;  // dead rows: gamma = 2^(x - huge) = 0
-  if (r < nt) {
-    const int n_part = 2 * a.n_tiles;
-    float m = -3.0e38f, s = 0.f;
-    for (int y0 = 0; y0 < n_part; y0 += 8) {
-      float2 q[8];
+  double acc = 0.0;
+  int seg_acc = -1;
+  auto flush = [&]() {   // warp-uniform: the 32 lanes of a warp share a block, hence a segment
+    double tot = acc;
 #pragma unroll
-      for (int y = 0; y < 8; ++y) q[y] = y0 + y < n_part ? __ldg(a.partial + (size_t)(y0 + y) * a.P + p) : make_float2(-3.0e38f, 0.f);
-      float mg = m;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && seg_acc >= 0 && tot != 0.0) atomicAdd(a.out_loglik + seg_acc, tot);
+    acc = 0.0;
+  };
+  for (int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6); b < nb2; b += (int64_t)gridDim.x * 4) {
+    const int nt = a.blk_nt[b];
+    const int seg = a.blk_seg[b];
+    const int64_t p = b * BLK + r;
+    float lse2 = 3.0e38f, ll = 0.f;  // dead rows: gamma = 2^(x - huge) = 0
+    if (r < nt) {
+      const int n_part = 2 * a.n_tiles;
+      float m = -3.0e38f, s = 0.f;
+      for (int y0 = 0; y0 < n_part; y0 += 8) {
+        float2 q[8];
 #pragma unroll
-      for (int y = 0; y < 8; ++y) mg = fmaxf(mg, q[y].x);
-      s *= ex2(m - mg);
+        for (int y = 0; y < 8; ++y) q[y] = y0 + y < n_part ? __ldg(a.partial + (size_t)(y0 + y) * a.P + p) : make_float2(-3.0e38f, 0.f);
+        float mg = m;
 #pragma unroll
-      for (int y = 0; y < 8; ++y) s += q[y].y * ex2(q[y].x - mg);
-      m = mg;
+        for (int y = 0; y < 8; ++y) mg = fmaxf(mg, q[y].x);
+        s *= ex2(m - mg);
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += q[y].y * ex2(q[y].x - mg);
+        m = mg;
+      }
+      lse2 = m + lg2(s);
+      ll = lse2 * 0.69314718055994530942f;
+      a.frame_lse[a.blk_t0[b] + r] = ll;
     }
-    lse2 = m + lg2(s);
-    ll = lse2 * 0.69314718055994530942f;
-    a.frame_lse[a.blk_t0[b] + r] = ll;
+    a.lse2[p] = lse2 < 1.0e38f ? lse2 - 12.f : lse2;   // log2(kGammaScale) = 12
+    if (seg != seg_acc) {
+      flush();
+      seg_acc = seg;
+    }
+    acc += (double)ll;
   }
-  a.lse2[p] = lse2 < 1.0e38f ? lse2 - 12.f : lse2;   // log2(kGammaScale) = 12
-  const float tot = warp_sum(ll);
-  if (lane == 0 && nt > 0 && tot != 0.f) atomicAdd(a.out_loglik + a.blk_seg[b], (double)tot);
+  flush();
 }
 
 // ================================================================================================ pass STATS
@@ -776,7 +794,10 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   }
 #undef SSP_EM_LSE
   SSP_LAUNCH_CHECK("gmm_em_lse_kernel");
-  em_merge_kernel<<<(unsigned)((w.nb_max + 3) / 4), 256, 0, st>>>(a);
+  {
+    const int64_t groups = (w.nb_max + 3) / 4, cap = 8 * (int64_t)num_sms;
+    em_merge_kernel<<<(unsigned)(groups < cap ? groups : cap), 256, 0, st>>>(a);
+  }
   SSP_LAUNCH_CHECK("em_merge_kernel");
 #define SSP_EM_STATS(ks)                                                                                                  \
   case ks:                                                                                                                \
