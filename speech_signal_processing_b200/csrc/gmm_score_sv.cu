@@ -724,18 +724,25 @@ static int launch_ks(const Args& a, unsigned grid, bool first, cudaStream_t st) 
 
 // Large model sets are scored in GROUPS whose tile images stay resident in L2 while all frames pass by: one launch per
 // group over the same frames, the per-frame stabilisers of the first launch kept in the workspace.  (Round 1 streamed the
-// whole set -- 197 MB at config 4 -- once per 256-frame unit: 36 GB of DRAM reads per call, 48x the algorithmic bytes.)
-// SSP_SV_GROUP_MB sets the group's footprint (default 24 MB; 0 = one launch over the whole set).
+// whole set -- 197 MB of TF32 images at config 4 -- once per 256-frame unit: 36 GB of DRAM reads per call, 48x the
+// algorithmic bytes.)  SSP_SV_GROUP_MB caps a group's footprint (default 48 MB; 0 = one launch over the whole set); the
+// groups are balanced, so a set just above the cap is not split into a full group and a sliver.  Measured at config 4 with
+// the 99 MB of FP16 images, ms per call / DRAM bytes per call: 24 MB (4 launches) 673 / 2.26 GB, 48 MB (2 launches) 671,
+// one launch 668 / 8.44 GB -- the 126 MB L2 does not hold a 99 MB set that every SM streams, and 0.5 % of time is not
+// worth 13x the algorithmic traffic.
 static int sv_group_models(const SvLayout& L) {
   static double mb = -1.0;
   if (mb < 0.0) {
     const char* e = getenv("SSP_SV_GROUP_MB");
-    mb = e ? atof(e) : 24.0;
+    mb = e ? atof(e) : 48.0;
   }
   if (mb <= 0.0) return L.n_models;
   const double per_model = (double)L.Kp * L.KS * 2.0;  // FP16 images
-  int g = (int)(mb * 1048576.0 / per_model) / sv::CHUNK * sv::CHUNK;
-  if (g < sv::CHUNK) g = sv::CHUNK;
+  int cap = (int)(mb * 1048576.0 / per_model) / sv::CHUNK * sv::CHUNK;
+  if (cap < sv::CHUNK) cap = sv::CHUNK;
+  if (cap >= L.n_models) return L.n_models;
+  const int n_groups = (L.n_models + cap - 1) / cap;
+  int g = ((L.n_models + n_groups - 1) / n_groups + sv::CHUNK - 1) / sv::CHUNK * sv::CHUNK;
   return g >= L.n_models ? L.n_models : g;
 }
 
