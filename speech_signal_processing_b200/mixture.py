@@ -99,7 +99,8 @@ class ModelSet:
     @_lib.on_device
     def score(self, feats, frame_offsets, precision="auto", want_frame_lse=False):
         """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None).
-        ``precision``: "fp32" (CUDA cores), "tf32" / "tf32x2" / "tf32x3" (tcgen05, 1 / 2 / 3 TF32 passes) or "auto"
+        ``precision``: "fp32" (CUDA cores), "tf32" / "tf32x2" / "tf32x3" (tcgen05, 1 / 2 / 3 passes of 11-bit operands; the
+        single pass streams FP16 images of the models) or "auto"
         (:func:`resolve_precision`)."""
         torch = _lib.require_cuda()
         frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
@@ -175,11 +176,12 @@ class SharedModelSet:
     """``n_models`` diagonal GMMs that share ONE weight vector and ONE variance matrix and differ in their means --
     what mean-only MAP enrolment from a UBM yields (:func:`~speech_signal_processing_b200.ubm.map_adapt` with
     ``adapt=("means",)``).  Scored by the shared-variance tensor kernel (``ssp_gmm_score_shared``): the part of the
-    log-likelihood common to all models -- the logit of the reference member ``ref_model`` (the UBM), with the model
-    operand split in two TF32 pieces -- is evaluated once per frame block; the per-model contraction is D + 2 long
-    instead of 2D + 2 and acts on ``means[s] - means[ref_model]``, so TF32 rounding scales with the distance from the
-    reference and cancels in log-likelihood ratios against it.  Results equal :class:`ModelSet`
-    ``.score(precision="tf32")`` on the expanded set to TF32 rounding or better."""
+    log-likelihood common to all models -- the logit of the reference member ``ref_model`` (the UBM), evaluated to FP32
+    grade in three FP16 passes -- is computed once per frame block; the per-model contraction is D + 2 long instead of
+    2D + 2 and acts on ``means[s] - means[ref_model]`` in FP16 operands (the 11-bit significand of TF32), so its rounding
+    scales with the distance from the reference and cancels in log-likelihood ratios against it.  Results equal
+    :class:`ModelSet` ``.score(precision="tf32")`` on the expanded set to that rung's rounding or better.  Needs
+    D <= 39 and parameters inside FP16's range (``NotImplementedError`` otherwise: use :meth:`expand` / :class:`ModelSet`)."""
 
     def __init__(self, weights, variances, means, ref_model=-1, device=None):
         torch = _lib.require_cuda()
@@ -224,7 +226,7 @@ class SharedModelSet:
         """(scores (n_utts, n_models) cuda float64, frame_lse (n_models, total) cuda float32 | None)."""
         torch = _lib.require_cuda()
         if precision not in ("tf32", "auto"):
-            raise ValueError("the shared-variance kernel computes in single-pass TF32; expand() to a ModelSet for the "
+            raise ValueError("the shared-variance kernel has one precision rung (11-bit operands, FP32-grade common part); expand() to a ModelSet for the "
                              "other precisions")
         frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
         n_utts, total = len(frame_offsets) - 1, int(frame_offsets[-1])
