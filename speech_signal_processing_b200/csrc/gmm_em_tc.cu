@@ -478,7 +478,14 @@ __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
 // GEMM2(k - 1) (statistics); both rings are released by the completion of GEMM2(k), so the loads of step k + 1 are
 // issued two GEMMs before they are needed.
 namespace p3 {
-constexpr int NF = 3, NX = 2;
+#ifndef SSP_EM_NF
+#define SSP_EM_NF 3
+#define SSP_EM_NX 4
+#endif
+// ring depths, measured at config 3 (ms per statistics call, three runs each on one box; single runs scatter by up to 5 ms):
+// (NF, NX) = (3, 2) 21.6 / 21.6 / 22.6, (4, 3) 21.5 / 21.3 / 21.1, (3, 4) 21.0 / 20.8 -- the FP16 Xt images freed the shared
+// memory for the deeper Xt ring
+constexpr int NF = SSP_EM_NF, NX = SSP_EM_NX;
 constexpr uint32_t COL_LOGIT = 0;    // + 64 * (2 * tile + buffer)
 constexpr uint32_t COL_STAT = 256;   // + KDb * tile
 constexpr int CTRL = 96;             // warp 0: producer; warps 1, 2: MMA issuers of tile 0 / tile 1 (a step's MMAs are 32-40
@@ -777,7 +784,7 @@ int launch_stats_tc(const float* feats, const int64_t* seg_offsets, int64_t n_se
   const int64_t gx_l = min(gx, (nb_lo + 1) / 2), gx_s = min(gx, nb_lo);
   const size_t TB = w.img_bytes();
   const size_t smem_lse = (2 + NS_L) * TB + 16 * sizeof(uint64_t) + 64;
-  const size_t smem_stats = 2 * TB + p3::NF * (TB / 2 + 256) + p3::NX * (TB / 2) + 24 * sizeof(uint64_t) + 64;
+  const size_t smem_stats = 2 * TB + p3::NF * (TB / 2 + 256) + p3::NX * (TB / 2) + (13 + 2 * p3::NF + 2 * p3::NX) * sizeof(uint64_t) + 64;
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SSP_EM_POLY_PAIRS");  // share of the LSE pass's exponentials on the FMA pipe (pairs of 16)
