@@ -779,7 +779,7 @@ def run_b200(a):
     flop_per_launch = 4.0 * D * K * (frames / a.steps) * n_models
     k_ms = float(np.mean(score_ms))
     achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
-    general_f16 = (not shared) and a.precision == "tf32" and os.environ.get("SSP_TC_TF32", "0") != "1"
+    general_f16 = (not shared) and a.precision != "fp32" and os.environ.get("SSP_TC_TF32", "0") != "1"
     if shared or general_f16:
         # kind::f16 MMAs (FP16 operands, FP32 accumulation): that pipe's measured dense rate
         peak, bound = peaks["bf16_tflops_sustained"], "tensor"
@@ -833,8 +833,10 @@ def run_b200(a):
         "metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("f16 operands (11-bit significand, as tf32) / f32 accumulate; common part 3-pass f32 grade" if shared else
-                  {"tf32": "f16 operands (11-bit significand, as tf32) / f32 accumulate" if general_f16 else "tf32", "tf32x2": "tf32 (2 passes)",
-                   "tf32x3": "tf32 (3 passes)", "fp32": "f32"}[a.precision]), "data": "synthetic",
+                  {"tf32": "f16 operands (11-bit significand, as tf32) / f32 accumulate" if general_f16 else "tf32",
+                   "tf32x2": "f16 operands, model operand as hi + lo (2 passes)" if general_f16 else "tf32 (2 passes)",
+                   "tf32x3": "f16 hi + lo pieces of both operands (3 passes, f32 grade)" if general_f16 else "tf32 (3 passes)",
+                   "fp32": "f32"}[a.precision]), "data": "synthetic",
         "config": {"workload": workload_name(a), "parallelism": f"utterances sharded x{world}, models replicated",
                    "l2": "inputs per step (0.96 GB PCM, 0.1-0.33 GB model tiles) exceed the 126 MB L2", "scorer": a.scorer,
                    "audio": "synth.synth_pcm_torch (counter-based; the CPU arm and the oracle check regenerate the same utterances)",

@@ -195,14 +195,14 @@ int ssp_gmm_pack_models(const double* weights, const double* means, const double
 
 #define SSP_PREC_FP32 0 /* CUDA-core FP32 FMA, ~1e-7 relative                              */
 #define SSP_PREC_TF32 1 /* one tcgen05 pass, operands rounded to an 11-bit significand, FP32 accumulate in TMEM:
-                           1e-4 relative on the utterance score at K >= 512 components and ~300 frames.  Issued as
-                           kind::f16 from FP16 images of the pack (TF32's significand, K = 16 per MMA, half the bytes)
-                           when every model value fits FP16's range, else as kind::tf32; a frame outside that range is
-                           re-scored in FP32 (tc_fixup_kernel)                                                  */
+                           1e-4 relative on the utterance score at K >= 512 components and ~300 frames            */
 #define SSP_PREC_TF32X2 2 /* two passes, A.B_hi + A.B_lo: the model operand exact to 2^-22 (its rounding is the
                              systematic part of the one-pass error), frames still rounded                       */
-#define SSP_PREC_TF32X3 3 /* three passes (3xTF32), A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: FP32-grade, ~5e-7 relative;
+#define SSP_PREC_TF32X3 3 /* three passes, A_hi.B_hi + A_hi.B_lo + A_lo.B_hi: FP32-grade, ~5e-7 relative;
                              what LLRs of small models / short utterances need (abs 1e-3)                       */
+/* The three tensor rungs are issued as kind::f16 from FP16 images of the pack (FP16 has TF32's 11-bit significand, one
+ * MMA covers K = 16 instead of 8, tiles are half the bytes) when every model value fits FP16's range, else as kind::tf32
+ * from the TF32 images; a frame outside that range (|x| > 255) is re-scored in FP32 by tc_fixup_kernel. */
 
 /*
  * scores[u, m] = mean over the frames of utterance u of log sum_c w_c N(x_t; mu_mc, var_mc)

@@ -54,7 +54,7 @@ struct PackLayout {
   int Kp;  // K rounded up to kTileN (padded components have cst = -1e30, zero rows)
   int DP;  // D padded for the CUDA-core kernels: 16, 32, 40, 64 or 80
   int KD;  // contraction length of the tensor kernel: roundup(2D + 2, 8)
-  size_t off_ab, off_cst, off_tile, off_tile_lo, off_tile_bf, off_tile_h, off_flag, bytes;  // off_tile_bf == 0: no BF16 images (n_models > 1)
+  size_t off_ab, off_cst, off_tile, off_tile_lo, off_tile_bf, off_tile_h, off_tile_hl, off_flag, bytes;  // off_tile_bf == 0: no BF16 images (n_models > 1)
   int KDb() const { return (2 * D + 2 + 15) / 16 * 16; }  // contraction length of the BF16 / FP16 images (multiple of 16)
   size_t tile_floats() const { return (size_t)kTileN * KD; }
 };
@@ -141,13 +141,16 @@ inline bool make_layout(const ssp_gmm_dims* dims, PackLayout* L) {
     L->off_tile_bf = o;
     o = up(o + (size_t)L->n_models * (L->Kp / kTileN) * 512 * L->KDb());
   }
-  // FP16 images of the same rows for the single-pass scoring rung (kind::f16: K = 16 per MMA, half the bytes; an FP16
-  // significand has TF32's 11 bits): [model][Kp/128 tiles][KDb/8][128][8 half], + a flag the pack kernel raises when a
-  // value leaves FP16's range (ssp_gmm_score then streams the TF32 images instead)
+  // FP16 images of the same rows for the tensor scoring rungs (kind::f16: K = 16 per MMA, half the bytes; an FP16
+  // significand has TF32's 11 bits): [model][Kp/128 tiles][KDb/8][128][8 half], hi and residual, + a flag the pack kernel
+  // raises when a value leaves FP16's range (ssp_gmm_score then streams the TF32 images instead)
   L->off_tile_h = 0;
+  L->off_tile_hl = 0;
   L->off_flag = 0;
   if (2 * L->D + 2 <= 80) {
     L->off_tile_h = o;
+    o = up(o + (size_t)L->n_models * L->Kp * L->KDb() * 2);
+    L->off_tile_hl = o;   // residual FP16 images (hi + lo exact to ~2^-22): the 2- and 3-pass rungs
     o = up(o + (size_t)L->n_models * L->Kp * L->KDb() * 2);
     L->off_flag = o;
     o = up(o + 128);

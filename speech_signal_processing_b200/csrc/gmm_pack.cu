@@ -20,7 +20,7 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
                                 const double* __restrict__ var, int n_models, int K, int Kp, int D, int DP, int KD,
                                 float2* __restrict__ ab, float* __restrict__ cst, float* __restrict__ tiles,
                                 float* __restrict__ tiles_lo, __nv_bfloat16* __restrict__ tiles_bf, int KDb,
-                                __half* __restrict__ tiles_h, int* __restrict__ h_overflow) {
+                                __half* __restrict__ tiles_h, __half* __restrict__ tiles_hl, int* __restrict__ h_overflow) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_models * Kp) return;
   int m = (int)(idx / Kp), c = (int)(idx % Kp);
@@ -47,17 +47,23 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   // FP16 image of the tile (single-pass scoring rung): element (j, n) at ((j/8)*128 + n)*8 + j%8
   __half* th = tiles_h ? tiles_h + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KDb : nullptr;
   bool h_bad = false;
-  auto h_put = [&](int j, double v) {
+  __half* thl = tiles_hl ? tiles_hl + ((int64_t)m * (Kp / kTileN) + c / kTileN) * (int64_t)kTileN * KDb : nullptr;
+  auto h_put = [&](int j, double v, bool with_residual = true) {   // hi image: fp16(v); residual image: fp16(v - hi); returns hi
     const __half h = __float2half_rn((float)v);
     if (!(fabs((double)__half2float(h)) <= 65504.0)) h_bad = true;
-    th[(((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7)] = h;
+    const int64_t at = (((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7);
+    th[at] = h;
+    if (thl && with_residual) thl[at] = __float2half_rn((float)(v - (double)__half2float(h)));
     return (double)__half2float(h);
   };
   if (th)
-    for (int j = 0; j < KDb; ++j) th[(((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7)] = __float2half_rn(0.f);
+    for (int j = 0; j < KDb; ++j) {
+      th[(((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7)] = __float2half_rn(0.f);
+      if (thl) thl[(((int64_t)(j >> 3)) * kTileN + n) * 8 + (j & 7)] = __float2half_rn(0.f);
+    }
   const double LOG2E = 1.4426950408889634074;
   if (c >= K) {
-    if (th) h_put(2 * D, -60000.0);  // 2^-60000 == 0: padded components never contribute
+    if (th) h_put(2 * D, -60000.0, false);  // 2^-60000 == 0: padded components never contribute
     if (tbf) bf_at(0, 2 * D) = __float2bfloat16_rn(-1e30f);
     for (int d = 0; d < DP; ++d) ab_row[d] = make_float2(0.f, 0.f);
     cst[idx] = -1e30f;
@@ -109,8 +115,11 @@ __global__ void gmm_pack_kernel(const double* __restrict__ w, const double* __re
   }
   if (th) {  // two FP16 pieces of the constant against the two "one" columns
     const double ch = c2 > -60000.0 ? c2 : -60000.0;   // (zero-weight components)
-    const double got = h_put(2 * D, ch);
-    h_put(2 * D + 1, ch - got);
+    // the constant as three FP16 pieces: two in the hi image (so that the single-pass rung has it to ~2^-22), the third in
+    // the residual image
+    const double c1 = h_put(2 * D, ch, false);
+    const double c2 = h_put(2 * D + 1, ch - c1, false);
+    if (thl) thl[(((int64_t)((2 * D) >> 3)) * kTileN + n) * 8 + ((2 * D) & 7)] = __float2half_rn((float)(ch - c1 - c2));
     if (h_bad) *h_overflow = 1;
   }
   if (tbf) {  // three BF16 pieces of the constant (24 bits) against the two "one" columns of the frame operand
@@ -135,6 +144,7 @@ int launch_pack(const double* w, const double* mu, const double* var, const Pack
                                                        L.off_tile_lo ? (float*)(base + L.off_tile_lo) : nullptr,
                                                        L.off_tile_bf ? (__nv_bfloat16*)(base + L.off_tile_bf) : nullptr, L.KDb(),
                                                        L.off_tile_h ? (__half*)(base + L.off_tile_h) : nullptr,
+                                                       L.off_tile_hl ? (__half*)(base + L.off_tile_hl) : nullptr,
                                                        L.off_flag ? (int*)(base + L.off_flag) : nullptr);
   note_pack(pack);
   SSP_LAUNCH_CHECK("gmm_pack_kernel");

@@ -133,12 +133,11 @@ struct Args {
   float* frame_lse;
 };
 
-// kH: the single-pass rung from FP16 operands (kind::f16, K = 16 per MMA: half the MMA instructions, half the bytes of a model
-// tile and of the frame operand; an FP16 significand has TF32's 11 bits).  a.KD is then the FP16 contraction length.
+// kH: FP16 operands (kind::f16, K = 16 per MMA: half the MMA instructions, half the bytes of a model tile and of the frame
+// operand; an FP16 significand has TF32's 11 bits, so every rung keeps its error).  a.KD is then the FP16 contraction length.
 template <int kPolyPairs, int MB, int NPARTS, bool kH = false>
 __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const Args a) {
   static_assert(NPARTS >= 1 && NPARTS <= 3 && (MB == 1 || MB == 2) && (NPARTS < 3 || MB == 1), "see the rung table");
-  static_assert(!kH || NPARTS == 1, "FP16 operands serve the single-pass rung");
   constexpr uint32_t ELT = kH ? 2u : 4u;
   constexpr int UNIT = BM * MB, EPI_WARPS = 8 * MB;
   constexpr int A_IMAGES = MB * (NPARTS == 3 ? 2 : 1);  // hi images of every row block, then the lo images
@@ -232,17 +231,16 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
           const uint32_t d_tmem = tmem_base + slot * BN;
           const uint64_t ad0 = a_desc0 + (uint64_t)(mb * tile_units), al0 = a_desc0 + (uint64_t)((MB + mb) * tile_units);
           if (elect_one()) {
-            if (kH) {
-              mma_f16_ss(d_tmem, ad0, bd0, idesc, 0u);
-              for (int k = 1; k < ksteps; ++k) mma_f16_ss(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), idesc, 1u);
-            } else {
-            tc_mma_tf32(d_tmem, ad0, bd0, kIdesc, 0u);
-            for (int k = 1; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), kIdesc, 1u);
-            }
+            auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+              if (kH) mma_f16_ss(d_tmem, ad, bd, idesc, acc);
+              else tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
+            };
+            mma(ad0, bd0, 0u);
+            for (int k = 1; k < ksteps; ++k) mma(ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), 1u);
             if (NPARTS >= 2)
-              for (int k = 0; k < ksteps; ++k) tc_mma_tf32(d_tmem, ad0 + (uint64_t)(k * kstep), bl0 + (uint64_t)(k * kstep), kIdesc, 1u);
+              for (int k = 0; k < ksteps; ++k) mma(ad0 + (uint64_t)(k * kstep), bl0 + (uint64_t)(k * kstep), 1u);
             if (NPARTS == 3)
-              for (int k = 0; k < ksteps; ++k) tc_mma_tf32(d_tmem, al0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), kIdesc, 1u);
+              for (int k = 0; k < ksteps; ++k) mma(al0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), 1u);
             tc_commit(t_full + slot);
           }
           __syncwarp();
@@ -285,7 +283,9 @@ __global__ void __launch_bounds__(threads_of(MB), 1) gmm_score_tc_kernel(const A
           else if (j < 2 * a.D) { float x = live ? xr[j - a.D] : 0.f; v = x * x; }
           else if (j < 2 * a.D + 2) v = 1.f;
           if (kH) {   // a frame outside FP16's range gives inf -> NaN scores for its utterance; see launch_score_tc
-            dst_h[(size_t)(j >> 3) * (BM * 8) + (j & 7)] = __float2half_rn(v);
+            const __half h = __float2half_rn(v);
+            dst_h[(size_t)(j >> 3) * (BM * 8) + (j & 7)] = h;
+            if (NPARTS == 3) dst_h[(size_t)MB * tile_floats + (size_t)(j >> 3) * (BM * 8) + (j & 7)] = __float2half_rn(v - __half2float(h));
             continue;
           }
           const float hi = rna_tf32(v);
@@ -473,9 +473,10 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
   a.scores = scores;
   a.frame_lse = frame_lse;
   const int mb = parts == 3 ? 1 : 2, unit = BM * mb;
-  const bool use_h = parts == 1 && pack_h_usable(pack, L, st);
+  const bool use_h = pack_h_usable(pack, L, st);
   if (use_h) {
     a.tiles = (const float*)((const char*)pack + L.off_tile_h);
+    a.tiles_lo = (const float*)((const char*)pack + L.off_tile_hl);
     a.KD = L.KDb();
   }
   const size_t tile_bytes = (size_t)BN * a.KD * (use_h ? 2 : 4);
@@ -498,8 +499,8 @@ int launch_score_tc(const float* feats, const int64_t* offsets, int64_t n_utts, 
 #define SSP_TC_LAUNCH(pp, MBv, NP)                                                                                              \
   do {                                                                                                                          \
     if (use_h) {                                                                                                                \
-      SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      gmm_score_tc_kernel<pp, MBv, 1, true><<<grid, threads_of(MBv), smem, st>>>(a);                                           \
+      SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      gmm_score_tc_kernel<pp, MBv, NP, true><<<grid, threads_of(MBv), smem, st>>>(a);                                          \
     } else {                                                                                                                    \
       SSP_CUDA_OK(cudaFuncSetAttribute(gmm_score_tc_kernel<pp, MBv, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       gmm_score_tc_kernel<pp, MBv, NP><<<grid, threads_of(MBv), smem, st>>>(a);                                                \

@@ -153,6 +153,6 @@ def test_pack_sizes_follow_the_documented_layouts(lib):
     assert 0 < general[0] < general[1] < general[2]
     per_model = (general[2] - general[1]) / 99.0
     # per component: E-section (float2 x 40 + cst) + TF32 hi and lo tiles (80 floats each) + BF16 hi and lo images of the
-    # statistics kernels (80 each, sets of <= 1024 models) + FP16 tiles (80 halfs)
-    assert abs(per_model - 1024 * (40 * 8 + 4 + 2 * 80 * 4 + 2 * 80 * 2 + 80 * 2)) < 4096
+    # statistics kernels (80 each, sets of <= 1024 models) + FP16 hi and lo tiles (80 halfs each)
+    assert abs(per_model - 1024 * (40 * 8 + 4 + 2 * 80 * 4 + 2 * 80 * 2 + 2 * 80 * 2)) < 4096
     assert int(lib.ssp_gmm_pack_bytes(C.byref(_lib.GmmDims(1, 64, 81)))) == 0

@@ -504,7 +504,7 @@ def test_identify_routes_shared_base_model_lists_to_the_shared_variance_kernel()
     # default precision at K = 64: the 3-pass general tensor kernel for speakers and UBM, LLRs at the survey's bar
     _lib.load().ssp_reset_launch_count()
     pred3, who3 = ssp.identify(tests, models, ubm)
-    assert _lib.launch_log() == {"gmm_pack_kernel": 2, "gmm_score_tc_kernel<3 passes>": 2}
+    assert _lib.launch_log() == {"gmm_pack_kernel": 2, "gmm_score_tc_kernel<3 passes>": 2, "tc_fixup_kernel": 2}   # (FP16 pieces + range net)
     np.testing.assert_allclose(pred3, ref, rtol=0, atol=LLR_ATOL)
     assert (who3 == who_ref).all()
     # a UBM handed over as a ModelSet: pred is still the LLR, whichever kernel is selected (speaker score - UBM score)
