@@ -389,3 +389,56 @@ def test_load_data_walks_the_tree_like_the_reference(tmp_path, capsys):
     rx3, ry3, _ = reference_walk()
     assert y3 == ry3 and all(np.array_equal(a, b) for a, b in zip(x3, rx3))
     ubm.label_encoder.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# arithmetic of the FP16-operand scoring kernels, emulated in numpy (no GPU): why the shared-variance kernel stores speakers as
+# differences from the reference and evaluates the common part in three FP16 passes
+# ------------------------------------------------------------------------------------------------
+def test_fp16_operand_scheme_error_budget():
+    from speech_signal_processing_b200 import synth
+
+    rs = np.random.RandomState(7)
+    k, d, t = 256, 39, 200
+    w, mu, var = synth.synth_ubm(k, d, seed=5)
+    spk = synth.synth_speaker_means(mu, 1, seed=6, shift=0.25)[0]
+    x = synth.sample_gmm(w, mu, var, t, seed=8)
+    log2e = 1.4426950408889634
+
+    def h(a):      # round to FP16 (11-bit significand), keep float64 for the FP32-or-better accumulation of the tensor core
+        return np.asarray(a, dtype=np.float16).astype(np.float64)
+
+    def logits64(m):  # (t, k) in log2 units, float64
+        p = 1.0 / var
+        c = np.log(w) - 0.5 * (d * np.log(2 * np.pi) + (m * m * p).sum(1)) + 0.5 * np.log(p).sum(1)
+        return ((x * x) @ (-0.5 * p).T + x @ (m * p).T + c) * log2e
+
+    # ---- common part: A = [x^2, x], B = [-1/(2 var), mu_ref / var]; one pass vs three passes (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo)
+    a = np.concatenate([x * x, x], axis=1)
+    b = np.concatenate([-0.5 / var, mu / var], axis=1) * log2e
+    exact = a @ b.T
+    a_hi, b_hi = h(a), h(b)
+    a_lo, b_lo = h(a - a_hi), h(b - b_hi)
+    one = a_hi @ b_hi.T
+    three = one + a_lo @ b_hi.T + a_hi @ b_lo.T
+    err1, err3 = np.abs(one - exact).max(), np.abs(three - exact).max()
+    assert err1 > 5e-3            # an 11-bit pass alone moves a logit by ~1e-2: too much for posteriors or LLRs of small models
+    assert err3 < 3e-7 * np.abs(exact).max()   # the three-pass form is FP32 grade (what is left is a_lo . b_lo ~ 2^-22): 4e-5 on |logit| <= 434
+    # ---- per-speaker part: rounding (mu_s - mu_ref) / var instead of mu_s / var
+    full = h(x) @ h(spk / var * log2e).T
+    diff = h(x) @ h((spk - mu) / var * log2e).T
+    err_full = np.abs(full - x @ (spk / var * log2e).T).max()
+    err_diff = np.abs(diff - x @ ((spk - mu) / var * log2e).T).max()
+    assert err_diff < 0.35 * err_full   # MAP-adapted means sit close to the UBM's: the same 11 bits cost several times less
+    # ---- and the log-likelihood ratio of an utterance: common part exact enough to cancel, differences in one FP16 pass
+    ck = (-0.5 * ((spk * spk - mu * mu) / var).sum(1)) * log2e
+    l_ref = logits64(mu)
+    l_spk_kernel = three + (np.log(w) - 0.5 * (d * np.log(2 * np.pi) + (mu * mu / var).sum(1)) - 0.5 * np.log(var).sum(1)) * log2e + diff + ck
+
+    def lse2(l):
+        m = l.max(1, keepdims=True)
+        return (m[:, 0] + np.log2(np.exp2(l - m).sum(1)))
+
+    llr_exact = (lse2(logits64(spk)) - lse2(l_ref)).mean() / log2e
+    llr_kernel = (lse2(l_spk_kernel) - lse2(l_ref)).mean() / log2e
+    assert abs(llr_kernel - llr_exact) < 1e-3   # LLR within 1e-3 absolute
