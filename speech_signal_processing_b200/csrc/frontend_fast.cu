@@ -26,6 +26,11 @@
 
 namespace ssp {
 
+#ifndef SSP_FE_MIN_CTAS
+#define SSP_FE_MIN_CTAS 2  // CTAs per SM the register allocation aims at.  3 (<= 85 registers: 80 + 292 bytes of spills, and no
+                           // materialised deltas to fit the shared memory) measured 108.6 ms at config 2 against 33.2 ms
+#endif
+
 namespace ff {
 constexpr int W = 8;          // warps per CTA == frames per batch
 constexpr int NH = 256;       // complex FFT length
@@ -81,7 +86,7 @@ __host__ __device__ inline size_t carve_floats(const ssp_frontend_cfg& c, int ma
 constexpr int SK_FL = 400, SK_SH = 160, SK_NF = 24, SK_NC = 13;
 
 template <typename PcmT, bool kSk>
-__global__ void __launch_bounds__(256, 2) frontend512_kernel(const FrontendArgs a, const int flags, const int64_t n_utts) {
+__global__ void __launch_bounds__(256, SSP_FE_MIN_CTAS) frontend512_kernel(const FrontendArgs a, const int flags, const int64_t n_utts) {
   const int materialize = flags & 1;  // bit 1: never take the direct-load path (A/B knob SSP_FE_STAGED)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ssp_frontend_cfg& cfg = a.cfg;
