@@ -478,6 +478,11 @@ __global__ void __launch_bounds__(256) em_merge_kernel(const Args a) {
 // GEMM2(k - 1) (statistics); both rings are released by the completion of GEMM2(k), so the loads of step k + 1 are
 // issued two GEMMs before they are needed.
 namespace p3 {
+#ifndef SSP_EM_XT_LO
+#define SSP_EM_XT_LO 1  // 1: the statistics GEMM also multiplies the residual (lo) FP16 piece of the frames.  0 (A/B builds) saves 4 of
+                        // 23 MMAs per step (19.7 vs 21.0 ms per call at config 3) but the 11-bit x and x^2 cancel in S/N - mean^2:
+                        // variances off by up to 60 % in test_em_trajectory_matches_sklearn
+#endif
 #ifndef SSP_EM_NF
 #define SSP_EM_NF 3
 #define SSP_EM_NX 4
@@ -609,9 +614,11 @@ __global__ void __launch_bounds__(p3::THREADS_S, 1) gmm_em_stats_kernel(const Ar
 #pragma unroll
           for (int q = 0; q < BLK / 16; ++q)
             mma_f16_ts(t_stat, t_gam + 32u * (q >> 1) + 8u * (q & 1), xhi + (uint64_t)(q * ks_x), idesc2, (first && q == 0) ? 0u : 1u);
+#if SSP_EM_XT_LO
 #pragma unroll
           for (int q = 0; q < BLK / 16; ++q)
             mma_f16_ts(t_stat, t_gam + 32u * (q >> 1) + 8u * (q & 1), xlo + (uint64_t)(q * ks_x), idesc2, 1u);
+#endif
           if (flush) tc_commit(st_done + t);
           tc_commit(f_empty + p % NF);
           tc_commit(x_empty + xs);
